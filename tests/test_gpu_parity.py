@@ -1,0 +1,178 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed
+outputs of the reference script.  Bit-exact: everything on this path is integer / byte work."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import c_oracle, pe_oracle
+from vstrains_b200 import pe_inference, synth
+from vstrains_b200._lib import VspeError
+
+pytestmark = pytest.mark.gpu
+
+
+def _info(ids, mat, tmp_path, name):
+    path = str(tmp_path / name)
+    pe_inference.write_info(path, ids, mat)
+    with open(path, "rb") as f:
+        return f.read()
+
+
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_golden_fixtures_bit_exact(golden, tmp_path, force_generic):
+    if golden.status != 0:
+        with pytest.raises(VspeError) as ei:
+            pe_inference.pe_inference(golden.gfa, golden.fwd, golden.rve, golden.k)
+        assert ei.value.code == -2
+        return
+    ids, node, short, stats = pe_inference.pe_inference(golden.gfa, golden.fwd, golden.rve, golden.k,
+                                                        options={"force_generic": force_generic})
+    assert _info(ids, node, tmp_path, "pe_info") == golden.pe_info
+    assert _info(ids, short, tmp_path, "st_info") == golden.st_info
+    _, _, ostats, _ = pe_oracle.run_bytes(golden.gfa, golden.fwd, golden.rve, golden.k)
+    for k, v in ostats.items():
+        assert stats[k] == v
+
+
+def test_cli_drop_in_writes_identical_files(golden, tmp_path):
+    for name, data in (("g.gfa", golden.gfa), ("f.fq", golden.fwd), ("r.fq", golden.rve)):
+        (tmp_path / name).write_bytes(data)
+    out = tmp_path / "aln"
+    out.mkdir()
+    (out / "stale").write_text("x")            # the script owns DIR: rm -rf then mkdir
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "utils", "VStrains_PE_Inference.py"),
+                        "-g", str(tmp_path / "g.gfa"), "-o", str(out) + "/", "-f", str(tmp_path / "f.fq"),
+                        "-r", str(tmp_path / "r.fq"), "-k", str(golden.k)], capture_output=True)
+    if golden.status != 0:
+        assert p.returncode != 0
+        return
+    assert p.returncode == 0, p.stderr.decode()
+    assert sorted(os.listdir(out)) == ["pe_info", "st_info"]
+    assert (out / "pe_info").read_bytes() == golden.pe_info
+    assert (out / "st_info").read_bytes() == golden.st_info
+    assert b"Paired-End Information Alignment" in p.stdout
+
+
+def test_record_split_matches_universal_newlines(golden):
+    with pe_inference.PEIndex([b"ACGTACGTAC"], 3) as ix:
+        for fq in (golden.fwd, golden.rve):
+            n_lines, start, length = ix.split_records(fq)
+            lines = pe_oracle.split_lines(fq)
+            assert n_lines == len(lines)
+            assert len(start) == len(lines) // 4
+            text = fq.decode()
+            for r in range(len(start)):
+                seq = lines[4 * r + 1][:-1]
+                assert text[int(start[r]):int(start[r]) + int(length[r])] == seq
+
+
+def test_record_split_edge_cases():
+    cases = [b"", b"\n", b"\r", b"\r\n", b"a", b"a\nb\nc\nd", b"a\nb\nc\nd\n", b"\n\n\n\n\n\n\n\n",
+             b"@h\r\nAC\r\n+\r\nII\r\n@h\rGT\r+\rII\r", b"@h\nACGT\r\r\n+\nIIII\n", b"x" * 100000 + b"\n" + b"ACGT\n+\nIIII\n" * 3,
+             b"@a\nAC" + b"G" * 70000 + b"\n+\n" + b"I" * 70002 + b"\n"]
+    with pe_inference.PEIndex([b"ACGTACGTAC"], 3) as ix:
+        for fq in cases:
+            n_lines, start, length = ix.split_records(fq)
+            lines = pe_oracle.split_lines(fq)
+            assert n_lines == len(lines), fq[:40]
+            assert len(start) == len(lines) // 4
+            for r in range(len(start)):
+                assert fq[int(start[r]):int(start[r]) + int(length[r])].decode() == lines[4 * r + 1][:-1]
+
+
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_per_read_mapping_matches_oracle(golden, force_generic):
+    if golden.status != 0:
+        return
+    ids, seqs = pe_inference.parse_gfa_nodes(golden.gfa)
+    with pe_inference.PEIndex(seqs, golden.k) as ix:
+        ix.set_option("force_generic", force_generic)
+        for fq in (golden.fwd, golden.rve):
+            off, nodes, status = ix.map_reads(fq)
+            ooff, onodes, ostatus = c_oracle.map_reads(golden.gfa, fq, golden.k)
+            assert np.array_equal(status, ostatus)
+            assert np.array_equal(off.astype(np.int64), ooff)
+            assert np.array_equal(nodes.astype(np.int64), onodes.astype(np.int64))
+
+
+@pytest.mark.parametrize("name,pairs", [("C1", 6000), ("C2", 6000), ("C3", 4000), ("C4", 3000)])
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_synthetic_configs_match_c_oracle(name, pairs, force_generic):
+    cfg = synth.CONFIGS[name]
+    g, f, r = synth.generate(cfg, pairs=pairs)
+    gfa = g.to_gfa()
+    ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"force_generic": force_generic})
+    onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
+    assert np.array_equal(node.astype(np.int64), onode)
+    assert np.array_equal(short.astype(np.int64), oshort)
+    for k, v in ostats.items():
+        assert stats[k] == v
+    assert stats["kernel_launches"] > 0
+
+
+def test_chunked_streaming_equals_single_chunk():
+    cfg = synth.CONFIGS["C1"]
+    g, f, r = synth.generate(cfg, pairs=9000)
+    ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())
+    res = []
+    for chunk_mb in (256, 1):
+        with pe_inference.PEIndex(seqs, cfg.k) as ix:
+            ix.set_option("chunk_mb", chunk_mb)
+            ix.count_host(f, r)
+            res.append(ix.matrices() + (ix.stats(),))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    for k in ("total_pairs", "n_pairs", "short_pairs", "used_pairs", "n_keys"):
+        assert res[0][2][k] == res[1][2][k]
+
+
+def test_counts_accumulate_over_calls_and_shards_sum_exactly():
+    """Multi-GPU contract on one device: disjoint record ranges summed == whole (integer adds)."""
+    cfg = synth.CONFIGS["C3"]
+    g, f, r = synth.generate(cfg, pairs=4000)
+    ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())
+    rec_f, rec_r = (2 * 150 + 18), (2 * 150 + 18)
+    from vstrains_b200 import shard
+    with pe_inference.PEIndex(seqs, cfg.k) as ix:
+        ix.count_host(f, r)
+        whole = ix.matrices()
+        wstats = ix.stats()
+        ix.reset()
+        for lo_f, hi_f, lo_r, hi_r in shard.shard_ranges(f, r, 3):
+            ix.count_host(f[lo_f:hi_f], r[lo_r:hi_r])
+        parts = ix.matrices()
+        pstats = ix.stats()
+    assert np.array_equal(whole[0], parts[0]) and np.array_equal(whole[1], parts[1])
+    for k in ("total_pairs", "n_pairs", "short_pairs", "used_pairs"):
+        assert wstats[k] == pstats[k]
+
+
+def test_device_resident_entry_point_matches_host_entry_point():
+    import torch
+    cfg = synth.CONFIGS["C2"]
+    g, f, r = synth.generate(cfg, pairs=5000)
+    ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())
+    with pe_inference.PEIndex(seqs, cfg.k) as ix:
+        ix.count_host(f, r)
+        host = ix.matrices()
+        ix.reset()
+        # deliberately misaligned device buffers (shards start at arbitrary byte offsets)
+        df = torch.zeros(f.size + 7, dtype=torch.uint8, device="cuda")
+        dr = torch.zeros(r.size + 3, dtype=torch.uint8, device="cuda")
+        df[7:] = torch.from_numpy(f).cuda()
+        dr[3:] = torch.from_numpy(r).cuda()
+        torch.cuda.synchronize()
+        ix.count_device(df.data_ptr() + 7, f.size, dr.data_ptr() + 3, r.size)
+        dev = ix.matrices()
+        p, n = ix.matrices_device()
+        assert p != 0 and n == 2 * len(seqs) ** 2
+    assert np.array_equal(host[0], dev[0]) and np.array_equal(host[1], dev[1])
+
+
+def test_non_ascii_input_is_rejected():
+    with pytest.raises(VspeError) as ei:
+        pe_inference.pe_inference(b"S\t1\tACGTACGTAC\n", b"@r\nACGT\xc3\xa9\n+\nIIIII\n", b"@r\nACGTA\n+\nIIIII\n", 3)
+    assert ei.value.code == -3

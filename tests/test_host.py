@@ -1,0 +1,99 @@
+"""CPU-side tests: C ABI surface, host-side mirror logic, dense writer (no GPU needed)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, parse_info
+from oracle import pe_oracle
+from vstrains_b200 import _lib, pe_inference
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = _lib.lib()
+    syms = _lib.declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert getattr(L, s) is not None
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH]).decode()
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(syms) <= exported
+
+
+def test_library_is_built_for_sm100a_only():
+    out = subprocess.check_output(["/usr/local/cuda/bin/cuobjdump", "-lelf", _lib.LIB_PATH]).decode()
+    archs = {l.split(".")[-2] for l in out.splitlines() if "sm_" in l}
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_a_gpu():
+    p = ctypes.c_void_p()
+    rc = _lib.lib().vspe_create(0, ctypes.byref(p))
+    assert rc == -6
+    assert b"no CPU fallback" in _lib.lib().vspe_last_error()
+    with pytest.raises(_lib.VspeError):
+        pe_inference.pe_inference(b"S\t1\tACGTACGT\n", b"", b"", 3)
+
+
+def test_parse_gfa_nodes_matches_oracle(golden):
+    ids, seqs = pe_inference.parse_gfa_nodes(golden.gfa)
+    oids, oseqs = pe_oracle.parse_gfa(golden.gfa)
+    assert ids == oids
+    assert [s.decode() for s in seqs] == oseqs
+
+
+def test_parse_gfa_unterminated_last_line_loses_a_char():
+    gfa = b"S\ta\tACGTAC\nS\tb\tGGGTTT"
+    ids, seqs = pe_inference.parse_gfa_nodes(gfa)
+    assert (ids, seqs) == pe_oracle.parse_gfa(gfa)[0:1] + ([b"ACGTAC", b"GGGTT"],)
+
+
+def test_dense_writer_reproduces_reference_files(golden, tmp_path):
+    if golden.status != 0:
+        return
+    ids, _ = pe_oracle.parse_gfa(golden.gfa)
+    for name, data in (("pe_info", golden.pe_info), ("st_info", golden.st_info)):
+        mat = parse_info(data, ids) if ids else np.zeros((0, 0), np.int64)
+        path = str(tmp_path / name)
+        pe_inference.write_info(path, ids, mat.astype(np.uint64))
+        with open(path, "rb") as f:
+            assert f.read() == data
+
+
+def test_dense_writer_large_values_and_threads(tmp_path):
+    n = 150
+    rng = np.random.default_rng(3)
+    mat = rng.integers(0, 2**40, size=(n, n), dtype=np.uint64)
+    mat[0, 0] = 0
+    mat[1, 1] = 2**63 + 5
+    ids = ["n%d" % (i * 7919) for i in range(n)]
+    path = str(tmp_path / "pe_info")
+    pe_inference.write_info(path, ids, mat)
+    exp = "".join("%s:%s:%d\n" % (ids[i], ids[j], int(mat[i, j])) for i in range(n) for j in range(n))
+    with open(path) as f:
+        assert f.read() == exp
+
+
+def test_shims_keep_the_reference_names():
+    assert pe_inference.reverse_seq("AACG") == "CGTT"
+    with pytest.raises(KeyError):
+        pe_inference.reverse_seq("ACNG")
+    with pytest.raises(TypeError):
+        pe_inference.single_end_read_mapping("ACGT", {}, [4], 3, 1)
+    sys.path.insert(0, os.path.join(ROOT, "utils"))
+    import importlib
+    mod = importlib.import_module("VStrains_PE_Inference")
+    for name in ("main", "reverse_seq", "single_end_read_mapping"):
+        assert hasattr(mod, name)

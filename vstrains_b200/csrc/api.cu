@@ -1,0 +1,650 @@
+// api.cu -- the C ABI of libvspe.so (declared in include/vspe.h) and the host-side plumbing:
+// context, chunked pinned streaming, GFA S-line parsing, dense text writer, whole-run driver.
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <thread>
+
+#include "ctx.cuh"
+
+namespace vspe {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int map_reads_generic_list(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                           const uint32_t* d_worklist, uint64_t n_items, ReadSlot* d_slots);
+int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                   uint64_t n_reads, ReadSlot* d_slots);
+
+// ---------------------------------------------------------------------------------------
+// per-mate streaming state
+// ---------------------------------------------------------------------------------------
+struct MateStream {
+    uint64_t line_base = 0;     // terminators seen so far
+    uint64_t lines = 0;         // total lines once the stream ended
+    uint64_t n_slots = 0;       // records with a result slot
+};
+
+static inline uint64_t seq_lines_before(uint64_t x) { return (x + 2) / 4; }   // #{l < x : l % 4 == 1}
+
+static int check_kernel_errors(Ctx* c) {
+    unsigned long long e = 0;
+    VSPE_CUDA(cudaMemcpyAsync(&e, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    if (e & ERRF_NON_ASCII) { set_error("input contains a byte >= 0x80 (non-ASCII FASTQ is outside the reference's contract)"); return VSPE_ERR_NON_ASCII; }
+    if (e & ERRF_SPILL_FULL) { set_error("node-list spill pool exhausted"); return VSPE_ERR_LIMIT; }
+    if (e & ERRF_KEYS_FULL) { set_error("key buffer exhausted"); return VSPE_ERR_LIMIT; }
+    return VSPE_OK;
+}
+
+// One chunk of one mate's byte stream, resident on the device.  The chunk must start at a line
+// start and (unless it is the last chunk) end right after a terminator.
+static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint64_t n, bool is_last, int last_byte) {
+    if (n == 0) {
+        if (is_last) ms.lines = ms.line_base;
+        return VSPE_OK;
+    }
+    MateBuf& mb = c->mate[m];
+    uint64_t n_terms = 0;
+    cudaEvent_t e0 = c->ev[2], e1 = c->ev[3], e2 = c->ev[4];
+    VSPE_CUDA(cudaEventRecord(e0, c->stream));
+    VSPE_TRY(scan_count_lines(c, d_buf, n, &n_terms));
+    const uint64_t lb = ms.line_base;
+    const uint64_t rec_first = seq_lines_before(lb);
+    const uint64_t n_seq = seq_lines_before(lb + n_terms) - rec_first;
+    VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
+    VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
+    VSPE_TRY(mb.slots.reserve(rec_first + n_seq + 1, true, c->stream));
+    VSPE_TRY(scan_index_records(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p));
+    VSPE_CUDA(cudaEventRecord(e1, c->stream));
+    if (n_seq) {
+        if (c->opt_force_generic)
+            VSPE_TRY(map_reads_generic_list(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, nullptr, n_seq, mb.slots.p + rec_first));
+        else
+            VSPE_TRY(map_reads_fast(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, n_seq, mb.slots.p + rec_first));
+    }
+    VSPE_CUDA(cudaEventRecord(e2, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, e0, e1);
+    cudaEventElapsedTime(&b, e1, e2);
+    c->stats.ms_scan += a;
+    c->stats.ms_map += b;
+    ms.n_slots = rec_first + n_seq;
+    ms.line_base = lb + n_terms;
+    if (is_last) {
+        bool term = last_byte == '\n' || last_byte == '\r';
+        ms.lines = ms.line_base + (term ? 0 : 1);
+    }
+    return VSPE_OK;
+}
+
+static int finish_pairs(Ctx* c, const MateStream& f, const MateStream& r) {
+    uint64_t total = std::min(f.lines / 4, r.lines / 4);       // PE_Inference.py:154
+    cudaEvent_t e0 = c->ev[5], e1 = c->ev[6];
+    VSPE_CUDA(cudaEventRecord(e0, c->stream));
+    VSPE_TRY(count_pairs(c, c->mate[0].slots.p, c->mate[1].slots.p, total));
+    VSPE_CUDA(cudaEventRecord(e1, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->stats.ms_count += ms;
+    return check_kernel_errors(c);
+}
+
+static int require_index(Ctx* c) {
+    if (!c || !c->index.built) { set_error("vspe_index_build must succeed before this call"); return VSPE_ERR_ARG; }
+    VSPE_CUDA(cudaSetDevice(c->device));
+    return VSPE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------------------
+// Largest cut <= hi such that [lo, cut) ends right after a line terminator and does not
+// split a "\r\n"; returns lo if the range holds no usable terminator.
+static uint64_t cut_at_line(const uint8_t* p, uint64_t lo, uint64_t hi, uint64_t n) {
+    uint64_t i = hi;
+    while (i > lo) {
+        uint8_t c = p[i - 1];
+        if (c == '\n') return i;
+        if (c == '\r' && i < n && p[i] != '\n') return i;
+        i--;
+    }
+    return lo;
+}
+
+static void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t n) {
+    unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (n < (8u << 20) || nt == 1) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    size_t per = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) {
+        size_t a = (size_t)t * per, b = std::min(n, a + per);
+        if (a >= b) break;
+        th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
+    }
+    for (auto& t : th) t.join();
+}
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Stream one mate's host buffer through the device in line-aligned chunks with two staging
+// buffers: the copy of chunk i+1 overlaps the kernels of chunk i.
+static int stream_mate_host(Ctx* c, int m, MateStream& ms, const uint8_t* src, uint64_t n) {
+    if (n == 0) return feed_chunk(c, m, ms, nullptr, 0, true, -1);
+    const uint64_t chunk = (uint64_t)std::max<int64_t>(1, c->opt_chunk_mb) << 20;
+    const bool pinned_src = is_pinned(src);
+    struct Piece { uint64_t lo, hi; };
+    std::vector<Piece> pieces;
+    for (uint64_t lo = 0; lo < n;) {
+        uint64_t hi = std::min(n, lo + chunk);
+        if (hi < n) {
+            uint64_t cut = cut_at_line(src, lo, hi, n);
+            while (cut == lo && hi < n) {                 // a line longer than the chunk: extend
+                hi = std::min(n, hi + chunk);
+                cut = hi == n ? n : cut_at_line(src, lo, hi, n);
+            }
+            hi = cut;
+        }
+        pieces.push_back({lo, hi});
+        lo = hi;
+    }
+    uint64_t max_piece = 0;
+    for (auto& p : pieces) max_piece = std::max(max_piece, p.hi - p.lo);
+    for (int b = 0; b < 2; b++) VSPE_TRY(c->dev_in[b].reserve(max_piece + 64));
+    if (!pinned_src && c->pinned_bytes < max_piece) {
+        for (int b = 0; b < 2; b++) {
+            if (c->pinned[b]) cudaFreeHost(c->pinned[b]);
+            c->pinned[b] = nullptr;
+            VSPE_CUDA(cudaMallocHost(&c->pinned[b], max_piece + 64));
+        }
+        c->pinned_bytes = max_piece;
+    }
+    cudaEvent_t copied[2];
+    for (int b = 0; b < 2; b++) VSPE_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    auto issue_copy = [&](size_t i) -> int {
+        int b = (int)(i & 1);
+        const Piece& p = pieces[i];
+        const uint8_t* from = src + p.lo;
+        if (!pinned_src) { parallel_memcpy(c->pinned[b], from, p.hi - p.lo); from = c->pinned[b]; }
+        VSPE_CUDA(cudaMemcpyAsync(c->dev_in[b].p, from, p.hi - p.lo, cudaMemcpyHostToDevice, c->copy_stream[b]));
+        VSPE_CUDA(cudaEventRecord(copied[b], c->copy_stream[b]));
+        return VSPE_OK;
+    };
+    int rc = VSPE_OK;
+    rc = issue_copy(0);
+    for (size_t i = 0; rc == VSPE_OK && i < pieces.size(); i++) {
+        int b = (int)(i & 1);
+        // chunk i-1 (other buffer) was fully processed (feed_chunk syncs), so buffer b^1 is free
+        if (i + 1 < pieces.size()) rc = issue_copy(i + 1);
+        if (rc != VSPE_OK) break;
+        if (cudaStreamWaitEvent(c->stream, copied[b], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); rc = VSPE_ERR_CUDA; break; }
+        bool last = i + 1 == pieces.size();
+        rc = feed_chunk(c, m, ms, c->dev_in[b].p, pieces[i].hi - pieces[i].lo, last, last ? src[n - 1] : -1);
+    }
+    cudaStreamSynchronize(c->copy_stream[0]);
+    cudaStreamSynchronize(c->copy_stream[1]);
+    cudaStreamSynchronize(c->stream);
+    for (int b = 0; b < 2; b++) cudaEventDestroy(copied[b]);
+    return rc;
+}
+
+// Python text-mode line iteration + `Line[:-1]` (PE_Inference.py:105-106) over raw bytes.
+struct GfaNodes {
+    std::vector<std::string> ids;
+    std::vector<uint8_t> seqs;
+    std::vector<uint64_t> off{0};
+};
+
+static int parse_gfa_bytes(const uint8_t* g, uint64_t n, GfaNodes& out) {
+    uint64_t s = 0, i = 0;
+    auto handle = [&](uint64_t a, uint64_t b) -> int {     // content [a, b)
+        if (b <= a || g[a] != 'S') return VSPE_OK;
+        if (b - a > 1 && g[a + 1] != '\t') return VSPE_OK;  // first field is not exactly "S"
+        uint64_t p = a + 1;
+        if (p >= b) { set_error("GFA S line without an id field"); return VSPE_ERR_GFA; }
+        uint64_t f1s = p + 1;
+        p = f1s;
+        while (p < b && g[p] != '\t') p++;
+        uint64_t f1e = p;
+        if (p >= b) { set_error("GFA S line without a sequence field"); return VSPE_ERR_GFA; }
+        uint64_t f2s = p + 1;
+        p = f2s;
+        while (p < b && g[p] != '\t') p++;
+        out.ids.emplace_back(reinterpret_cast<const char*>(g + f1s), f1e - f1s);
+        out.seqs.insert(out.seqs.end(), g + f2s, g + p);
+        out.off.push_back(out.seqs.size());
+        return VSPE_OK;
+    };
+    while (i < n) {
+        uint8_t ch = g[i];
+        if (ch & 0x80) { set_error("GFA contains a non-ASCII byte"); return VSPE_ERR_NON_ASCII; }
+        if (ch == '\n' || ch == '\r') {
+            VSPE_TRY(handle(s, i));
+            if (ch == '\r' && i + 1 < n && g[i + 1] == '\n') i++;
+            i++;
+            s = i;
+        } else {
+            i++;
+        }
+    }
+    if (s < n) VSPE_TRY(handle(s, n - 1));      // unterminated last line: [:-1] eats a real char
+    return VSPE_OK;
+}
+
+struct MappedFile {
+    const uint8_t* p = nullptr;
+    uint64_t n = 0;
+    int fd = -1;
+    ~MappedFile() {
+        if (p && n) munmap(const_cast<uint8_t*>(p), n);
+        if (fd >= 0) close(fd);
+    }
+    int open_ro(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) { set_error("cannot open %s: %s", path, strerror(errno)); return VSPE_ERR_IO; }
+        struct stat st;
+        if (fstat(fd, &st) != 0) { set_error("cannot stat %s", path); return VSPE_ERR_IO; }
+        n = (uint64_t)st.st_size;
+        if (n) {
+            void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { set_error("cannot mmap %s: %s", path, strerror(errno)); p = nullptr; return VSPE_ERR_IO; }
+            madvise(m, n, MADV_SEQUENTIAL);
+            p = static_cast<const uint8_t*>(m);
+        }
+        return VSPE_OK;
+    }
+};
+
+static inline char* put_u64(char* p, uint64_t v) {
+    char tmp[24];
+    int k = 0;
+    do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (k) *p++ = tmp[--k];
+    return p;
+}
+
+}  // namespace vspe
+
+using namespace vspe;
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+struct vspe_ctx : public vspe::Ctx {};
+
+const char* vspe_last_error(void) { return get_error(); }
+const char* vspe_version(void) { return "vspe-b200 0.1 (sm_100a)"; }
+
+int vspe_create(int device, vspe_ctx** out) {
+    if (!out) { set_error("null out pointer"); return VSPE_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); libvspe has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return VSPE_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return VSPE_ERR_ARG; }
+    VSPE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VSPE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libvspe is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return VSPE_ERR_CUDA;
+    }
+    vspe_ctx* c = new vspe_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    VSPE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) VSPE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream[b], cudaStreamNonBlocking));
+    for (auto& ev : c->ev) VSPE_CUDA(cudaEventCreate(&ev));
+    VSPE_TRY(c->counters.reserve(CNT_COUNT_));
+    VSPE_CUDA(cudaMemset(c->counters.p, 0, c->counters.cap * 8));
+    *out = c;
+    return VSPE_OK;
+}
+
+void vspe_destroy(vspe_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int b = 0; b < 2; b++) {
+        if (c->pinned[b]) cudaFreeHost(c->pinned[b]);
+        if (c->copy_stream[b]) cudaStreamDestroy(c->copy_stream[b]);
+    }
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int vspe_index_build(vspe_ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len) {
+    if (!c || !seq_off || (n_nodes && !seqs && seq_off[n_nodes])) { set_error("bad arguments"); return VSPE_ERR_ARG; }
+    VSPE_CUDA(cudaSetDevice(c->device));
+    c->scratch_valid = false;
+    VSPE_TRY(index_build_device(c, seqs, seq_off, n_nodes, split_len));
+    return vspe_reset(c);
+}
+
+int vspe_reset(vspe_ctx* c) {
+    VSPE_TRY(require_index(c));
+    uint64_t nn = 2ull * c->index.n_nodes * c->index.n_nodes;
+    if (nn) VSPE_CUDA(cudaMemsetAsync(c->mats.p, 0, nn * 8, c->stream));
+    VSPE_CUDA(cudaMemsetAsync(c->counters.p, 0, CNT_COUNT_ * 8, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    vspe_stats keep = c->stats;
+    c->stats = {};
+    c->stats_overridden = false;
+    c->stats.ms_index = keep.ms_index;
+    c->stats.n_nodes = keep.n_nodes;
+    c->stats.n_kmers = keep.n_kmers;
+    c->stats.table_slots = keep.table_slots;
+    c->launches = 0;
+    return VSPE_OK;
+}
+
+static void begin_call(vspe_ctx* c) {
+    // the spill pool is per call: slots of earlier calls are no longer referenced
+    cudaMemsetAsync(c->counters.p + CNT_SPILL_CURSOR, 0, 8, c->stream);
+}
+
+int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const uint8_t* d_rve, uint64_t n_rve) {
+    VSPE_TRY(require_index(c));
+    begin_call(c);
+    cudaEvent_t t0 = c->ev[0], t1 = c->ev[1];
+    VSPE_CUDA(cudaEventRecord(t0, c->stream));
+    MateStream f, r;
+    const uint8_t* bufs[2] = {d_fwd, d_rve};
+    uint64_t ns[2] = {n_fwd, n_rve};
+    MateStream* ms[2] = {&f, &r};
+    for (int m = 0; m < 2; m++) {
+        int last = -1;
+        if (ns[m]) {
+            uint8_t b = 0;
+            VSPE_CUDA(cudaMemcpyAsync(&b, bufs[m] + ns[m] - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+            VSPE_CUDA(cudaStreamSynchronize(c->stream));
+            last = b;
+        }
+        VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last));
+    }
+    VSPE_TRY(finish_pairs(c, f, r));
+    VSPE_CUDA(cudaEventRecord(t1, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    float ms_total = 0;
+    cudaEventElapsedTime(&ms_total, t0, t1);
+    c->stats.ms_total = ms_total;
+    c->stats.bytes_fwd += n_fwd;
+    c->stats.bytes_rve += n_rve;
+    return VSPE_OK;
+}
+
+int vspe_count_host(vspe_ctx* c, const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve) {
+    VSPE_TRY(require_index(c));
+    if ((n_fwd && !fwd) || (n_rve && !rve)) { set_error("null input buffer"); return VSPE_ERR_ARG; }
+    begin_call(c);
+    cudaEvent_t t0 = c->ev[7];
+    VSPE_CUDA(cudaEventRecord(t0, c->stream));
+    MateStream f, r;
+    VSPE_TRY(stream_mate_host(c, 0, f, fwd, n_fwd));
+    VSPE_TRY(stream_mate_host(c, 1, r, rve, n_rve));
+    VSPE_TRY(finish_pairs(c, f, r));
+    cudaEvent_t t1 = c->ev[1];
+    VSPE_CUDA(cudaEventRecord(t1, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    float ms_total = 0;
+    cudaEventElapsedTime(&ms_total, t0, t1);
+    c->stats.ms_total = ms_total;
+    c->stats.bytes_fwd += n_fwd;
+    c->stats.bytes_rve += n_rve;
+    return VSPE_OK;
+}
+
+int vspe_matrices_device(vspe_ctx* c, uint64_t** d_mats, uint64_t* n_elems) {
+    VSPE_TRY(require_index(c));
+    if (d_mats) *d_mats = c->mats.p;
+    if (n_elems) *n_elems = 2ull * c->index.n_nodes * c->index.n_nodes;
+    return VSPE_OK;
+}
+
+int vspe_matrices_host(vspe_ctx* c, uint64_t* node_mat, uint64_t* short_mat) {
+    VSPE_TRY(require_index(c));
+    uint64_t nn = (uint64_t)c->index.n_nodes * c->index.n_nodes;
+    if (nn == 0) return VSPE_OK;
+    if (node_mat) VSPE_CUDA(cudaMemcpyAsync(node_mat, c->mats.p, nn * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (short_mat) VSPE_CUDA(cudaMemcpyAsync(short_mat, c->mats.p + nn, nn * 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    return VSPE_OK;
+}
+
+int vspe_get_stats(vspe_ctx* c, vspe_stats* out) {
+    if (!c || !out) { set_error("null argument"); return VSPE_ERR_ARG; }
+    VSPE_CUDA(cudaSetDevice(c->device));
+    unsigned long long h[CNT_COUNT_];
+    VSPE_CUDA(cudaMemcpy(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (!c->stats_overridden) {
+        c->stats.n_pairs = h[CNT_N];
+        c->stats.short_pairs = h[CNT_SHORT];
+        c->stats.used_pairs = h[CNT_USED];
+    }
+    c->stats.n_keys = h[CNT_KEYS];
+    c->stats.reads_fast = h[CNT_FAST];
+    c->stats.reads_generic = h[CNT_GENERIC];
+    c->stats.kernel_launches = c->launches;
+    *out = c->stats;
+    return VSPE_OK;
+}
+
+int vspe_set_pair_counters(vspe_ctx* c, uint64_t total, uint64_t n, uint64_t shrt, uint64_t used) {
+    if (!c) { set_error("null context"); return VSPE_ERR_ARG; }
+    c->stats.total_pairs = total;
+    c->stats.n_pairs = n;
+    c->stats.short_pairs = shrt;
+    c->stats.used_pairs = used;
+    c->stats_overridden = true;
+    return VSPE_OK;
+}
+
+int vspe_split_records(vspe_ctx* c, const uint8_t* fq, uint64_t n_bytes, uint64_t* n_lines, uint64_t* n_records,
+                       const uint64_t** seq_start, const uint32_t** seq_len) {
+    if (!c) { set_error("null context"); return VSPE_ERR_ARG; }
+    VSPE_CUDA(cudaSetDevice(c->device));
+    uint64_t lines = 0, recs = 0;
+    c->h_seq_start.clear();
+    c->h_seq_len.clear();
+    if (n_bytes) {
+        VSPE_TRY(c->dev_in[0].reserve(n_bytes + 64));
+        VSPE_CUDA(cudaMemcpyAsync(c->dev_in[0].p, fq, n_bytes, cudaMemcpyHostToDevice, c->stream));
+        uint64_t n_terms = 0;
+        VSPE_TRY(scan_count_lines(c, c->dev_in[0].p, n_bytes, &n_terms));
+        uint64_t n_seq = seq_lines_before(n_terms);
+        Records& rec = c->mate[0].rec;
+        VSPE_TRY(rec.seq_start.reserve(n_seq + 2));
+        VSPE_TRY(rec.seq_end.reserve(n_seq + 2));
+        VSPE_TRY(scan_index_records(c, c->dev_in[0].p, n_bytes, 0, 0, n_seq, rec.seq_start.p, rec.seq_end.p));
+        bool term = fq[n_bytes - 1] == '\n' || fq[n_bytes - 1] == '\r';
+        lines = n_terms + (term ? 0 : 1);
+        recs = lines / 4;
+        std::vector<uint64_t> e(n_seq);
+        c->h_seq_start.resize(n_seq);
+        if (n_seq) {
+            VSPE_CUDA(cudaMemcpyAsync(c->h_seq_start.data(), rec.seq_start.p, n_seq * 8, cudaMemcpyDeviceToHost, c->stream));
+            VSPE_CUDA(cudaMemcpyAsync(e.data(), rec.seq_end.p, n_seq * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+        c->h_seq_start.resize(recs);
+        c->h_seq_len.resize(recs);
+        for (uint64_t r = 0; r < recs; r++) c->h_seq_len[r] = (uint32_t)(e[r] - c->h_seq_start[r]);
+        VSPE_TRY(check_kernel_errors(c));
+    }
+    if (n_lines) *n_lines = lines;
+    if (n_records) *n_records = recs;
+    if (seq_start) *seq_start = c->h_seq_start.data();
+    if (seq_len) *seq_len = c->h_seq_len.data();
+    return VSPE_OK;
+}
+
+int vspe_map_reads(vspe_ctx* c, const uint8_t* fq, uint64_t n_bytes, uint64_t* n_reads, const uint64_t** offsets,
+                   const uint32_t** nodes, const uint8_t** status) {
+    VSPE_TRY(require_index(c));
+    begin_call(c);
+    MateStream ms;
+    VSPE_TRY(stream_mate_host(c, 0, ms, fq, n_bytes));
+    VSPE_TRY(check_kernel_errors(c));
+    uint64_t recs = ms.lines / 4;
+    std::vector<ReadSlot> slots(recs);
+    if (recs) VSPE_CUDA(cudaMemcpy(slots.data(), c->mate[0].slots.p, recs * sizeof(ReadSlot), cudaMemcpyDeviceToHost));
+    unsigned long long spill_n = 0;
+    VSPE_CUDA(cudaMemcpy(&spill_n, c->counters.p + CNT_SPILL_CURSOR, 8, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> spill(spill_n);
+    if (spill_n) VSPE_CUDA(cudaMemcpy(spill.data(), c->spill.p, spill_n * 4, cudaMemcpyDeviceToHost));
+    c->h_offsets.assign(recs + 1, 0);
+    c->h_nodes.clear();
+    c->h_status.assign(recs, 0);
+    for (uint64_t r = 0; r < recs; r++) {
+        c->h_offsets[r] = c->h_nodes.size();
+        uint32_t st = slots[r].hdr & 0xFF, n = slots[r].hdr >> 8;
+        c->h_status[r] = (uint8_t)st;
+        if (st != ST_OK) continue;
+        const uint32_t* ids = n <= (uint32_t)SLOT_IDS ? slots[r].ids : spill.data() + slots[r].ids[0];
+        c->h_nodes.insert(c->h_nodes.end(), ids, ids + n);
+    }
+    c->h_offsets[recs] = c->h_nodes.size();
+    if (c->h_nodes.empty()) c->h_nodes.push_back(0);
+    if (n_reads) *n_reads = recs;
+    if (offsets) *offsets = c->h_offsets.data();
+    if (nodes) *nodes = c->h_nodes.data();
+    if (status) *status = c->h_status.data();
+    return VSPE_OK;
+}
+
+int vspe_write_info(const char* path, const char* const* ids, uint32_t n, const uint64_t* mat) {
+    if (!path || (n && (!ids || !mat))) { set_error("bad arguments"); return VSPE_ERR_ARG; }
+    int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) { set_error("cannot create %s: %s", path, strerror(errno)); return VSPE_ERR_IO; }
+    std::vector<size_t> idlen(n);
+    size_t maxid = 0;
+    for (uint32_t i = 0; i < n; i++) { idlen[i] = strlen(ids[i]); maxid = std::max(maxid, idlen[i]); }
+    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (n < 64) nt = 1;
+    // rows are formatted in parallel into per-thread buffers (bounded slabs), written in order
+    const uint32_t SLAB = std::max<uint32_t>(nt, 64);           // rows per round
+    std::vector<std::vector<char>> buf(nt);
+    int rc = VSPE_OK;
+    for (uint32_t r0 = 0; r0 < n && rc == VSPE_OK; r0 += SLAB) {
+        uint32_t r1 = std::min(n, r0 + SLAB);
+        uint32_t per = (r1 - r0 + nt - 1) / nt;
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) {
+            uint32_t a = r0 + t * per, b = std::min(r1, a + per);
+            buf[t].clear();
+            if (a >= b) continue;
+            th.emplace_back([&, t, a, b] {
+                std::vector<char>& out = buf[t];
+                out.resize((size_t)(b - a) * n * (2 * maxid + 24));
+                char* p = out.data();
+                for (uint32_t i = a; i < b; i++) {
+                    const uint64_t* row = mat + (size_t)i * n;
+                    for (uint32_t j = 0; j < n; j++) {
+                        memcpy(p, ids[i], idlen[i]); p += idlen[i]; *p++ = ':';
+                        memcpy(p, ids[j], idlen[j]); p += idlen[j]; *p++ = ':';
+                        p = put_u64(p, row[j]);
+                        *p++ = '\n';
+                    }
+                }
+                out.resize(p - out.data());
+            });
+        }
+        for (auto& t : th) t.join();
+        for (unsigned t = 0; t < nt && rc == VSPE_OK; t++) {
+            const char* p = buf[t].data();
+            size_t left = buf[t].size();
+            while (left) {
+                ssize_t w = ::write(fd, p, left);
+                if (w < 0) { if (errno == EINTR) continue; set_error("write to %s failed: %s", path, strerror(errno)); rc = VSPE_ERR_IO; break; }
+                p += w; left -= (size_t)w;
+            }
+        }
+    }
+    if (close(fd) != 0 && rc == VSPE_OK) { set_error("close of %s failed", path); rc = VSPE_ERR_IO; }
+    return rc;
+}
+
+static int rm_rf(const std::string& dir) {
+    // PE_Inference.py:95 `rm -rf DIR`: the script owns its output directory
+    std::string cmd = "rm -rf -- '";
+    for (char ch : dir) { if (ch == '\'') cmd += "'\\''"; else cmd += ch; }
+    cmd += "'";
+    return system(cmd.c_str());
+}
+
+int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, int kmer_size, const char* out_dir,
+             int n_gpus, vspe_stats* stats) {
+    if (!gfa_path || !fwd_path || !rve_path || !out_dir || kmer_size < 1) { set_error("bad arguments"); return VSPE_ERR_ARG; }
+    if (n_gpus != 1) { set_error("vspe_run: multi-GPU runs go through vspe_run_multi (n_gpus=%d)", n_gpus); return VSPE_ERR_ARG; }
+    std::string dir(out_dir);
+    if (!dir.empty() && dir.back() == '/') dir.pop_back();      // :93-94
+    if (dir.empty()) { set_error("empty output directory"); return VSPE_ERR_ARG; }
+    if (rm_rf(dir) != 0 || mkdir(dir.c_str(), 0777) != 0) {
+        // os.makedirs creates parents too
+        std::string cmd = "mkdir -p -- '" + dir + "'";
+        if (system(cmd.c_str()) != 0) { set_error("cannot create output directory %s", dir.c_str()); return VSPE_ERR_IO; }
+    }
+    MappedFile g, f, r;
+    VSPE_TRY(g.open_ro(gfa_path));
+    GfaNodes nodes;
+    VSPE_TRY(parse_gfa_bytes(g.p, g.n, nodes));
+    VSPE_TRY(f.open_ro(fwd_path));
+    VSPE_TRY(r.open_ro(rve_path));
+    vspe_ctx* c = nullptr;
+    VSPE_TRY(vspe_create(0, &c));
+    int rc = vspe_index_build(c, nodes.seqs.data(), nodes.off.data(), (uint32_t)nodes.ids.size(), (uint32_t)kmer_size + 1);
+    if (rc == VSPE_OK) rc = vspe_count_host(c, f.p, f.n, r.p, r.n);
+    uint32_t N = (uint32_t)nodes.ids.size();
+    std::vector<uint64_t> nm((size_t)N * N), sm((size_t)N * N);
+    if (rc == VSPE_OK) rc = vspe_matrices_host(c, nm.data(), sm.data());
+    if (rc == VSPE_OK && stats) rc = vspe_get_stats(c, stats);
+    vspe_destroy(c);
+    if (rc != VSPE_OK) return rc;
+    std::vector<const char*> idp(N);
+    for (uint32_t i = 0; i < N; i++) idp[i] = nodes.ids[i].c_str();
+    VSPE_TRY(vspe_write_info((dir + "/pe_info").c_str(), idp.data(), N, nm.data()));
+    VSPE_TRY(vspe_write_info((dir + "/st_info").c_str(), idp.data(), N, sm.data()));
+    return VSPE_OK;
+}
+
+void* vspe_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_error("cudaMallocHost(%zu) failed", bytes); cudaGetLastError(); return nullptr; }
+    return p;
+}
+void vspe_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) { set_error("bad arguments"); return VSPE_ERR_ARG; }
+    if (!strcmp(name, "force_generic")) c->opt_force_generic = value;
+    else if (!strcmp(name, "chunk_mb")) c->opt_chunk_mb = value;
+    else { set_error("unknown option %s", name); return VSPE_ERR_ARG; }
+    return VSPE_OK;
+}
+
+}  // extern "C"

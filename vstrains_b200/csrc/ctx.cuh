@@ -1,0 +1,74 @@
+// ctx.cuh -- the per-device context behind the opaque vspe_ctx handle.
+#pragma once
+#include "vspe_internal.cuh"
+
+namespace vspe {
+
+// device-side counters (one u64 each), zeroed by vspe_reset
+enum Counter {
+    CNT_TOTAL = 0, CNT_N, CNT_SHORT, CNT_USED, CNT_KEYS,
+    CNT_SPILL_CURSOR,        // next free entry of the spill pool
+    CNT_ERR,                 // error bit flags raised by kernels
+    CNT_FAST, CNT_GENERIC,   // reads resolved per tier
+    CNT_WORK,                // generic-tier worklist length
+    CNT_COUNT_
+};
+static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4;
+
+struct MateBuf {
+    Records rec;
+    DevBuf<ReadSlot> slots;
+    uint64_t n_recs = 0;      // complete records = lines / 4
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev[8] = {};
+    Index index;
+    DevBuf<uint64_t> mats;            // [2][N][N] node_mat then short_mat
+    DevBuf<unsigned long long> counters;
+    // K1 scratch
+    DevBuf<uint32_t> tile_counts;
+    DevBuf<uint64_t> tile_base;
+    MateBuf mate[2];
+    // K4 generic-tier scratch
+    DevBuf<uint32_t> warp_scratch;
+    bool scratch_valid = false;       // warp_scratch initialised for the current index
+    DevBuf<uint32_t> spill;
+    // K5/K6 scratch
+    DevBuf<uint32_t> keys;
+    DevBuf<unsigned long long> bucket;   // [3][n_buckets + 1]: histogram, start, cursor
+    DevBuf<unsigned long long> block_sums;
+    bool count_attr_set = false;
+    // staging for host-input entry points
+    uint8_t* pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes = 0;
+    DevBuf<uint8_t> dev_in[2];
+    // host copies for vspe_map_reads / vspe_split_records
+    std::vector<uint64_t> h_offsets, h_seq_start;
+    std::vector<uint32_t> h_nodes, h_seq_len;
+    std::vector<uint8_t> h_status;
+    // options
+    int64_t opt_force_generic = 0;
+    int64_t opt_chunk_mb = 256;
+    // accounting
+    vspe_stats stats = {};
+    bool stats_overridden = false;
+    uint64_t launches = 0;
+    int sm_count = 148;
+};
+
+#define VSPE_LAUNCH_CHECK(c)                                                             \
+    do {                                                                                 \
+        (c)->launches++;                                                                 \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) {                                                        \
+            vspe::set_error("kernel launch failed: %s at %s:%d", cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                         \
+            return VSPE_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+
+}  // namespace vspe

@@ -1,0 +1,222 @@
+// index.cu -- K3: (k+1)-mer hash index over the node sequences and their reverse complements.
+//
+// Replaces the Python dict build of reference utils/VStrains_PE_Inference.py:117-135
+// (kmer_htable[kmer].append((i, sub_i)) for the forward k-mer and for reverse_seq(kmer)).
+// Layout and semantics are described in vspe_internal.cuh (IndexView).
+#include "ctx.cuh"
+
+namespace vspe {
+
+// --- pack both strands of every node into the 2-bit text ---------------------------------
+__global__ void __launch_bounds__(256)
+k_pack_text(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_off,
+            const uint32_t* __restrict__ strand_start, const uint32_t* __restrict__ node_len,
+            uint32_t n2, uint32_t text_len, uint64_t* __restrict__ text, uint32_t n_words) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint64_t b0 = (uint64_t)w * 32;
+    uint64_t word = 0;
+    if (b0 < text_len) {
+        uint32_t q = strand_of(strand_start, n2, (uint32_t)b0);
+        for (uint32_t j = 0; j < 32; j++) {
+            uint64_t b = b0 + j;
+            if (b >= text_len) break;
+            while (b >= strand_start[q + 1]) q++;
+            uint32_t i = q >> 1, s = q & 1;
+            uint32_t o = (uint32_t)(b - strand_start[q]);
+            uint32_t len = node_len[i];
+            uint32_t c = s ? seqs[seq_off[i] + (len - 1 - o)] : seqs[seq_off[i] + o];
+            uint64_t code = base_code(c) ^ (s ? 2u : 0u);
+            word |= code << (2 * j);
+        }
+    }
+    text[w] = word;
+}
+
+// --- one table entry per (k+1)-mer occurrence -----------------------------------------------
+__global__ void __launch_bounds__(256)
+k_index_insert(IndexView ix, unsigned long long* __restrict__ slots64) {
+    uint32_t tp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tp >= ix.text_len) return;
+    uint32_t q = strand_of(ix.strand_start, 2 * ix.n_nodes, tp);
+    if ((uint64_t)tp + ix.split_len > ix.strand_start[q + 1]) return;
+    uint64_t h = hash_packed(ix.text, tp, ix.split_len);
+    uint32_t meta = ((uint32_t)h & ~ix.node_mask) | (q >> 1);
+    unsigned long long entry = ((unsigned long long)meta << 32) | tp;
+    uint32_t j = slot_of(h, ix.slot_mask);
+    while (true) {
+        unsigned long long old = atomicCAS(&slots64[j], EMPTY_SLOT, entry);
+        if (old == EMPTY_SLOT) break;
+        j = (j + 1) & ix.slot_mask;
+    }
+}
+
+// number of postings whose (k+1)-mer equals the window at text position tp
+__device__ __forceinline__ uint32_t count_postings_text(const IndexView& ix, uint32_t tp, uint64_t h) {
+    uint32_t cnt = 0;
+    uint32_t j = slot_of(h, ix.slot_mask);
+    while (true) {
+        uint2 e = __ldg(ix.slots + j);
+        if (e.x == EMPTY_TP) break;
+        if (fp_match(e.y, h, ix.node_mask) && (e.x == tp || text_equal(ix.text, e.x, tp, ix.split_len))) cnt++;
+        j = (j + 1) & ix.slot_mask;
+    }
+    return cnt;
+}
+
+// --- uniq bitmap: exactly one posting in total for the k-mer starting at tp -------------------
+__global__ void __launch_bounds__(256)
+k_index_unique(IndexView ix, uint32_t* __restrict__ uniq, uint32_t n_words) {
+    uint32_t tp = blockIdx.x * blockDim.x + threadIdx.x;   // blockDim multiple of 32
+    bool flag = false;
+    if (tp < ix.text_len) {
+        uint32_t q = strand_of(ix.strand_start, 2 * ix.n_nodes, tp);
+        if ((uint64_t)tp + ix.split_len <= ix.strand_start[q + 1]) {
+            uint64_t h = hash_packed(ix.text, tp, ix.split_len);
+            flag = count_postings_text(ix, tp, h) == 1;
+        }
+    }
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, flag);
+    if ((threadIdx.x & 31) == 0 && (tp >> 5) < n_words) uniq[tp >> 5] = m;
+}
+
+// --- successor table: for the last window of every strand and every next base b, the text
+// position of the k-mer (window[1:] + b) if it has exactly one posting, else NONE32.
+// This is a precomputed table lookup, so it is exact for any graph, not only de Bruijn ones.
+__global__ void __launch_bounds__(128)
+k_index_succ(IndexView ix, uint32_t* __restrict__ succ) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t q = t >> 2, b = t & 3;
+    if (q >= 2 * ix.n_nodes) return;
+    uint32_t s0 = ix.strand_start[q], s1 = ix.strand_start[q + 1];
+    uint32_t L = ix.split_len;
+    uint32_t res = NONE32;
+    if (s1 - s0 >= L) {
+        uint64_t from = (uint64_t)s1 - L + 1;        // last L-1 bases of the strand
+        uint64_t h = HASH_SEED;
+        for (uint32_t m = 0; m < L; m += 32) {
+            uint64_t w = extract64(ix.text, from + m);
+            uint32_t rem = L - m;                     // bases of the query in this word
+            // position L-1 of the query is the appended base b
+            if (rem <= 32) {
+                uint64_t keep = (rem - 1 < 32) ? ((rem - 1 == 0) ? 0ull : ((1ull << (2 * (rem - 1))) - 1)) : ~0ull;
+                w = (w & keep) | ((uint64_t)b << (2 * (rem - 1)));
+                if (rem < 32) w &= (1ull << (2 * rem)) - 1;
+            }
+            h = hash_mix(h, w);
+        }
+        h = hash_final(h);
+        uint32_t cnt = 0, found = NONE32;
+        uint32_t j = slot_of(h, ix.slot_mask);
+        while (true) {
+            uint2 e = __ldg(ix.slots + j);
+            if (e.x == EMPTY_TP) break;
+            if (fp_match(e.y, h, ix.node_mask)) {
+                // compare L-1 overlap bases, then the appended base
+                bool eq = text_equal(ix.text, e.x, from, L - 1) && text_base(ix.text, (uint64_t)e.x + L - 1) == b;
+                if (eq) { cnt++; found = e.x; }
+            }
+            j = (j + 1) & ix.slot_mask;
+        }
+        if (cnt == 1) res = found;
+    }
+    succ[t] = res;
+}
+
+int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len) {
+    Index& ix = c->index;
+    ix.built = false;
+    if (split_len < 2) { set_error("split_len must be >= 2 (kmer_size >= 1)"); return VSPE_ERR_ARG; }
+    // host validation == the reference's failure modes
+    std::vector<uint32_t> h_ss(2 * (size_t)n_nodes + 1), h_len(n_nodes ? n_nodes : 1);
+    uint64_t text_len = 0, n_kmers = 0;
+    for (uint32_t i = 0; i < n_nodes; i++) {
+        uint64_t len = seq_off[i + 1] - seq_off[i];
+        if (len > 0x7FFFFFFFull) { set_error("node %u longer than 2^31", i); return VSPE_ERR_LIMIT; }
+        h_len[i] = (uint32_t)len;
+        const uint8_t* s = seqs + seq_off[i];
+        bool indexed = len >= split_len;
+        if (indexed) {
+            for (uint64_t j = 0; j < len; j++)
+                if (!is_acgt(s[j])) {
+                    set_error("node #%u: character 0x%02x at offset %llu is not one of ACGT "
+                              "(the reference raises KeyError in reverse_seq)", i, s[j], (unsigned long long)j);
+                    return VSPE_ERR_NODE_SEQ;
+                }
+            n_kmers += 2 * (len - split_len + 1);
+        }
+        h_ss[2 * i] = (uint32_t)text_len;
+        if (indexed) text_len += len;
+        h_ss[2 * i + 1] = (uint32_t)text_len;
+        if (indexed) text_len += len;
+        if (text_len >= 0xFFFFFF00ull) { set_error("graph too large: packed text exceeds 2^32 bases"); return VSPE_ERR_LIMIT; }
+    }
+    h_ss[2 * (size_t)n_nodes] = (uint32_t)text_len;
+    uint32_t nbits = 1;
+    while (nbits < 31 && (1ull << nbits) < n_nodes) nbits++;
+    uint64_t slots = 1024;
+    while (slots < 2 * n_kmers + 2) slots <<= 1;
+    if (slots > 0x80000000ull) { set_error("graph too large: hash table exceeds 2^31 slots"); return VSPE_ERR_LIMIT; }
+
+    cudaStream_t st = c->stream;
+    uint32_t n_words = (uint32_t)((text_len + 31) / 32) + 4;
+    VSPE_TRY(ix.text.reserve(n_words));
+    VSPE_TRY(ix.strand_start.reserve(h_ss.size()));
+    VSPE_TRY(ix.node_len.reserve(h_len.size()));
+    VSPE_TRY(ix.slots.reserve(slots));
+    VSPE_TRY(ix.uniq.reserve(n_words));
+    VSPE_TRY(ix.succ.reserve(8 * (size_t)n_nodes + 8));
+    DevBuf<uint8_t> d_seqs;
+    DevBuf<uint64_t> d_off;
+    uint64_t seq_bytes = n_nodes ? seq_off[n_nodes] : 0;
+    VSPE_TRY(d_seqs.reserve(seq_bytes + 1));
+    VSPE_TRY(d_off.reserve((size_t)n_nodes + 1));
+    cudaEvent_t e0 = c->ev[0], e1 = c->ev[1];
+    VSPE_CUDA(cudaEventRecord(e0, st));
+    if (seq_bytes) VSPE_CUDA(cudaMemcpyAsync(d_seqs.p, seqs, seq_bytes, cudaMemcpyHostToDevice, st));
+    VSPE_CUDA(cudaMemcpyAsync(d_off.p, seq_off, ((size_t)n_nodes + 1) * 8, cudaMemcpyHostToDevice, st));
+    VSPE_CUDA(cudaMemcpyAsync(ix.strand_start.p, h_ss.data(), h_ss.size() * 4, cudaMemcpyHostToDevice, st));
+    VSPE_CUDA(cudaMemcpyAsync(ix.node_len.p, h_len.data(), (size_t)n_nodes * 4, cudaMemcpyHostToDevice, st));
+    VSPE_CUDA(cudaMemsetAsync(ix.slots.p, 0xFF, slots * sizeof(uint2), st));
+    VSPE_CUDA(cudaMemsetAsync(ix.uniq.p, 0, (size_t)n_words * 4, st));
+
+    ix.text_len = (uint32_t)text_len;
+    ix.slot_mask = (uint32_t)(slots - 1);
+    ix.node_mask = (1u << nbits) - 1;
+    ix.split_len = split_len;
+    ix.n_nodes = n_nodes;
+    ix.n_kmers = n_kmers;
+    IndexView v = ix.view();
+
+    k_pack_text<<<(n_words + 255) / 256, 256, 0, st>>>(d_seqs.p, d_off.p, ix.strand_start.p, ix.node_len.p,
+                                                       2 * n_nodes, ix.text_len, ix.text.p, n_words);
+    VSPE_LAUNCH_CHECK(c);
+    if (text_len) {
+        uint32_t nb = (uint32_t)((text_len + 255) / 256);
+        k_index_insert<<<nb, 256, 0, st>>>(v, (unsigned long long*)ix.slots.p);
+        VSPE_LAUNCH_CHECK(c);
+        k_index_unique<<<nb, 256, 0, st>>>(v, ix.uniq.p, n_words);
+        VSPE_LAUNCH_CHECK(c);
+    }
+    if (n_nodes) {
+        k_index_succ<<<(8 * n_nodes + 127) / 128, 128, 0, st>>>(v, ix.succ.p);
+        VSPE_LAUNCH_CHECK(c);
+    }
+    VSPE_CUDA(cudaEventRecord(e1, st));
+    VSPE_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->stats.ms_index = ms;
+    c->stats.n_nodes = n_nodes;
+    c->stats.n_kmers = n_kmers;
+    c->stats.table_slots = slots;
+    // count matrices: dense [2][N][N] u64
+    uint64_t nn = 2ull * n_nodes * n_nodes;
+    VSPE_TRY(c->mats.reserve(nn ? nn : 1));
+    VSPE_CUDA(cudaMemsetAsync(c->mats.p, 0, (nn ? nn : 1) * 8, st));
+    VSPE_CUDA(cudaStreamSynchronize(st));
+    ix.built = true;
+    return VSPE_OK;
+}
+
+}  // namespace vspe

@@ -1,0 +1,232 @@
+// vspe_internal.cuh -- shared layouts and device helpers for libvspe.so (sm_100a only).
+//
+// Domain vocabulary follows the reference (utils/VStrains_PE_Inference.py): nodes (GFA
+// segments), (k+1)-mers of length split_len, postings (node ids per k-mer), read pairs,
+// node_mat / short_mat.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vspe.h"
+
+namespace vspe {
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define VSPE_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            vspe::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__),       \
+                            __FILE__, __LINE__, #call);                                   \
+            return VSPE_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define VSPE_TRY(call)                  \
+    do {                                \
+        int r__ = (call);               \
+        if (r__ != VSPE_OK) return r__; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Index layout in HBM (built by K3, read by K4)
+//
+//   text      2-bit packed bases, base j at bits [2(j&31), 2(j&31)+2) of word j>>5.
+//             Node i with len_i >= split_len contributes its forward strand at
+//             [strand_start[2i], strand_start[2i+1]) and its reverse complement at
+//             [strand_start[2i+1], strand_start[2i+2]).  Shorter nodes contribute nothing.
+//             Code = (ascii >> 1) & 3: A=0 C=1 T=2 G=3; complement = code ^ 2.
+//   slots     open-addressing (linear probing) table of 8-byte entries {tp, meta}:
+//             tp   = text position of one (k+1)-mer occurrence (0xFFFFFFFF = empty)
+//             meta = (fingerprint & ~node_mask) | node index
+//             Every occurrence of every (k+1)-mer of both strands is its own entry, so the
+//             entries whose text equals a query are exactly the reference's postings
+//             multiset (PE_Inference.py:117-135; palindromes appear twice because both
+//             strands are stored).
+//   uniq      1 bit per text position: the (k+1)-mer starting there has exactly one posting.
+// ---------------------------------------------------------------------------------------
+struct IndexView {
+    const uint64_t* text;
+    const uint32_t* strand_start;   // [2N+1]
+    const uint32_t* node_len;       // [N] full node length (also for nodes without k-mers)
+    const uint2* slots;
+    const uint32_t* uniq;           // bitmap over text positions
+    const uint32_t* succ;           // [2N][4] text position of the unique successor k-mer or NONE
+    uint32_t text_len;              // bases
+    uint32_t slot_mask;
+    uint32_t node_mask;             // (1 << nbits) - 1
+    uint32_t split_len;
+    uint32_t n_nodes;
+};
+
+static constexpr uint32_t EMPTY_TP = 0xFFFFFFFFu;
+static constexpr uint64_t EMPTY_SLOT = 0xFFFFFFFFFFFFFFFFull;
+static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+
+__host__ __device__ __forceinline__ uint64_t hash_mix(uint64_t h, uint64_t w) {
+    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+__host__ __device__ __forceinline__ uint64_t hash_final(uint64_t h) {
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    return h ^ (h >> 32);
+}
+static constexpr uint64_t HASH_SEED = 0x243F6A8885A308D3ull;
+
+// ascii -> 2-bit code; valid only for A,C,G,T (upper case)
+__host__ __device__ __forceinline__ uint32_t base_code(uint32_t c) { return (c >> 1) & 3u; }
+__host__ __device__ __forceinline__ bool is_acgt(uint32_t c) {
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
+
+#ifdef __CUDACC__
+// 32 bases (64 bits) starting at base offset b of a packed array (2 pad words required).
+__device__ __forceinline__ uint64_t extract64(const uint64_t* __restrict__ t, uint64_t b) {
+    uint64_t w = b >> 5;
+    uint32_t s = (uint32_t)(b & 31) * 2;
+    uint64_t lo = __ldg(t + w);
+    if (s == 0) return lo;
+    uint64_t hi = __ldg(t + w + 1);
+    return (lo >> s) | (hi << (64 - s));
+}
+
+__device__ __forceinline__ uint32_t text_base(const uint64_t* __restrict__ t, uint64_t b) {
+    return (uint32_t)(__ldg(t + (b >> 5)) >> ((b & 31) * 2)) & 3u;
+}
+
+// hash of the L-base window starting at base b of a packed array
+__device__ __forceinline__ uint64_t hash_packed(const uint64_t* __restrict__ t, uint64_t b, uint32_t L) {
+    uint64_t h = HASH_SEED;
+    for (uint32_t m = 0; m < L; m += 32) {
+        uint64_t w = extract64(t, b + m);
+        uint32_t rem = L - m;
+        if (rem < 32) w &= (1ull << (2 * rem)) - 1;
+        h = hash_mix(h, w);
+    }
+    return hash_final(h);
+}
+
+__device__ __forceinline__ uint32_t slot_of(uint64_t h, uint32_t mask) { return (uint32_t)(h >> 32) & mask; }
+__device__ __forceinline__ bool fp_match(uint32_t meta, uint64_t h, uint32_t node_mask) {
+    return (((uint32_t)h ^ meta) & ~node_mask) == 0;
+}
+
+// are the L-base windows at text positions a and b equal?
+__device__ __forceinline__ bool text_equal(const uint64_t* __restrict__ t, uint64_t a, uint64_t b, uint32_t L) {
+    for (uint32_t m = 0; m < L; m += 32) {
+        uint64_t x = extract64(t, a + m) ^ extract64(t, b + m);
+        uint32_t rem = L - m;
+        if (rem < 32) x &= (1ull << (2 * rem)) - 1;
+        if (x) return false;
+    }
+    return true;
+}
+
+// strand index q (0..2N-1) containing text position tp: largest q with strand_start[q] <= tp
+// among strands of non-zero length.
+__device__ __forceinline__ uint32_t strand_of(const uint32_t* __restrict__ ss, uint32_t n2, uint32_t tp) {
+    uint32_t lo = 0, hi = n2;     // invariant: ss[lo] <= tp < ss[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(ss + mid) <= tp) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
+// Per-read result written by K4 and read by K5: 64 bytes.
+//   hdr = status | n << 8      status: 0 mapped, 1 has 'N', 2 short
+//   n <= SLOT_IDS: ids[0..n) ascending node indices
+//   n >  SLOT_IDS: ids[0] = offset into the spill pool where the n ids live
+// ---------------------------------------------------------------------------------------
+static constexpr int SLOT_IDS = 15;
+struct __align__(64) ReadSlot {
+    uint32_t hdr;
+    uint32_t ids[SLOT_IDS];
+};
+static constexpr uint32_t ST_OK = 0, ST_N = 1, ST_SHORT = 2;
+
+// ---------------------------------------------------------------------------------------
+// simple owning device buffer
+// ---------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // grow to at least n elements (contents discarded unless keep)
+    int reserve(size_t n, bool keep = false, cudaStream_t st = 0) {
+        if (n <= cap) return VSPE_OK;
+        size_t ncap = n + n / 4 + 64;
+        T* q = nullptr;
+        VSPE_CUDA(cudaMalloc(&q, ncap * sizeof(T)));
+        if (keep && p && cap) {
+            VSPE_CUDA(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
+            VSPE_CUDA(cudaStreamSynchronize(st));
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = ncap;
+        return VSPE_OK;
+    }
+};
+
+struct Index {
+    DevBuf<uint64_t> text;
+    DevBuf<uint32_t> strand_start;
+    DevBuf<uint32_t> node_len;
+    DevBuf<uint2> slots;
+    DevBuf<uint32_t> uniq;
+    DevBuf<uint32_t> succ;
+    uint32_t text_len = 0, slot_mask = 0, node_mask = 0, split_len = 0, n_nodes = 0;
+    uint64_t n_kmers = 0;
+    bool built = false;
+    IndexView view() const {
+        IndexView v;
+        v.text = text.p; v.strand_start = strand_start.p; v.node_len = node_len.p;
+        v.slots = slots.p; v.uniq = uniq.p; v.succ = succ.p;
+        v.text_len = text_len; v.slot_mask = slot_mask; v.node_mask = node_mask;
+        v.split_len = split_len; v.n_nodes = n_nodes;
+        return v;
+    }
+};
+
+// per-mate record table produced by K1 for one chunk
+struct Records {
+    DevBuf<uint64_t> seq_start;   // chunk-relative byte offset of the 2nd line of each record
+    DevBuf<uint64_t> seq_end;     // one past its last content byte
+};
+
+struct Ctx;   // defined in api.cu
+
+// ---- kernels' host launchers (each returns VSPE_OK / error and counts its launches) ----
+int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len);
+
+// K1: count terminators / index records of a device buffer.
+int scan_count_lines(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms);
+int scan_index_records(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first,
+                       uint64_t n_slots, uint64_t* d_seq_start, uint64_t* d_seq_end);
+
+// K2+K4: map reads [0, n_reads) of a chunk into slots[rec_off + r]
+int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                      uint64_t n_reads, ReadSlot* d_slots);
+
+// K5+K6: pairs [0, total) of two slot arrays -> += into dense matrices
+int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total);
+
+}  // namespace vspe

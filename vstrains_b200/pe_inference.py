@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference's paired-end link inference script.
+
+Same names, flags, stdout lines, side effects and output files as reference
+``utils/VStrains_PE_Inference.py`` (``main()`` :51-211); the compute goes through the C ABI of
+``libvspe.so`` (CUDA, sm_100a).  There is no CPU path here: without the library or a B200 every
+call raises / exits non-zero.
+
+In-process API::
+
+    ids, node_mat, short_mat, stats = pe_inference(gfa, fwd, rve, kmer_size)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import os
+import sys
+import time
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import Stats, VspeError, check
+
+rev_dict = {"A": "T", "T": "A", "C": "G", "G": "C"}
+
+
+def reverse_seq(seq: str):
+    """Same contract as reference utils/VStrains_PE_Inference.py:12-13 (KeyError on non-ACGT).
+    Kept for API fidelity; the index build does this on the device."""
+    return "".join(rev_dict[x] for x in reversed(seq))
+
+
+def _u8(x) -> np.ndarray:
+    if isinstance(x, np.ndarray):
+        return np.ascontiguousarray(x.view(np.uint8).reshape(-1))
+    return np.frombuffer(bytes(x) if not isinstance(x, (bytes, bytearray, memoryview)) else x, dtype=np.uint8)
+
+
+def parse_gfa_nodes(gfa: bytes) -> Tuple[List[str], List[bytes]]:
+    """S lines of a GFA in file order -- reference :101-112 (text mode, ``Line[:-1].split('\\t')``)."""
+    ids, seqs = [], []
+    text = gfa.replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+    lines = text.split(b"\n")
+    terminated = text.endswith(b"\n")
+    if terminated:
+        lines.pop()
+    for n, line in enumerate(lines):
+        if not terminated and n == len(lines) - 1:
+            line = line[:-1]                      # `Line[:-1]` eats a real char of an unterminated last line
+        f = line.split(b"\t")
+        if f[0] == b"S":
+            if len(f) < 3:
+                raise VspeError(-4, "GFA S line with fewer than 3 fields")
+            ids.append(f[1].decode("ascii"))
+            seqs.append(f[2])
+    return ids, seqs
+
+
+class PEIndex:
+    """Device-resident (k+1)-mer index + count matrices for one graph (one GPU)."""
+
+    def __init__(self, seqs: Sequence[bytes], kmer_size: int, device: int = 0):
+        self._L = _lib.lib()
+        self._ctx = ctypes.c_void_p()
+        check(self._L.vspe_create(device, ctypes.byref(self._ctx)))
+        self.n_nodes = len(seqs)
+        self.split_len = kmer_size + 1
+        cat = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        if seqs:
+            off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+        try:
+            check(self._L.vspe_index_build(self._ctx, cat.ctypes.data if cat.size else None, off.ctypes.data,
+                                           self.n_nodes, self.split_len))
+        except Exception:
+            self.close()
+            raise
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._L.vspe_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, name: str, value: int):
+        check(self._L.vspe_set_option(self._ctx, name.encode(), int(value)))
+
+    def reset(self):
+        check(self._L.vspe_reset(self._ctx))
+
+    def count_host(self, fwd, rve):
+        f, r = _u8(fwd), _u8(rve)
+        check(self._L.vspe_count_host(self._ctx, f.ctypes.data if f.size else None, f.size,
+                                      r.ctypes.data if r.size else None, r.size))
+
+    def count_host_ptr(self, fptr: int, fn: int, rptr: int, rn: int):
+        check(self._L.vspe_count_host(self._ctx, fptr, fn, rptr, rn))
+
+    def count_device(self, fptr: int, fn: int, rptr: int, rn: int):
+        """fptr/rptr: device pointers (e.g. torch ``tensor.data_ptr()``) on this context's GPU."""
+        check(self._L.vspe_count_device(self._ctx, fptr, fn, rptr, rn))
+
+    def matrices(self) -> Tuple[np.ndarray, np.ndarray]:
+        n = self.n_nodes
+        node = np.zeros((n, n), dtype=np.uint64)
+        short = np.zeros((n, n), dtype=np.uint64)
+        check(self._L.vspe_matrices_host(self._ctx, node.ctypes.data, short.ctypes.data))
+        return node, short
+
+    def matrices_device(self) -> Tuple[int, int]:
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        check(self._L.vspe_matrices_device(self._ctx, ctypes.byref(p), ctypes.byref(n)))
+        return p.value or 0, n.value
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(self._L.vspe_get_stats(self._ctx, ctypes.byref(s)))
+        return s.as_dict()
+
+    def set_pair_counters(self, total, n, short, used):
+        check(self._L.vspe_set_pair_counters(self._ctx, total, n, short, used))
+
+    def map_reads(self, fq) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """-> (offsets[R+1], nodes, status[R]) for every complete record of one FASTQ buffer."""
+        b = _u8(fq)
+        nr, po, pn, ps = ctypes.c_uint64(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        check(self._L.vspe_map_reads(self._ctx, b.ctypes.data if b.size else None, b.size, ctypes.byref(nr),
+                                     ctypes.byref(po), ctypes.byref(pn), ctypes.byref(ps)))
+        R = nr.value
+        off = np.ctypeslib.as_array(ctypes.cast(po, ctypes.POINTER(ctypes.c_uint64)), (R + 1,)).copy()
+        nodes = np.ctypeslib.as_array(ctypes.cast(pn, ctypes.POINTER(ctypes.c_uint32)), (max(int(off[-1]), 1),)).copy()[:int(off[-1])]
+        status = np.ctypeslib.as_array(ctypes.cast(ps, ctypes.POINTER(ctypes.c_uint8)), (max(R, 1),)).copy()[:R] if R else np.zeros(0, np.uint8)
+        return off, nodes, status
+
+    def split_records(self, fq) -> Tuple[int, np.ndarray, np.ndarray]:
+        b = _u8(fq)
+        nl, nr, ps, pl = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_void_p(), ctypes.c_void_p()
+        check(self._L.vspe_split_records(self._ctx, b.ctypes.data if b.size else None, b.size, ctypes.byref(nl),
+                                         ctypes.byref(nr), ctypes.byref(ps), ctypes.byref(pl)))
+        R = nr.value
+        if R == 0:
+            return nl.value, np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+        st = np.ctypeslib.as_array(ctypes.cast(ps, ctypes.POINTER(ctypes.c_uint64)), (R,)).copy()
+        ln = np.ctypeslib.as_array(ctypes.cast(pl, ctypes.POINTER(ctypes.c_uint32)), (R,)).copy()
+        return nl.value, st, ln
+
+
+def pe_inference(gfa: bytes, fwd, rve, kmer_size: int, device: int = 0, options: Optional[dict] = None):
+    """In-memory equivalent of the reference script: -> (ids, node_mat, short_mat, stats)."""
+    ids, seqs = parse_gfa_nodes(gfa)
+    with PEIndex(seqs, kmer_size, device) as ix:
+        for k, v in (options or {}).items():
+            ix.set_option(k, v)
+        ix.count_host(fwd, rve)
+        node, short = ix.matrices()
+        return ids, node, short, ix.stats()
+
+
+def write_info(path: str, ids: Sequence[str], mat: np.ndarray):
+    """Dense ``id_i:id_j:count`` writer (reference :194-207) through the C ABI."""
+    n = len(ids)
+    arr = (ctypes.c_char_p * max(n, 1))(*[i.encode() for i in ids])
+    m = np.ascontiguousarray(mat, dtype=np.uint64)
+    check(_lib.lib().vspe_write_info(path.encode(), arr, n, m.ctypes.data if n else None))
+
+
+def single_end_read_mapping(seq: str, kmer_htable, index2seqlen: list, split_len: int, len_index2id: int):
+    """API-fidelity shim for reference :16-48.  ``kmer_htable`` must be a :class:`PEIndex`
+    (the device index); the Python dict of the reference is not accepted because this package
+    has no CPU path."""
+    if not isinstance(kmer_htable, PEIndex):
+        raise TypeError("kmer_htable must be a vstrains_b200.pe_inference.PEIndex (device index)")
+    fq = ("@q\n%s\n+\n%s\n" % (seq, "I" * len(seq))).encode()
+    off, nodes, status = kmer_htable.map_reads(fq)
+    return [int(x) for x in nodes[off[0]:off[1]]] if status[0] == 0 else []
+
+
+def main(argv: Optional[Sequence[str]] = None):
+    print("----------------------Paired-End Information Alignment----------------------")
+    parser = argparse.ArgumentParser(prog="pe_info",
+                                     description="""Align Paired-End reads to nodes in graph to obtain strong links""")
+    parser.add_argument("-g", "--gfa,", dest="gfa", type=str, required=True, help="graph, .gfa format")
+    parser.add_argument("-o", "--output_dir", dest="dir", type=str, required=True, help="output directory")
+    parser.add_argument("-f", "--forward", dest="fwd", required=True, help="forward read, .fastq")
+    parser.add_argument("-r", "--reverse", dest="rve", required=True, help="reverse read, .fastq")
+    parser.add_argument("-k", "--kmer_size", dest="kmer_size", type=int, default=128, help="unique kmer size")
+    parser.add_argument("--gpus", dest="gpus", type=int, default=int(os.environ.get("VSPE_GPUS", "1")),
+                        help="GPUs of this box to shard read pairs over (env VSPE_GPUS)")
+    args = parser.parse_args(argv)
+    glb_start = time.time()
+    print("Start aligning reads to gfa nodes")
+    st = Stats()
+    L = _lib.lib()
+    check(L.vspe_run(args.gfa.encode(), args.fwd.encode(), args.rve.encode(), args.kmer_size, args.dir.encode(),
+                     args.gpus, ctypes.byref(st)))
+    out_dir = args.dir[:-1] if args.dir.endswith("/") else args.dir
+    print("Number of processed reads: ", st.total_pairs)
+    print("pairs used / with N / too short: ", st.used_pairs, st.n_pairs, st.short_pairs)
+    print("Global time elapsed: ", time.time() - glb_start)
+    print("result stored in: ", "{0}/pe_info".format(out_dir))
+
+
+if __name__ == "__main__":
+    try:
+        main()
+    except VspeError as e:
+        print(str(e), file=sys.stderr)
+        sys.exit(1)
+    sys.exit(0)
