@@ -447,7 +447,7 @@ int vspe_get_stats(vspe_ctx* c, vspe_stats* out) {
         c->stats.used_pairs = h[CNT_USED];
     }
     c->stats.n_keys = h[CNT_KEYS];
-    c->stats.reads_fast = h[CNT_FAST];
+    c->stats.reads_fast = h[CNT_FAST] - h[CNT_BAILED];
     c->stats.reads_generic = h[CNT_GENERIC];
     c->stats.kernel_launches = c->launches;
     *out = c->stats;

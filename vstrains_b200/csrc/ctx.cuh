@@ -11,6 +11,7 @@ enum Counter {
     CNT_ERR,                 // error bit flags raised by kernels
     CNT_FAST, CNT_GENERIC,   // reads resolved per tier
     CNT_WORK,                // generic-tier worklist length
+    CNT_BAILED,              // reads the fast tier handed to the exhaustive tier
     CNT_COUNT_
 };
 static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4;
@@ -37,6 +38,7 @@ struct Ctx {
     DevBuf<uint32_t> warp_scratch;
     bool scratch_valid = false;       // warp_scratch initialised for the current index
     DevBuf<uint32_t> spill;
+    DevBuf<uint32_t> worklist;
     // K5/K6 scratch
     DevBuf<uint32_t> keys;
     DevBuf<unsigned long long> bucket;   // [3][n_buckets + 1]: histogram, start, cursor

@@ -25,13 +25,14 @@ __device__ __forceinline__ bool keep_node(uint32_t v, uint32_t kmin, uint32_t le
 
 __global__ void __launch_bounds__(MG_WARPS * 32)
 k_map_generic(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
-              const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ worklist, uint64_t n_items,
-              ReadSlot* __restrict__ slots, uint32_t* __restrict__ scratch, uint64_t scratch_stride,
+              const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ worklist, uint64_t n_items_arg,
+              const unsigned long long* __restrict__ n_items_dev, ReadSlot* __restrict__ slots, uint32_t* __restrict__ scratch, uint64_t scratch_stride,
               uint32_t* __restrict__ spill, uint64_t spill_cap, unsigned long long* __restrict__ counters) {
     __shared__ uint32_t s_ntouch[MG_WARPS];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t gwarp = (uint64_t)blockIdx.x * MG_WARPS + wib, nwarps = (uint64_t)gridDim.x * MG_WARPS;
     const uint32_t N = ix.n_nodes, L = ix.split_len;
+    const uint64_t n_items = n_items_dev ? *n_items_dev : n_items_arg;
     uint32_t* v = scratch + gwarp * scratch_stride;
     uint32_t* kmin = v + N;
     uint32_t* list = kmin + N;            // [TOUCH_CAP] unsorted, then [N + ...] sorted / compacted
@@ -154,8 +155,10 @@ k_map_generic(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __r
         }
         __syncwarp();
     }
-    if (threadIdx.x == 0 && blockIdx.x == 0 && worklist == nullptr)
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
         atomicAdd(&counters[CNT_GENERIC], (unsigned long long)n_items);
+        if (worklist) atomicAdd(&counters[CNT_BAILED], (unsigned long long)n_items);
+    }
 }
 
 __global__ void k_fill_u32(uint32_t* p, uint64_t n, uint32_t val) {
@@ -182,27 +185,27 @@ static int prepare_scratch(Ctx* c, uint32_t n_blocks, uint64_t* stride_out) {
     return VSPE_OK;
 }
 
-static uint32_t generic_blocks(Ctx* c, uint64_t n_items) {
-    uint64_t want = (n_items + MG_WARPS - 1) / MG_WARPS;
+// Grid of the exhaustive tier: fixed per index (the scratch layout depends on it), bounded so the
+// per-warp scratch (3N u32) stays within a few GiB for very large graphs.
+static uint32_t generic_blocks(Ctx* c) {
     uint64_t cap = (uint64_t)c->sm_count * 8;
-    // bound scratch for very large graphs (3N u32 per warp)
     uint64_t per_block = (3ull * c->index.n_nodes + 2 * TOUCH_CAP + 32) * MG_WARPS * 4;
     uint64_t budget = 8ull << 30;
     if (per_block * cap > budget) cap = budget / per_block ? budget / per_block : 1;
-    return (uint32_t)(want < cap ? (want ? want : 1) : cap);
+    return (uint32_t)cap;
 }
 
 int map_reads_generic_list(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                            const uint32_t* d_worklist, uint64_t n_items, ReadSlot* d_slots) {
     if (n_items == 0) return VSPE_OK;
     // the scratch layout depends on the grid, so keep the grid fixed per context size class
-    uint32_t nb = generic_blocks(c, ~0ull);
+    uint32_t nb = generic_blocks(c);
     uint64_t stride;
     VSPE_TRY(prepare_scratch(c, nb, &stride));
     if (!c->spill.p) VSPE_TRY(c->spill.reserve(4u << 20));
     uint64_t want = (n_items + MG_WARPS - 1) / MG_WARPS;
     uint32_t grid = (uint32_t)(want < nb ? want : nb);
-    k_map_generic<<<grid, MG_WARPS * 32, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, d_worklist, n_items,
+    k_map_generic<<<grid, MG_WARPS * 32, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, d_worklist, n_items, nullptr,
                                                          d_slots, c->warp_scratch.p, stride, c->spill.p, c->spill.cap, c->counters.p);
     VSPE_LAUNCH_CHECK(c);
     return VSPE_OK;
@@ -213,10 +216,17 @@ int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start,
     return map_reads_generic_list(c, d_buf, d_seq_start, d_seq_end, nullptr, n_reads, d_slots);
 }
 
-// until the seed-and-extend tier is linked in, every read takes the exhaustive tier
-__attribute__((weak)) int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
-                   uint64_t n_reads, ReadSlot* d_slots) {
-    return map_reads_generic(c, d_buf, d_seq_start, d_seq_end, n_reads, d_slots);
+// worklist whose length lives on the device (no host round trip): a modest persistent grid
+int map_reads_generic_dev(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                          const uint32_t* d_worklist, const unsigned long long* d_n_items, ReadSlot* d_slots) {
+    uint32_t nb = generic_blocks(c);
+    uint64_t stride;
+    VSPE_TRY(prepare_scratch(c, nb, &stride));
+    if (!c->spill.p) VSPE_TRY(c->spill.reserve(4u << 20));
+    k_map_generic<<<nb, MG_WARPS * 32, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, d_worklist, 0, d_n_items,
+                                                       d_slots, c->warp_scratch.p, stride, c->spill.p, c->spill.cap, c->counters.p);
+    VSPE_LAUNCH_CHECK(c);
+    return VSPE_OK;
 }
 
 }  // namespace vspe
