@@ -249,11 +249,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ---------------------------------------------------------
-    for _ in range(warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)           # samples across warm-up + timed region (steps are ms-short)
     sampler.start()
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < warmup or time.perf_counter() - t_w < 1.0:     # >= W steps and >= 1 s under load
+        step_device()
+        n_w += 1
+    barrier()
     stage = {"ms_scan": 0.0, "ms_map": 0.0, "ms_count": 0.0, "ms_total": 0.0}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

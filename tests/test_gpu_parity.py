@@ -57,8 +57,10 @@ def test_cli_drop_in_writes_identical_files(golden, tmp_path):
     assert b"Paired-End Information Alignment" in p.stdout
 
 
-def test_record_split_matches_universal_newlines(golden):
+@pytest.mark.parametrize("two_pass", [0, 1])
+def test_record_split_matches_universal_newlines(golden, two_pass):
     with pe_inference.PEIndex([b"ACGTACGTAC"], 3) as ix:
+        ix.set_option("scan_two_pass", two_pass)
         for fq in (golden.fwd, golden.rve):
             n_lines, start, length = ix.split_records(fq)
             lines = pe_oracle.split_lines(fq)
@@ -70,11 +72,14 @@ def test_record_split_matches_universal_newlines(golden):
                 assert text[int(start[r]):int(start[r]) + int(length[r])] == seq
 
 
-def test_record_split_edge_cases():
-    cases = [b"", b"\n", b"\r", b"\r\n", b"a", b"a\nb\nc\nd", b"a\nb\nc\nd\n", b"\n\n\n\n\n\n\n\n",
+@pytest.mark.parametrize("two_pass", [0, 1])
+def test_record_split_edge_cases(two_pass):
+    cases = [b"\n" * 70000, b"a\n" * 40000, (b"@r\nAC\n+\nII\n" * 9000)[:-1],
+             b"", b"\n", b"\r", b"\r\n", b"a", b"a\nb\nc\nd", b"a\nb\nc\nd\n", b"\n\n\n\n\n\n\n\n",
              b"@h\r\nAC\r\n+\r\nII\r\n@h\rGT\r+\rII\r", b"@h\nACGT\r\r\n+\nIIII\n", b"x" * 100000 + b"\n" + b"ACGT\n+\nIIII\n" * 3,
              b"@a\nAC" + b"G" * 70000 + b"\n+\n" + b"I" * 70002 + b"\n"]
     with pe_inference.PEIndex([b"ACGTACGTAC"], 3) as ix:
+        ix.set_option("scan_two_pass", two_pass)
         for fq in cases:
             n_lines, start, length = ix.split_records(fq)
             lines = pe_oracle.split_lines(fq)
@@ -119,14 +124,16 @@ def test_chunked_streaming_equals_single_chunk():
     g, f, r = synth.generate(cfg, pairs=9000)
     ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())
     res = []
-    for chunk_mb in (256, 1):
+    for chunk_mb, two_pass in ((256, 0), (1, 0), (1, 1)):
         with pe_inference.PEIndex(seqs, cfg.k) as ix:
             ix.set_option("chunk_mb", chunk_mb)
+            ix.set_option("scan_two_pass", two_pass)
             ix.count_host(f, r)
             res.append(ix.matrices() + (ix.stats(),))
-    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
-    for k in ("total_pairs", "n_pairs", "short_pairs", "used_pairs", "n_keys"):
-        assert res[0][2][k] == res[1][2][k]
+    for other in res[1:]:
+        assert np.array_equal(res[0][0], other[0]) and np.array_equal(res[0][1], other[1])
+        for k in ("total_pairs", "n_pairs", "short_pairs", "used_pairs", "n_keys"):
+            assert res[0][2][k] == other[2][k]
 
 
 def test_counts_accumulate_over_calls_and_shards_sum_exactly():

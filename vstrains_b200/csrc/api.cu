@@ -61,14 +61,32 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     uint64_t n_terms = 0;
     cudaEvent_t e0 = c->ev[2], e1 = c->ev[3], e2 = c->ev[4];
     VSPE_CUDA(cudaEventRecord(e0, c->stream));
-    VSPE_TRY(scan_count_lines(c, d_buf, n, &n_terms));
     const uint64_t lb = ms.line_base;
     const uint64_t rec_first = seq_lines_before(lb);
-    const uint64_t n_seq = seq_lines_before(lb + n_terms) - rec_first;
-    VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
-    VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
+    uint64_t n_seq = 0;
+    if (c->opt_scan_two_pass) {
+        VSPE_TRY(scan_count_lines(c, d_buf, n, &n_terms));
+        n_seq = seq_lines_before(lb + n_terms) - rec_first;
+        VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
+        VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
+        VSPE_TRY(scan_index_records(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p));
+    } else {
+        // one pass with a guessed table size (a FASTQ record is rarely under 48 bytes); if the
+        // guess was too small the pass is repeated once with the exact size
+        uint64_t guess = n / 48 + 1024;
+        bool overflow = false;
+        VSPE_TRY(mb.rec.seq_start.reserve(guess + 2));
+        VSPE_TRY(mb.rec.seq_end.reserve(guess + 2));
+        VSPE_TRY(scan_records_single_pass(c, d_buf, n, lb, rec_first, mb.rec.seq_start.cap - 2, mb.rec.seq_start.p, mb.rec.seq_end.p,
+                                          &n_terms, &overflow));
+        n_seq = seq_lines_before(lb + n_terms) - rec_first;
+        if (overflow) {
+            VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
+            VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
+            VSPE_TRY(scan_records_single_pass(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p, &n_terms, &overflow));
+        }
+    }
     VSPE_TRY(mb.slots.reserve(rec_first + n_seq + 1, true, c->stream));
-    VSPE_TRY(scan_index_records(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p));
     VSPE_CUDA(cudaEventRecord(e1, c->stream));
     if (n_seq) {
         if (c->opt_force_generic)
@@ -125,6 +143,24 @@ static uint64_t cut_at_line(const uint8_t* p, uint64_t lo, uint64_t hi, uint64_t
         i--;
     }
     return lo;
+}
+
+// Longest 2nd-line length among the first records of a FASTQ prefix (sizes the packed rows of
+// the seed-and-extend tier; a wrong hint only sends longer reads to the exhaustive tier).
+static uint32_t seq_len_hint(const uint8_t* p, uint64_t n) {
+    uint64_t line = 0, start = 0, best = 0;
+    for (uint64_t i = 0; i < n && line < 64; i++) {
+        uint8_t c = p[i];
+        bool term = c == '\n' || (c == '\r' && !(i + 1 < n && p[i + 1] == '\n'));
+        if (!term) continue;
+        if ((line & 3) == 1) {
+            uint64_t e = (c == '\n' && i > start && p[i - 1] == '\r') ? i - 1 : i;
+            best = std::max(best, e - start);
+        }
+        line++;
+        start = i + 1;
+    }
+    return (uint32_t)std::min<uint64_t>(best, 1u << 20);
 }
 
 static void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t n) {
@@ -377,16 +413,24 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
     const uint8_t* bufs[2] = {d_fwd, d_rve};
     uint64_t ns[2] = {n_fwd, n_rve};
     MateStream* ms[2] = {&f, &r};
-    for (int m = 0; m < 2; m++) {
-        int last = -1;
-        if (ns[m]) {
+    int last[2] = {-1, -1};
+    uint32_t hint = 0;
+    {   // one small D2H per mate: its last byte (does the file end with a terminator?) and a
+        // prefix to size the packed rows
+        std::vector<uint8_t> head(16384);
+        for (int m = 0; m < 2; m++) {
+            if (!ns[m]) continue;
             uint8_t b = 0;
+            uint64_t hn = std::min<uint64_t>(ns[m], head.size());
             VSPE_CUDA(cudaMemcpyAsync(&b, bufs[m] + ns[m] - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+            VSPE_CUDA(cudaMemcpyAsync(head.data(), bufs[m], hn, cudaMemcpyDeviceToHost, c->stream));
             VSPE_CUDA(cudaStreamSynchronize(c->stream));
-            last = b;
+            last[m] = b;
+            hint = std::max(hint, seq_len_hint(head.data(), hn));
         }
-        VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last));
     }
+    c->read_len_hint = hint;
+    for (int m = 0; m < 2; m++) VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last[m]));
     VSPE_TRY(finish_pairs(c, f, r));
     VSPE_CUDA(cudaEventRecord(t1, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
@@ -405,6 +449,7 @@ int vspe_count_host(vspe_ctx* c, const uint8_t* fwd, uint64_t n_fwd, const uint8
     cudaEvent_t t0 = c->ev[7];
     VSPE_CUDA(cudaEventRecord(t0, c->stream));
     MateStream f, r;
+    c->read_len_hint = std::max(seq_len_hint(fwd, std::min<uint64_t>(n_fwd, 16384)), seq_len_hint(rve, std::min<uint64_t>(n_rve, 16384)));
     VSPE_TRY(stream_mate_host(c, 0, f, fwd, n_fwd));
     VSPE_TRY(stream_mate_host(c, 1, r, rve, n_rve));
     VSPE_TRY(finish_pairs(c, f, r));
@@ -474,13 +519,26 @@ int vspe_split_records(vspe_ctx* c, const uint8_t* fq, uint64_t n_bytes, uint64_
     if (n_bytes) {
         VSPE_TRY(c->dev_in[0].reserve(n_bytes + 64));
         VSPE_CUDA(cudaMemcpyAsync(c->dev_in[0].p, fq, n_bytes, cudaMemcpyHostToDevice, c->stream));
-        uint64_t n_terms = 0;
-        VSPE_TRY(scan_count_lines(c, c->dev_in[0].p, n_bytes, &n_terms));
-        uint64_t n_seq = seq_lines_before(n_terms);
+        uint64_t n_terms = 0, n_seq = 0;
         Records& rec = c->mate[0].rec;
-        VSPE_TRY(rec.seq_start.reserve(n_seq + 2));
-        VSPE_TRY(rec.seq_end.reserve(n_seq + 2));
-        VSPE_TRY(scan_index_records(c, c->dev_in[0].p, n_bytes, 0, 0, n_seq, rec.seq_start.p, rec.seq_end.p));
+        if (c->opt_scan_two_pass) {
+            VSPE_TRY(scan_count_lines(c, c->dev_in[0].p, n_bytes, &n_terms));
+            n_seq = seq_lines_before(n_terms);
+            VSPE_TRY(rec.seq_start.reserve(n_seq + 2));
+            VSPE_TRY(rec.seq_end.reserve(n_seq + 2));
+            VSPE_TRY(scan_index_records(c, c->dev_in[0].p, n_bytes, 0, 0, n_seq, rec.seq_start.p, rec.seq_end.p));
+        } else {
+            bool overflow = false;
+            VSPE_TRY(rec.seq_start.reserve(n_bytes / 48 + 1026));
+            VSPE_TRY(rec.seq_end.reserve(n_bytes / 48 + 1026));
+            VSPE_TRY(scan_records_single_pass(c, c->dev_in[0].p, n_bytes, 0, 0, rec.seq_start.cap - 2, rec.seq_start.p, rec.seq_end.p, &n_terms, &overflow));
+            n_seq = seq_lines_before(n_terms);
+            if (overflow) {
+                VSPE_TRY(rec.seq_start.reserve(n_seq + 2));
+                VSPE_TRY(rec.seq_end.reserve(n_seq + 2));
+                VSPE_TRY(scan_records_single_pass(c, c->dev_in[0].p, n_bytes, 0, 0, n_seq, rec.seq_start.p, rec.seq_end.p, &n_terms, &overflow));
+            }
+        }
         bool term = fq[n_bytes - 1] == '\n' || fq[n_bytes - 1] == '\r';
         lines = n_terms + (term ? 0 : 1);
         recs = lines / 4;
@@ -508,6 +566,7 @@ int vspe_map_reads(vspe_ctx* c, const uint8_t* fq, uint64_t n_bytes, uint64_t* n
     VSPE_TRY(require_index(c));
     begin_call(c);
     MateStream ms;
+    c->read_len_hint = seq_len_hint(fq, std::min<uint64_t>(n_bytes, 16384));
     VSPE_TRY(stream_mate_host(c, 0, ms, fq, n_bytes));
     VSPE_TRY(check_kernel_errors(c));
     uint64_t recs = ms.lines / 4;
@@ -643,6 +702,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     if (!c || !name) { set_error("bad arguments"); return VSPE_ERR_ARG; }
     if (!strcmp(name, "force_generic")) c->opt_force_generic = value;
     else if (!strcmp(name, "chunk_mb")) c->opt_chunk_mb = value;
+    else if (!strcmp(name, "scan_two_pass")) c->opt_scan_two_pass = value;
     else { set_error("unknown option %s", name); return VSPE_ERR_ARG; }
     return VSPE_OK;
 }

@@ -14,7 +14,7 @@ enum Counter {
     CNT_BAILED,              // reads the fast tier handed to the exhaustive tier
     CNT_COUNT_
 };
-static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4;
+static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8;
 
 struct MateBuf {
     Records rec;
@@ -55,6 +55,8 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_scan_two_pass = 0;     // K1 as count + index passes (cross-check of the look-back kernel)
+    uint32_t read_len_hint = 320;      // longest sequence line among the first records of the input
     // accounting
     vspe_stats stats = {};
     bool stats_overridden = false;

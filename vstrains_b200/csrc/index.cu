@@ -81,7 +81,8 @@ k_index_unique(IndexView ix, uint32_t* __restrict__ uniq, uint32_t n_words) {
 }
 
 // --- successor table: for the last window of every strand and every next base b, the text
-// position of the k-mer (window[1:] + b) if it has exactly one posting, else NONE32.
+// position and node {tp, node} of the k-mer (window[1:] + b) if it has exactly one posting,
+// else {NONE32, 0}.
 // This is a precomputed table lookup, so it is exact for any graph, not only de Bruijn ones.
 __global__ void __launch_bounds__(128)
 k_index_succ(IndexView ix, uint32_t* __restrict__ succ) {
@@ -90,23 +91,22 @@ k_index_succ(IndexView ix, uint32_t* __restrict__ succ) {
     if (q >= 2 * ix.n_nodes) return;
     uint32_t s0 = ix.strand_start[q], s1 = ix.strand_start[q + 1];
     uint32_t L = ix.split_len;
-    uint32_t res = NONE32;
+    uint32_t res = NONE32, res_node = 0;
     if (s1 - s0 >= L) {
         uint64_t from = (uint64_t)s1 - L + 1;        // last L-1 bases of the strand
-        uint64_t h = HASH_SEED;
+        KmerHash hs;
         for (uint32_t m = 0; m < L; m += 32) {
             uint64_t w = extract64(ix.text, from + m);
             uint32_t rem = L - m;                     // bases of the query in this word
             // position L-1 of the query is the appended base b
             if (rem <= 32) {
-                uint64_t keep = (rem - 1 < 32) ? ((rem - 1 == 0) ? 0ull : ((1ull << (2 * (rem - 1))) - 1)) : ~0ull;
+                uint64_t keep = rem - 1 == 0 ? 0ull : ((1ull << (2 * (rem - 1))) - 1);
                 w = (w & keep) | ((uint64_t)b << (2 * (rem - 1)));
-                if (rem < 32) w &= (1ull << (2 * rem)) - 1;
             }
-            h = hash_mix(h, w);
+            hs.add64(w, rem);
         }
-        h = hash_final(h);
-        uint32_t cnt = 0, found = NONE32;
+        const uint64_t h = hs.finish();
+        uint32_t cnt = 0, found = NONE32, found_node = 0;
         uint32_t j = slot_of(h, ix.slot_mask);
         while (true) {
             uint2 e = __ldg(ix.slots + j);
@@ -114,13 +114,14 @@ k_index_succ(IndexView ix, uint32_t* __restrict__ succ) {
             if (fp_match(e.y, h, ix.node_mask)) {
                 // compare L-1 overlap bases, then the appended base
                 bool eq = text_equal(ix.text, e.x, from, L - 1) && text_base(ix.text, (uint64_t)e.x + L - 1) == b;
-                if (eq) { cnt++; found = e.x; }
+                if (eq) { cnt++; found = e.x; found_node = e.y & ix.node_mask; }
             }
             j = (j + 1) & ix.slot_mask;
         }
-        if (cnt == 1) res = found;
+        if (cnt == 1) { res = found; res_node = found_node; }
     }
-    succ[t] = res;
+    succ[2 * t] = res;
+    succ[2 * t + 1] = res_node;
 }
 
 int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len) {
@@ -165,7 +166,7 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
     VSPE_TRY(ix.node_len.reserve(h_len.size()));
     VSPE_TRY(ix.slots.reserve(slots));
     VSPE_TRY(ix.uniq.reserve(n_words));
-    VSPE_TRY(ix.succ.reserve(8 * (size_t)n_nodes + 8));
+    VSPE_TRY(ix.succ.reserve(16 * (size_t)n_nodes + 16));
     DevBuf<uint8_t> d_seqs;
     DevBuf<uint64_t> d_off;
     uint64_t seq_bytes = n_nodes ? seq_off[n_nodes] : 0;

@@ -16,11 +16,20 @@
 //   * bail:    a verified posting without the uniq bit (repeat / palindrome), a non-ACGT
 //              character, more than MAXN distinct nodes or a read longer than the packed
 //              capacity sends the read to the exhaustive tier.
-// Windows that miss (sequencing errors) are probed one by one, exactly like the reference.
+// A sequencing error breaks the chain.  Pass A walks the read left to right until its first
+// unknown window uA; pass B walks the REVERSE COMPLEMENT of the read (same code, same tables:
+// both strands of every node are indexed) from the other end down to its first unknown
+// window.  What is left in between -- normally exactly the windows covering the erroneous
+// base -- is probed by the whole warp cooperatively (phase 3); all of them must miss, as they
+// do for the reference, otherwise the read goes to the exhaustive tier.
 //
-// Phase 1 (K2): each warp packs 32 reads to 2 bits/base in shared memory with coalesced loads,
-//               flagging 'N' (upper case: PE_Inference.py:160) and other non-ACGT bytes.
-// Phase 2 (K4): one thread per read.
+// Phase 1 (K2): half-warps pack reads (and their reverse complements) to 2 bits/base in
+//               shared memory with coalesced loads, flagging 'N' (upper case:
+//               PE_Inference.py:160) and other non-ACGT bytes.
+// Phase 2 (K4): one thread per read, passes A and B.
+// Phase 3:      warp-cooperative confirmation probes of the unknown windows (one range at a
+//               time, 32 windows per step).
+// Phase 4:      one thread per read: sort by node index, saturation predicate, write the slot.
 #include "ctx.cuh"
 
 namespace vspe {
@@ -44,14 +53,17 @@ __device__ __forceinline__ uint64_t read64(const uint32_t* row, uint32_t b) {
 }
 
 __device__ __forceinline__ uint64_t hash_read(const uint32_t* row, uint32_t b, uint32_t L) {
-    uint64_t h = HASH_SEED;
-    for (uint32_t m = 0; m < L; m += 32) {
-        uint64_t w = read64(row, b + m);
-        uint32_t rem = L - m;
-        if (rem < 32) w &= (1ull << (2 * rem)) - 1;
-        h = hash_mix(h, w);
+    const uint32_t w0 = b >> 4, sh = (b & 15) * 2, n = (L + 15) >> 4;
+    KmerHash hs;
+    uint32_t x0 = row[w0];
+    for (uint32_t m = 0; m < n; m++) {
+        const uint32_t x1 = row[w0 + m + 1];
+        uint32_t v = __funnelshift_r(x0, x1, sh);
+        if (m == n - 1 && (L & 15)) v &= (1u << (2 * (L & 15))) - 1;
+        hs.add(v);
+        x0 = x1;
     }
-    return hash_final(h);
+    return hs.finish();
 }
 
 __device__ __forceinline__ bool read_equals_text(const uint32_t* row, uint32_t b, const uint64_t* __restrict__ text,
@@ -97,13 +109,97 @@ __device__ __forceinline__ uint32_t uniq_run(const uint32_t* __restrict__ uniq, 
 
 enum { PROBE_MISS = 0, PROBE_UNIQUE = 1, PROBE_MULTI = 2 };
 
-template <int STRIDE>
+// probe window b of a packed row: MISS, the UNIQUE posting, or MULTI (several postings)
+__device__ __forceinline__ int probe_window(const IndexView& ix, const uint32_t* row, uint32_t b, uint32_t& tp, uint32_t& node) {
+    const uint32_t L = ix.split_len;
+    const uint64_t h = hash_read(row, b, L);
+    uint32_t j = slot_of(h, ix.slot_mask);
+    while (true) {
+        const uint2 ent = __ldg(ix.slots + j);
+        if (ent.x == EMPTY_TP) return PROBE_MISS;
+        if (fp_match(ent.y, h, ix.node_mask) && read_equals_text(row, b, ix.text, ent.x, L)) {
+            tp = ent.x;
+            node = ent.y & ix.node_mask;
+            return ((__ldg(ix.uniq + (ent.x >> 5)) >> (ent.x & 31)) & 1) ? PROBE_UNIQUE : PROBE_MULTI;
+        }
+        j = (j + 1) & ix.slot_mask;
+    }
+}
+
+// add `hits` windows of `node` (smallest read position kminc) to the node list of read t
+__device__ __forceinline__ bool list_add(uint32_t (*s_node)[MF_THREADS], uint32_t (*s_vk)[MF_THREADS], uint32_t t,
+                                         uint32_t& nn, uint32_t node, uint32_t hits, uint32_t kminc) {
+    uint32_t a = 0;
+    for (; a < nn; a++) if (s_node[a][t] == node) break;
+    if (a == nn) {
+        if (nn == MAXN) return false;
+        s_node[a][t] = node;
+        s_vk[a][t] = hits | (kminc << 16);
+        nn++;
+    } else {
+        const uint32_t old = s_vk[a][t];
+        s_vk[a][t] = ((old & 0xFFFF) + hits) | (min(old >> 16, kminc) << 16);
+    }
+    return true;
+}
+
+// One directional pass over windows [0, limit) of a packed row.  Returns the first window whose
+// status is unknown (== limit when everything was resolved).  mirror: the row is the reverse
+// complement, so window i of the row is window npos-1-i of the read (only kmin needs that).
+__device__ __forceinline__ uint32_t run_pass(const IndexView& ix, const uint32_t* row, uint32_t rlen, uint32_t limit,
+                                             bool mirror, uint32_t npos, uint32_t (*s_node)[MF_THREADS],
+                                             uint32_t (*s_vk)[MF_THREADS], uint32_t t, uint32_t& nn, bool& bail) {
+    // (node list of read t: s_node[0..nn)[t], s_vk = hits | kmin << 16)
+    const uint32_t L = ix.split_len;
+    uint32_t i = 0;
+    uint32_t tp = NONE32, node = 0;
+    while (i < limit) {
+        if (tp == NONE32) {
+            const int res = probe_window(ix, row, i, tp, node);
+            if (res == PROBE_MULTI) { bail = true; return limit; }
+            if (res == PROBE_MISS) return i + 1;              // window i is a confirmed miss
+        }
+        // ---- extend along the node strand ----
+        const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
+        const bool rcs = tp >= s1;
+        const uint32_t q = 2 * node + (rcs ? 1u : 0u);
+        const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
+        const uint32_t room_t = send - (tp + L), room_r = rlen - (i + L);
+        const uint32_t max_ext = min(room_t, room_r);
+        const uint32_t ext = match_len(row, i + L, ix.text, tp + L, max_ext);
+        if (ext) {
+            if (uniq_run(ix.uniq, tp + 1, ext) < ext) { bail = true; return limit; }   // repeat inside the match
+        }
+        uint32_t hits = 1 + ext;
+        if (i + hits > limit) hits = limit - i;               // pass B must not re-count pass A's windows
+        const uint32_t kminc = mirror ? npos - i - hits : i;
+        if (!list_add(s_node, s_vk, t, nn, node, hits, kminc)) { bail = true; return limit; }
+        i += hits;
+        if (i >= limit) break;
+        if (ext < max_ext) return i;                          // mismatch inside the strand: unknown from here
+        if (ext == room_t) {
+            // the strand ended exactly here: successor for the read's next base, if unique
+            const uint32_t nb = i + L - 1;
+            const uint32_t b = (row[nb >> 4] >> ((nb & 15) * 2)) & 3u;
+            const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
+            tp = sc.x;
+            node = sc.y;
+        } else {
+            tp = NONE32;                                      // (unreachable: ext == room_r means i == npos)
+        }
+    }
+    return limit;
+}
+
+template <int STRIDE, int LPR>
 __global__ void __launch_bounds__(MF_THREADS)
 k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
            const uint64_t* __restrict__ seq_end, uint64_t n_reads, ReadSlot* __restrict__ slots,
            uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters) {
     constexpr uint32_t CAP = (STRIDE - 3) * 16;                   // bases per packed row
-    __shared__ uint32_t s_read[MF_THREADS * STRIDE];
+    constexpr uint32_t GROUPS = 32 / LPR;                          // reads packed per warp step
+    __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
+    __shared__ uint32_t s_rc[MF_THREADS * STRIDE];
     __shared__ uint32_t s_node[MAXN][MF_THREADS];
     __shared__ uint32_t s_vk[MAXN][MF_THREADS];                    // v | kmin << 16
     __shared__ uint32_t s_len[MF_THREADS];                         // rlen | flags << 24
@@ -112,174 +208,178 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     const uint64_t r0 = (uint64_t)blockIdx.x * MF_THREADS;
     const uint32_t L = ix.split_len;
 
-    // ---- phase 1: cooperative pack --------------------------------------------------------
-    for (uint32_t k = 0; k < 32; k++) {
-        const uint32_t t = wib * 32 + k;
-        const uint64_t r = r0 + t;
-        uint32_t* row = s_read + t * STRIDE;
-        if (r >= n_reads) {
-            if (lane == 0) s_len[t] = F_NONE;
-            continue;
-        }
-        const uint64_t s = seq_start[r], e = seq_end[r];
-        const uint64_t len64 = e - s;
-        if (len64 > CAP) {
-            // too long for the packed row: still need the 'N' test before the exhaustive tier
-            if (lane == 0) s_len[t] = F_LONG;
-            continue;
-        }
-        const uint32_t rlen = (uint32_t)len64;
-        const uint32_t nwords = (rlen + 15) >> 4;
-        bool anyN = false, anyBad = false;
-        for (uint32_t w0 = 0; w0 < nwords; w0 += 32) {
-            const uint32_t w = w0 + lane;
+    // ---- phase 1: cooperative pack (LPR lanes per read) -------------------------------------
+    {
+        const uint32_t grp = lane / LPR, gl = lane % LPR;
+        const uint32_t gmask = LPR == 32 ? 0xFFFFFFFFu : (((1u << LPR) - 1) << (grp * LPR));
+        for (uint32_t k = 0; k < 32 / GROUPS; k++) {
+            const uint32_t t = wib * 32 + k * GROUPS + grp;
+            const uint64_t r = r0 + t;
+            uint32_t* row = s_fwd + t * STRIDE;
+            uint32_t* rrow = s_rc + t * STRIDE;
+            uint64_t s = 0, len64 = 0;
+            const bool live = r < n_reads;
+            if (live) { s = seq_start[r]; len64 = seq_end[r] - s; }
+            const bool fits = live && len64 <= CAP;
+            const uint32_t rlen = fits ? (uint32_t)len64 : 0;
+            const uint32_t nwords = (rlen + 15) >> 4;
             uint32_t packed = 0;
             bool hasN = false, bad = false;
-            if (w < nwords) {
+            if (gl < nwords) {
                 // first byte of this lane's 16 bases, as an ABSOLUTE address (shards may be misaligned)
-                const uintptr_t a = reinterpret_cast<uintptr_t>(buf) + s + 16ull * w;
-                const uint32_t nb = min(16u, rlen - 16 * w);
+                const uintptr_t a = reinterpret_cast<uintptr_t>(buf) + s + 16ull * gl;
+                const uint32_t nb = min(16u, rlen - 16 * gl);
                 const uint32_t sh = (uint32_t)(a & 3) * 8;
                 const uint32_t* p = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-                // 5 aligned words cover 16 unaligned bytes; words entirely past the read are not touched
                 uint32_t x[5];
                 const uint32_t need = ((uint32_t)(a & 3) + nb + 3) >> 2;
 #pragma unroll
                 for (int j = 0; j < 5; j++) x[j] = (uint32_t)j < need ? __ldg(p + j) : 0u;
+                uint32_t diff = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    uint32_t c = __funnelshift_r(x[j], x[j + 1], sh);
+                    const uint32_t c = __funnelshift_r(x[j], x[j + 1], sh);
                     const int left = (int)nb - 4 * j;               // valid bytes in this word
                     if (left <= 0) break;
                     const uint32_t vm = left >= 4 ? 0xFFFFFFFFu : ((1u << (8 * left)) - 1);
-                    uint32_t ok = __vcmpeq4(c, 0x41414141u) | __vcmpeq4(c, 0x43434343u) |
-                                  __vcmpeq4(c, 0x47474747u) | __vcmpeq4(c, 0x54545454u);
-                    uint32_t isn = __vcmpeq4(c, 0x4E4E4E4Eu);
-                    hasN |= (isn & vm) != 0;
-                    bad |= (~(ok | isn) & vm) != 0;
-                    uint32_t code = ((c & vm) >> 1) & 0x03030303u;
-                    packed |= ((code * 0x01041040u) >> 24) << (8 * j);
+                    const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
+                    // the only byte with code k is "ACTG"[k] = 0x41 + 2k (+15 when k == 2)
+                    const uint32_t is2 = (c2 >> 1) & ~c2 & 0x01010101u;
+                    const uint32_t expect = 0x41414141u + 2 * c2 + 15 * is2;
+                    diff |= (expect ^ c) & vm;
+                    packed |= ((c2 * 0x01041040u) >> 24) << (8 * j);
+                }
+                if (diff) {                                         // rare: some byte is not ACGT
+                    for (uint32_t j = 0; j < nb; j++) {
+                        const uint32_t c = (__funnelshift_r(x[j >> 2], x[(j >> 2) + 1], sh) >> (8 * (j & 3))) & 0xFF;
+                        if (c == 'N') hasN = true;
+                        else if (!is_acgt(c)) bad = true;
+                    }
                 }
             }
-            if (w < (uint32_t)STRIDE) row[w] = packed;
-            anyN |= hasN;
-            anyBad |= bad;
+            // reverse complement: reverse the 2-bit groups of every word, complement, then
+            // realign by the (16*nwords - rlen) padding bases that now sit in front
+            uint32_t rv = __brev(packed);
+            rv = (((rv & 0x55555555u) << 1) | ((rv >> 1) & 0x55555555u)) ^ 0xAAAAAAAAu;
+            const int src0 = (int)nwords - 1 - (int)gl, src1 = src0 - 1;
+            uint32_t a0 = __shfl_sync(0xFFFFFFFFu, rv, (src0 >= 0 ? src0 : 0) + grp * LPR);
+            uint32_t a1 = __shfl_sync(0xFFFFFFFFu, rv, (src1 >= 0 ? src1 : 0) + grp * LPR);
+            if (src0 < 0) a0 = 0;
+            if (src1 < 0) a1 = 0;
+            const uint32_t pad = 16 * nwords - rlen;
+            const uint32_t rcw = __funnelshift_r(a0, a1, 2 * pad);
+            const uint32_t bN = __ballot_sync(0xFFFFFFFFu, hasN) & gmask;
+            const uint32_t bB = __ballot_sync(0xFFFFFFFFu, bad) & gmask;
+            if (fits) {
+                for (uint32_t w = gl; w < (uint32_t)STRIDE; w += LPR) {
+                    row[w] = w < nwords ? packed : 0u;
+                    rrow[w] = w < nwords ? rcw : 0u;
+                }
+            }
+            if (gl == 0)
+                s_len[t] = !live ? F_NONE : !fits ? F_LONG : (rlen | (bN ? F_N : 0) | (bB ? F_BAD : 0));
         }
-        anyN = __any_sync(0xFFFFFFFFu, anyN);
-        anyBad = __any_sync(0xFFFFFFFFu, anyBad);
-        // zero the pad words read64 may touch
-        for (uint32_t w = nwords + lane; w < (uint32_t)STRIDE; w += 32) row[w] = 0;
-        if (lane == 0) s_len[t] = rlen | (anyN ? F_N : 0) | (anyBad ? F_BAD : 0);
     }
-    __syncthreads();
+    __syncwarp();        // every warp packs, maps and confirms only its own 32 reads
 
-    // ---- phase 2: one thread per read -------------------------------------------------------
+    // ---- phase 2: one thread per read, passes A and B ---------------------------------------
     const uint32_t t = threadIdx.x;
     const uint64_t r = r0 + t;
-    const uint32_t lf = s_len[t];
+    uint32_t lf = s_len[t];
+    const uint32_t rlen = lf & 0xFFFFFF;
+    const uint32_t* row = s_fwd + t * STRIDE;
+    uint32_t nn = 0, unk_from = 0, unk_cnt = 0;
+    bool active = !(lf & (F_NONE | F_LONG | F_BAD | F_N)) && rlen >= L;
+    bool bail = (lf & (F_LONG | F_BAD)) != 0 && !(lf & F_NONE);
+    if ((lf & F_BAD) && ((lf & F_N) || rlen < L)) bail = false;    // N / short win over the bail
+    uint32_t npos = 0;
+    if (active) {
+        npos = rlen - L + 1;
+        const uint32_t uA = run_pass(ix, row, rlen, npos, false, npos, s_node, s_vk, t, nn, bail);
+        if (!bail && uA < npos) {
+            const uint32_t lim = npos - uA;
+            const uint32_t uB = run_pass(ix, s_rc + t * STRIDE, rlen, lim, true, npos, s_node, s_vk, t, nn, bail);
+            if (!bail && uB < lim) { unk_from = uA; unk_cnt = lim - uB; }
+        }
+    }
+    // ---- phase 3: the warp probes the unknown windows of its reads, one range at a time --------
+    // Normally every one of them misses (they cover a sequencing error).  A window that does hit
+    // a unique posting (a second error further along) is one more hit for that node; a window
+    // with several postings sends the read to the exhaustive tier.
+    {
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, unk_cnt > 0);
+        while (m) {
+            const int src = __ffs((int)m) - 1;
+            m &= m - 1;
+            const uint32_t from = __shfl_sync(0xFFFFFFFFu, unk_from, src);
+            const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, unk_cnt, src);
+            uint32_t tnn = __shfl_sync(0xFFFFFFFFu, nn, src);          // list length of read src (uniform copy)
+            const uint32_t tt = wib * 32 + src;
+            bool tbail = false;
+            for (uint32_t w0 = 0; w0 < cnt && !tbail; w0 += 32) {
+                const uint32_t w = w0 + lane;
+                uint32_t tp = 0, node = 0;
+                int res = PROBE_MISS;
+                if (w < cnt) res = probe_window(ix, s_fwd + tt * STRIDE, from + w, tp, node);
+                if (__any_sync(0xFFFFFFFFu, res == PROBE_MULTI)) { tbail = true; break; }
+                uint32_t hm = __ballot_sync(0xFFFFFFFFu, res == PROBE_UNIQUE);
+                while (hm) {
+                    const int leader = __ffs((int)hm) - 1;
+                    const uint32_t lnode = __shfl_sync(0xFFFFFFFFu, node, leader);
+                    const uint32_t grp = __ballot_sync(0xFFFFFFFFu, res == PROBE_UNIQUE && node == lnode);
+                    // every lane runs the (uniform) list update on shared memory; one lane stores
+                    uint32_t a = 0;
+                    for (; a < tnn; a++) if (s_node[a][tt] == lnode) break;
+                    const uint32_t hits = __popc(grp), kminc = from + w0 + (uint32_t)(__ffs((int)grp) - 1);
+                    if (a == tnn) {
+                        if (tnn == MAXN) { tbail = true; break; }
+                        if (lane == 0) { s_node[a][tt] = lnode; s_vk[a][tt] = hits | (kminc << 16); }
+                        tnn++;
+                    } else if (lane == 0) {
+                        const uint32_t old = s_vk[a][tt];
+                        s_vk[a][tt] = ((old & 0xFFFF) + hits) | (min(old >> 16, kminc) << 16);
+                    }
+                    __syncwarp();
+                    hm &= ~grp;
+                }
+            }
+            if (lane == (uint32_t)src) { nn = tnn; if (tbail) bail = true; }
+        }
+        __syncwarp();
+    }
+
+    // ---- phase 4: finalize -----------------------------------------------------------------
     if (lf & F_NONE) return;
     if (t == 0 && blockIdx.x == 0) atomicAdd(&counters[CNT_FAST], (unsigned long long)n_reads);
     ReadSlot* out = slots + r;
-    bool bail = (lf & (F_LONG | F_BAD)) != 0;
-    const uint32_t rlen = lf & 0xFFFFFF;
     if (!(lf & F_LONG)) {
         if (lf & F_N) { out->hdr = ST_N; return; }
         if (rlen < L) { out->hdr = ST_SHORT; return; }
     }
-    const uint32_t* row = s_read + t * STRIDE;
-    uint32_t nn = 0;
+    uint32_t n_out = 0;
     if (!bail) {
-        const uint32_t npos = rlen - L + 1;
-        uint32_t i = 0;
-        uint32_t walk_tp = NONE32;          // window i is already known to equal text window walk_tp (unique)
-        while (i < npos && !bail) {
-            uint32_t tp = walk_tp, node = 0;
-            walk_tp = NONE32;
-            if (tp == NONE32) {
-                // ---- seed: hash + probe window i ----
-                const uint64_t h = hash_read(row, i, L);
-                uint32_t j = slot_of(h, ix.slot_mask);
-                int res = PROBE_MISS;
-                while (true) {
-                    const uint2 ent = __ldg(ix.slots + j);
-                    if (ent.x == EMPTY_TP) break;
-                    if (fp_match(ent.y, h, ix.node_mask) && read_equals_text(row, i, ix.text, ent.x, L)) {
-                        const bool u = (__ldg(ix.uniq + (ent.x >> 5)) >> (ent.x & 31)) & 1;
-                        res = u ? PROBE_UNIQUE : PROBE_MULTI;
-                        tp = ent.x;
-                        node = ent.y & ix.node_mask;
-                        break;
-                    }
-                    j = (j + 1) & ix.slot_mask;
-                }
-                if (res == PROBE_MULTI) { bail = true; break; }
-                if (res == PROBE_MISS) { i++; continue; }
-            } else {
-                // node of a successor window: binary search over strand starts (small, cached)
-                node = strand_of(ix.strand_start, 2 * ix.n_nodes, tp) >> 1;
+        // sort by node index (ascending, as enumerate(nodes) does) and apply the predicate
+        for (uint32_t a = 1; a < nn; a++) {
+            const uint32_t kn = s_node[a][t], kv = s_vk[a][t];
+            int b = (int)a - 1;
+            while (b >= 0 && s_node[b][t] > kn) {
+                s_node[b + 1][t] = s_node[b][t];
+                s_vk[b + 1][t] = s_vk[b][t];
+                b--;
             }
-            // ---- extend along the node strand ----
-            const uint32_t s0 = __ldg(ix.strand_start + 2 * node), s1 = __ldg(ix.strand_start + 2 * node + 1);
-            const uint32_t q = 2 * node + (tp >= s1 ? 1u : 0u);
-            const uint32_t send = tp >= s1 ? __ldg(ix.strand_start + 2 * node + 2) : s1;
-            (void)s0;
-            const uint32_t room_t = send - (tp + L), room_r = rlen - (i + L);
-            const uint32_t max_ext = min(room_t, room_r);
-            uint32_t ext = match_len(row, i + L, ix.text, tp + L, max_ext);
-            if (ext) {
-                const uint32_t ur = uniq_run(ix.uniq, tp + 1, ext);
-                if (ur < ext) { bail = true; break; }      // a matching window with several postings
-            }
-            const uint32_t hits = 1 + ext;
-            // ---- accumulate (node, hits, first position) ----
-            {
-                uint32_t a = 0;
-                for (; a < nn; a++) if (s_node[a][t] == node) break;
-                if (a == nn) {
-                    if (nn == MAXN) { bail = true; break; }
-                    s_node[a][t] = node;
-                    s_vk[a][t] = hits | (i << 16);
-                    nn++;
-                } else {
-                    s_vk[a][t] += hits;                        // kmin keeps the first (smallest) position
-                }
-            }
-            i += hits;
-            // ---- walk to the successor when the strand ended exactly here ----
-            if (ext == room_t && i < npos) {
-                const uint32_t nb = i + L - 1;                 // the one new base of window i
-                const uint32_t b = (row[nb >> 4] >> ((nb & 15) * 2)) & 3u;
-                walk_tp = __ldg(ix.succ + 4 * q + b);
+            s_node[b + 1][t] = kn;
+            s_vk[b + 1][t] = kv;
+        }
+        for (uint32_t a = 0; a < nn; a++) {
+            const uint32_t node = s_node[a][t], vk = s_vk[a][t];
+            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) {
+                if (n_out < (uint32_t)SLOT_IDS) out->ids[n_out] = node;
+                n_out++;
             }
         }
+        if (n_out > (uint32_t)SLOT_IDS) bail = true;           // 16 kept nodes do not fit the slot
     }
     if (bail) {
-        const unsigned long long idx = atomicAdd(&counters[CNT_WORK], 1ull);
-        worklist[idx] = (uint32_t)(r);
-        return;
-    }
-    // ---- sort by node index (ascending, as enumerate(nodes) does) and apply the predicate ----
-    for (uint32_t a = 1; a < nn; a++) {
-        uint32_t kn = s_node[a][t], kv = s_vk[a][t];
-        int b = (int)a - 1;
-        while (b >= 0 && s_node[b][t] > kn) {
-            s_node[b + 1][t] = s_node[b][t];
-            s_vk[b + 1][t] = s_vk[b][t];
-            b--;
-        }
-        s_node[b + 1][t] = kn;
-        s_vk[b + 1][t] = kv;
-    }
-    uint32_t n_out = 0;
-    for (uint32_t a = 0; a < nn; a++) {
-        const uint32_t node = s_node[a][t], vk = s_vk[a][t];
-        if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) {
-            if (n_out < (uint32_t)SLOT_IDS) out->ids[n_out] = node;
-            n_out++;
-        }
-    }
-    if (n_out > (uint32_t)SLOT_IDS) {
-        // MAXN == 16 and SLOT_IDS == 15: a 16-node list does not fit the slot -> exhaustive tier
         const unsigned long long idx = atomicAdd(&counters[CNT_WORK], 1ull);
         worklist[idx] = (uint32_t)(r);
         return;
@@ -295,13 +395,21 @@ int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, co
     if (n_reads == 0) return VSPE_OK;
     if (n_reads > 0xFFFFFFFFull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
     const uint32_t L = c->index.split_len;
-    if (L > 0xFFFF) return map_reads_generic(c, d_buf, d_seq_start, d_seq_end, n_reads, d_slots);
+    if (L > 320) return map_reads_generic(c, d_buf, d_seq_start, d_seq_end, n_reads, d_slots);
     VSPE_TRY(c->worklist.reserve(n_reads));
     VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
     const uint32_t grid = (uint32_t)((n_reads + MF_THREADS - 1) / MF_THREADS);
-    // packed-row capacity 320 bases (covers 2x150, 2x250 and 2x300 runs); longer reads bail
-    k_map_fast<23><<<grid, MF_THREADS, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, n_reads, d_slots,
-                                                       c->worklist.p, c->counters.p);
+    // packed-row capacity by the read length seen in the first record; longer reads bail
+    const uint32_t hint = c->read_len_hint;
+    if (hint <= 160)
+        k_map_fast<13, 16><<<grid, MF_THREADS, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, n_reads, d_slots,
+                                                               c->worklist.p, c->counters.p);
+    else if (hint <= 256)
+        k_map_fast<19, 16><<<grid, MF_THREADS, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, n_reads, d_slots,
+                                                               c->worklist.p, c->counters.p);
+    else
+        k_map_fast<23, 32><<<grid, MF_THREADS, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, n_reads, d_slots,
+                                                               c->worklist.p, c->counters.p);
     VSPE_LAUNCH_CHECK(c);
     // the exhaustive tier consumes the worklist; its length stays on the device
     VSPE_TRY(map_reads_generic_dev(c, d_buf, d_seq_start, d_seq_end, c->worklist.p, c->counters.p + CNT_WORK, d_slots));

@@ -14,6 +14,8 @@ namespace vspe {
 
 static constexpr int MG_WARPS = 8;
 static constexpr uint32_t TOUCH_CAP = 256;
+static constexpr uint32_t G_STAGE = 1024;   // bytes of one read staged in shared memory per warp
+static constexpr uint32_t G_WORDS = 20;     // 16-base words kept per window for verification (L <= 320)
 
 __device__ __forceinline__ bool keep_node(uint32_t v, uint32_t kmin, uint32_t len, uint32_t rlen, uint32_t L) {
     // PE_Inference.py:36-47 in integers (see oracle/pe_oracle.py:map_read)
@@ -29,6 +31,7 @@ k_map_generic(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __r
               const unsigned long long* __restrict__ n_items_dev, ReadSlot* __restrict__ slots, uint32_t* __restrict__ scratch, uint64_t scratch_stride,
               uint32_t* __restrict__ spill, uint64_t spill_cap, unsigned long long* __restrict__ counters) {
     __shared__ uint32_t s_ntouch[MG_WARPS];
+    __shared__ uint8_t s_seq[MG_WARPS][G_STAGE];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t gwarp = (uint64_t)blockIdx.x * MG_WARPS + wib, nwarps = (uint64_t)gridDim.x * MG_WARPS;
     const uint32_t N = ix.n_nodes, L = ix.split_len;
@@ -43,9 +46,15 @@ k_map_generic(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __r
         const uint64_t s = seq_start[r], e = seq_end[r];
         const uint64_t rlen64 = e - s;
         const uint8_t* seq = buf + s;
-        // 'N' anywhere -> pair is skipped (checked before the length test, :160-163)
+        // stage the read in shared memory (coalesced) so the per-window loops hit LDS, and test
+        // for 'N' on the way: 'N' anywhere -> pair is skipped, checked before the length (:160-163)
+        const bool staged = rlen64 <= G_STAGE;
         bool hasN = false;
-        for (uint64_t i = lane; i < rlen64; i += 32) hasN |= (seq[i] == 'N');
+        for (uint64_t i = lane; i < rlen64; i += 32) {
+            const uint8_t ch = seq[i];
+            hasN |= (ch == 'N');
+            if (staged) s_seq[wib][i] = ch;
+        }
         hasN = __any_sync(0xFFFFFFFFu, hasN);
         if (hasN || rlen64 < L) {
             if (lane == 0) slots[r].hdr = hasN ? ST_N : ST_SHORT;
@@ -55,35 +64,52 @@ k_map_generic(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __r
             if (lane == 0) { atomicOr(&counters[CNT_ERR], (unsigned long long)ERRF_SPILL_FULL); slots[r].hdr = ST_OK; }
             continue;
         }
+        const uint8_t* sq = staged ? s_seq[wib] : seq;
         const uint32_t rlen = (uint32_t)rlen64, npos = rlen - L + 1;
+        const uint32_t n32 = (L + 15) >> 4;
+        const bool keep_words = n32 <= G_WORDS;
         if (lane == 0) s_ntouch[wib] = 0;
         __syncwarp();
         for (uint32_t i = lane; i < npos; i += 32) {
-            // hash the window from ASCII, exactly as hash_packed would on its packed form
-            uint64_t h = HASH_SEED, w = 0;
+            // hash the window from ASCII, feeding the same 16-base words hash_packed sees
+            KmerHash hs;
+            uint32_t w = 0, wv[G_WORDS];
             bool valid = true;
             for (uint32_t j = 0; j < L; j++) {
-                uint32_t c = seq[i + j];
+                const uint32_t c = sq[i + j];
                 if (!is_acgt(c)) { valid = false; break; }
-                w |= (uint64_t)base_code(c) << (2 * (j & 31));
-                if ((j & 31) == 31 || j == L - 1) { h = hash_mix(h, w); w = 0; }
+                w |= base_code(c) << (2 * (j & 15));
+                if ((j & 15) == 15 || j == L - 1) {
+                    hs.add(w);
+                    if (keep_words) wv[j >> 4] = w;
+                    w = 0;
+                }
             }
             if (!valid) continue;
-            h = hash_final(h);
+            const uint64_t h = hs.finish();
             uint32_t j = slot_of(h, ix.slot_mask);
             while (true) {
-                uint2 ent = __ldg(ix.slots + j);
+                const uint2 ent = __ldg(ix.slots + j);
                 if (ent.x == EMPTY_TP) break;
                 if (fp_match(ent.y, h, ix.node_mask)) {
                     bool eq = true;
-                    for (uint32_t t = 0; t < L; t++)
-                        if (text_base(ix.text, (uint64_t)ent.x + t) != base_code(seq[i + t])) { eq = false; break; }
+                    if (keep_words) {
+                        for (uint32_t m = 0; m < n32 && eq; m++) {
+                            uint32_t tw = (uint32_t)extract64(ix.text, (uint64_t)ent.x + 16 * m);
+                            const uint32_t rem = L - 16 * m;
+                            if (rem < 16) tw &= (1u << (2 * rem)) - 1;
+                            eq = tw == wv[m];
+                        }
+                    } else {
+                        for (uint32_t t = 0; t < L; t++)
+                            if (text_base(ix.text, (uint64_t)ent.x + t) != base_code(sq[i + t])) { eq = false; break; }
+                    }
                     if (eq) {
-                        uint32_t node = ent.y & ix.node_mask;
-                        uint32_t old = atomicAdd(&v[node], 1u);
+                        const uint32_t node = ent.y & ix.node_mask;
+                        const uint32_t old = atomicAdd(&v[node], 1u);
                         atomicMin(&kmin[node], i);
                         if (old == 0) {
-                            uint32_t idx = atomicAdd(&s_ntouch[wib], 1u);
+                            const uint32_t idx = atomicAdd(&s_ntouch[wib], 1u);
                             if (idx < TOUCH_CAP) list[idx] = node;
                         }
                     }

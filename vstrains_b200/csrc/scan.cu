@@ -166,6 +166,159 @@ k_index_records(const uint8_t* __restrict__ buf, uint64_t n, uint32_t head, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Single-pass variant: decoupled look-back over 16 KiB tiles (one read of the input).
+// Every tile publishes {flag, count} in one 64-bit word: flag 1 = tile aggregate, 2 = inclusive
+// prefix.  Tiles take their index from an atomic ticket so every predecessor is already running.
+// ---------------------------------------------------------------------------------------
+#define LB_AGG (1ull << 62)
+#define LB_INC (2ull << 62)
+#define LB_VAL ((1ull << 62) - 1)
+
+__device__ __forceinline__ void masks16(const uint8_t* __restrict__ buf, uint64_t n, int64_t p0, bool& non_ascii,
+                                        uint32_t& term, uint32_t& crlf_nl) {
+    // term: terminator positions; crlf_nl: '\n' terminators preceded by '\r' (content ends one earlier)
+    uint4 v;
+    if (p0 >= 0 && (uint64_t)p0 + 16 <= n) {
+        v = __ldg(reinterpret_cast<const uint4*>(buf + p0));
+    } else {
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 16; i++) {
+            int64_t p = p0 + i;
+            uint32_t c = (p >= 0 && (uint64_t)p < n) ? buf[p] : 0u;
+            w[i >> 2] |= c << (8 * (i & 3));
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if ((v.x | v.y | v.z | v.w) & 0x80808080u) non_ascii = true;
+    // bytes <= 0x0F are rare in FASTQ: test for them before building exact masks
+    const uint32_t lowx = ~(v.x | (v.x >> 1) | (v.x >> 2) | (v.x >> 3)) , lowy = ~(v.y | (v.y >> 1) | (v.y >> 2) | (v.y >> 3)),
+                   lowz = ~(v.z | (v.z >> 1) | (v.z >> 2) | (v.z >> 3)), loww = ~(v.w | (v.w >> 1) | (v.w >> 2) | (v.w >> 3));
+    term = 0;
+    crlf_nl = 0;
+    if (((lowx | lowy | lowz | loww) & 0x10101010u) == 0) return;     // no byte with a zero high nibble
+    uint32_t nl = movemask4(__vcmpeq4(v.x, 0x0A0A0A0Au)) | (movemask4(__vcmpeq4(v.y, 0x0A0A0A0Au)) << 4) |
+                  (movemask4(__vcmpeq4(v.z, 0x0A0A0A0Au)) << 8) | (movemask4(__vcmpeq4(v.w, 0x0A0A0A0Au)) << 12);
+    uint32_t cr = movemask4(__vcmpeq4(v.x, 0x0D0D0D0Du)) | (movemask4(__vcmpeq4(v.y, 0x0D0D0D0Du)) << 4) |
+                  (movemask4(__vcmpeq4(v.z, 0x0D0D0D0Du)) << 8) | (movemask4(__vcmpeq4(v.w, 0x0D0D0D0Du)) << 12);
+    // positions outside [0,n) were loaded as 0 and are neither
+    term = nl;
+    if (cr) {
+        int64_t pn = p0 + 16;
+        uint32_t next_nl = (pn >= 0 && (uint64_t)pn < n && buf[pn] == '\n') ? 0x8000u : 0u;
+        term |= cr & ~((nl >> 1) | next_nl);
+    }
+    crlf_nl = nl & (cr << 1);
+    if ((nl & 1) && p0 > 0 && buf[p0 - 1] == '\r') crlf_nl |= 1;
+}
+
+static constexpr int SR_WARPS = 8;                       // warps per block
+static constexpr int SR_ITERS = 16;                      // 512-byte warp rows per warp
+static constexpr int SR_TILE = SR_WARPS * SR_ITERS * 32 * 16;   // 64 KiB per block
+
+// Layout inside a tile: warp w owns the contiguous 8 KiB [w*8K, (w+1)*8K); in iteration `it` its
+// lanes read one coalesced 512-byte row.  Line order = (warp, iteration, lane), so the ranks come
+// from warp scans (shuffles) plus ONE block-level exchange of the 8 warp totals.
+__global__ void __launch_bounds__(SR_WARPS * 32)
+k_scan_records(const uint8_t* __restrict__ buf, uint64_t n, uint32_t head, unsigned long long* __restrict__ status,
+               unsigned int* __restrict__ ticket, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
+               uint64_t* __restrict__ seq_start, uint64_t* __restrict__ seq_end, unsigned long long* __restrict__ total_out,
+               uint32_t n_tiles, unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t s_wtot[SR_WARPS];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t g0 = ((uint64_t)tile * SR_WARPS + wib) * SR_ITERS * 32 + lane;    // first 16-byte vector of this lane
+    uint32_t mk[SR_ITERS], cnt = 0;                           // terminator mask | crlf mask << 16
+    bool bad = false;
+#pragma unroll
+    for (int it = 0; it < SR_ITERS; it++) {
+        const int64_t p0 = (int64_t)((g0 + (uint64_t)it * 32) * 16) - head;
+        uint32_t term = 0, crlf = 0;
+        if (p0 < (int64_t)n) masks16(buf, n, p0, bad, term, crlf);
+        mk[it] = term | (crlf << 16);
+        cnt += __popc(term);
+    }
+    if (bad) atomicOr(&counters[CNT_ERR], (unsigned long long)ERRF_NON_ASCII);
+    const uint32_t wtot = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane == 0) s_wtot[wib] = wtot;
+    __syncthreads();
+    uint32_t tile_total = 0, warp_base = 0;
+#pragma unroll
+    for (int w = 0; w < SR_WARPS; w++) {
+        const uint32_t x = s_wtot[w];
+        if (w < (int)wib) warp_base += x;
+        tile_total += x;
+    }
+    // publish the aggregate, look back for the exclusive prefix (warp 0)
+    if (wib == 0) {
+        volatile unsigned long long* vs = status;
+        if (tile == 0) {
+            if (lane == 0) { vs[0] = LB_INC | tile_total; s_excl = 0; }
+        } else {
+            if (lane == 0) vs[tile] = LB_AGG | tile_total;
+            unsigned long long excl = 0;
+            int64_t look = (int64_t)tile - 1;
+            while (true) {
+                const int64_t idx = look - lane;
+                unsigned long long st = idx >= 0 ? vs[idx] : LB_INC;
+                while (__any_sync(0xFFFFFFFFu, (st >> 62) == 0)) {
+                    if ((st >> 62) == 0) st = vs[idx];
+                }
+                const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2);
+                const int first = inc ? __ffs((int)inc) - 1 : 32;
+                unsigned long long c = (int)lane <= first ? (st & LB_VAL) : 0ull;
+                for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+                excl += c;
+                if (inc) break;
+                look -= 32;
+            }
+            if (lane == 0) { vs[tile] = LB_INC | (excl + tile_total); s_excl = excl; }
+        }
+        if (lane == 0 && tile == n_tiles - 1) *total_out = s_excl + tile_total;
+    }
+    __syncthreads();
+    uint64_t running = line_base + s_excl + warp_base;
+    if (tile == 0 && threadIdx.x == 0 && (line_base & 3) == 1 && n_slots > 0) seq_start[0] = 0;
+    bool overflow = false;
+#pragma unroll
+    for (int it = 0; it < SR_ITERS; it++) {
+        uint32_t mask = mk[it] & 0xFFFFu;
+        const uint32_t crlf = mk[it] >> 16;
+        const uint32_t c = __popc(mask);
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        const uint32_t row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        uint64_t line = running + inc - c;
+        running += row_total;
+        if (!mask) continue;
+        const int64_t p0 = (int64_t)((g0 + (uint64_t)it * 32) * 16) - head;
+        while (mask) {
+            const int i = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            const uint64_t p = (uint64_t)(p0 + i);
+            const uint32_t phase = (uint32_t)line & 3;
+            if (phase < 2) {
+                const uint64_t idx = (line >> 2) - rec_first;
+                if (idx < n_slots) {
+                    if (phase == 0) seq_start[idx] = p + 1;
+                    else seq_end[idx] = ((crlf >> i) & 1) ? p - 1 : p;
+                } else if (phase == 1) {
+                    overflow = true;
+                }
+            }
+            line++;
+        }
+    }
+    if (overflow) atomicOr(&counters[CNT_ERR], (unsigned long long)ERRF_SLOTS_FULL);
+}
+
 static inline uint32_t head_of(const uint8_t* p) { return (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15); }
 
 int scan_count_lines(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms) {
@@ -185,6 +338,38 @@ int scan_count_lines(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms
     VSPE_CUDA(cudaMemcpyAsync(&total, c->tile_base.p + n_tiles, 8, cudaMemcpyDeviceToHost, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     *n_terms = total;
+    return VSPE_OK;
+}
+
+// single pass: terminator count AND record table; *overflow is set when n_slots was too small
+// (the caller then retries with the exact size, which is known from *n_terms).
+int scan_records_single_pass(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first,
+                             uint64_t n_slots, uint64_t* d_seq_start, uint64_t* d_seq_end, uint64_t* n_terms, bool* overflow) {
+    *n_terms = 0;
+    *overflow = false;
+    if (n == 0) return VSPE_OK;
+    uint32_t head = head_of(d_buf);
+    uint64_t n_tiles = (n + head + SR_TILE - 1) / SR_TILE;
+    if (n_tiles > 0x7FFFFFFFull) { set_error("buffer too large for one scan launch"); return VSPE_ERR_LIMIT; }
+    VSPE_TRY(c->tile_base.reserve(n_tiles + 4));
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(c->tile_base.p);
+    VSPE_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 4) * 8, c->stream));
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(status + n_tiles + 1);
+    unsigned long long* total = status + n_tiles + 2;
+    k_scan_records<<<(uint32_t)n_tiles, SR_WARPS * 32, 0, c->stream>>>(d_buf, n, head, status, ticket, line_base, rec_first, n_slots,
+                                                                      d_seq_start, d_seq_end, total, (uint32_t)n_tiles, c->counters.p);
+    VSPE_LAUNCH_CHECK(c);
+    unsigned long long h_total = 0, h_err = 0;
+    VSPE_CUDA(cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    *n_terms = h_total;
+    if (h_err & ERRF_SLOTS_FULL) {
+        *overflow = true;
+        unsigned long long cleared = h_err & ~(unsigned long long)ERRF_SLOTS_FULL;
+        VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_ERR, &cleared, 8, cudaMemcpyHostToDevice, c->stream));
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    }
     return VSPE_OK;
 }
 

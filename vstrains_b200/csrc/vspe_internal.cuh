@@ -59,7 +59,7 @@ struct IndexView {
     const uint32_t* node_len;       // [N] full node length (also for nodes without k-mers)
     const uint2* slots;
     const uint32_t* uniq;           // bitmap over text positions
-    const uint32_t* succ;           // [2N][4] text position of the unique successor k-mer or NONE
+    const uint32_t* succ;           // [2N][4] {text position, node} of the unique successor k-mer or {NONE32, 0}
     uint32_t text_len;              // bases
     uint32_t slot_mask;
     uint32_t node_mask;             // (1 << nbits) - 1
@@ -71,16 +71,34 @@ static constexpr uint32_t EMPTY_TP = 0xFFFFFFFFu;
 static constexpr uint64_t EMPTY_SLOT = 0xFFFFFFFFFFFFFFFFull;
 static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 
-__host__ __device__ __forceinline__ uint64_t hash_mix(uint64_t h, uint64_t w) {
-    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
-    return h ^ (h >> 29);
-}
-__host__ __device__ __forceinline__ uint64_t hash_final(uint64_t h) {
-    h ^= h >> 32;
-    h *= 0xD6E8FEB86659FD93ull;
-    return h ^ (h >> 32);
-}
-static constexpr uint64_t HASH_SEED = 0x243F6A8885A308D3ull;
+// (k+1)-mer hash: the window is read as 32-bit words of 16 bases (the last one masked to the
+// window length); two multiply-add polynomial accumulators, each finished with fmix32.
+// The high half selects the slot, the low half is the fingerprint.  Every tier (packed text,
+// packed reads, raw ASCII) feeds the same word sequence, so they agree bit for bit.
+struct KmerHash {
+    uint32_t h1 = 0x243F6A88u, h2 = 0x85A308D3u;
+    __host__ __device__ __forceinline__ void add(uint32_t w) {
+        h1 = h1 * 0x9E3779B1u + w;
+        h2 = h2 * 0x85EBCA77u + w;
+    }
+    __host__ __device__ static __forceinline__ uint32_t fmix(uint32_t h) {
+        h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+        return h;
+    }
+    __host__ __device__ __forceinline__ uint64_t finish() const {
+        return ((uint64_t)fmix(h1) << 32) | fmix(h2 ^ (h1 >> 7));
+    }
+    // feed up to 32 bases held in a 64-bit word; rem = bases of the window left (>= 1)
+    __host__ __device__ __forceinline__ void add64(uint64_t w, uint32_t rem) {
+        uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+        if (rem < 16) lo &= (1u << (2 * rem)) - 1;
+        add(lo);
+        if (rem > 16) {
+            if (rem < 32) hi &= (1u << (2 * (rem - 16))) - 1;
+            add(hi);
+        }
+    }
+};
 
 // ascii -> 2-bit code; valid only for A,C,G,T (upper case)
 __host__ __device__ __forceinline__ uint32_t base_code(uint32_t c) { return (c >> 1) & 3u; }
@@ -105,14 +123,9 @@ __device__ __forceinline__ uint32_t text_base(const uint64_t* __restrict__ t, ui
 
 // hash of the L-base window starting at base b of a packed array
 __device__ __forceinline__ uint64_t hash_packed(const uint64_t* __restrict__ t, uint64_t b, uint32_t L) {
-    uint64_t h = HASH_SEED;
-    for (uint32_t m = 0; m < L; m += 32) {
-        uint64_t w = extract64(t, b + m);
-        uint32_t rem = L - m;
-        if (rem < 32) w &= (1ull << (2 * rem)) - 1;
-        h = hash_mix(h, w);
-    }
-    return hash_final(h);
+    KmerHash hs;
+    for (uint32_t m = 0; m < L; m += 32) hs.add64(extract64(t, b + m), L - m);
+    return hs.finish();
 }
 
 __device__ __forceinline__ uint32_t slot_of(uint64_t h, uint32_t mask) { return (uint32_t)(h >> 32) & mask; }
@@ -221,6 +234,9 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
 int scan_count_lines(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms);
 int scan_index_records(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first,
                        uint64_t n_slots, uint64_t* d_seq_start, uint64_t* d_seq_end);
+
+int scan_records_single_pass(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first,
+                             uint64_t n_slots, uint64_t* d_seq_start, uint64_t* d_seq_end, uint64_t* n_terms, bool* overflow);
 
 // K2+K4: map reads [0, n_reads) of a chunk into slots[rec_off + r]
 int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
