@@ -183,3 +183,35 @@ def test_non_ascii_input_is_rejected():
     with pytest.raises(VspeError) as ei:
         pe_inference.pe_inference(b"S\t1\tACGTACGTAC\n", b"@r\nACGT\xc3\xa9\n+\nIIIII\n", b"@r\nACGTA\n+\nIIIII\n", 3)
     assert ei.value.code == -3
+
+
+def test_run_rank_single_process_matches_oracle():
+    from vstrains_b200 import dist as vdist
+    cfg = synth.CONFIGS["C2"]
+    g, f, r = synth.generate(cfg, pairs=3000)
+    gfa = g.to_gfa()
+    ids, node, short, counters = vdist.run_rank(gfa, f, r, cfg.k, 0, 1, device=0)
+    onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
+    assert np.array_equal(node.astype(np.int64), onode) and np.array_equal(short.astype(np.int64), oshort)
+    assert counters == ostats
+
+
+def test_cli_multi_gpu_is_byte_identical(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cfg = synth.CONFIGS["C3"]
+    g, f, r = synth.generate(cfg, pairs=5000)
+    (tmp_path / "g.gfa").write_bytes(g.to_gfa())
+    f.tofile(tmp_path / "f.fq")
+    r.tofile(tmp_path / "r.fq")
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / ("aln%d" % gpus)
+        env = dict(os.environ, VSPE_GPUS=str(gpus))
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "utils", "VStrains_PE_Inference.py"), "-g", str(tmp_path / "g.gfa"),
+                            "-o", str(out), "-f", str(tmp_path / "f.fq"), "-r", str(tmp_path / "r.fq"), "-k", str(cfg.k)],
+                           capture_output=True, env=env)
+        assert p.returncode == 0, p.stderr.decode()
+        outs.append(((out / "pe_info").read_bytes(), (out / "st_info").read_bytes()))
+    assert outs[0] == outs[1]

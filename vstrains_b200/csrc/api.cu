@@ -28,6 +28,9 @@ int map_reads_generic_list(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
                            const uint32_t* d_worklist, uint64_t n_items, ReadSlot* d_slots);
 int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                    uint64_t n_reads, ReadSlot* d_slots);
+int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len,
+                  const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve, int n_gpus,
+                  std::vector<uint64_t>& node_mat, std::vector<uint64_t>& short_mat, vspe_stats* stats);
 
 // ---------------------------------------------------------------------------------------
 // per-mate streaming state
@@ -326,8 +329,6 @@ using namespace vspe;
 // C ABI
 // =========================================================================================
 extern "C" {
-
-struct vspe_ctx : public vspe::Ctx {};
 
 const char* vspe_last_error(void) { return get_error(); }
 const char* vspe_version(void) { return "vspe-b200 0.1 (sm_100a)"; }
@@ -659,7 +660,7 @@ static int rm_rf(const std::string& dir) {
 int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, int kmer_size, const char* out_dir,
              int n_gpus, vspe_stats* stats) {
     if (!gfa_path || !fwd_path || !rve_path || !out_dir || kmer_size < 1) { set_error("bad arguments"); return VSPE_ERR_ARG; }
-    if (n_gpus != 1) { set_error("vspe_run: multi-GPU runs go through vspe_run_multi (n_gpus=%d)", n_gpus); return VSPE_ERR_ARG; }
+    if (n_gpus < 1 || n_gpus > 16) { set_error("n_gpus must be in 1..16 (got %d)", n_gpus); return VSPE_ERR_ARG; }
     std::string dir(out_dir);
     if (!dir.empty() && dir.back() == '/') dir.pop_back();      // :93-94
     if (dir.empty()) { set_error("empty output directory"); return VSPE_ERR_ARG; }
@@ -674,16 +675,22 @@ int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, i
     VSPE_TRY(parse_gfa_bytes(g.p, g.n, nodes));
     VSPE_TRY(f.open_ro(fwd_path));
     VSPE_TRY(r.open_ro(rve_path));
-    vspe_ctx* c = nullptr;
-    VSPE_TRY(vspe_create(0, &c));
-    int rc = vspe_index_build(c, nodes.seqs.data(), nodes.off.data(), (uint32_t)nodes.ids.size(), (uint32_t)kmer_size + 1);
-    if (rc == VSPE_OK) rc = vspe_count_host(c, f.p, f.n, r.p, r.n);
     uint32_t N = (uint32_t)nodes.ids.size();
-    std::vector<uint64_t> nm((size_t)N * N), sm((size_t)N * N);
-    if (rc == VSPE_OK) rc = vspe_matrices_host(c, nm.data(), sm.data());
-    if (rc == VSPE_OK && stats) rc = vspe_get_stats(c, stats);
-    vspe_destroy(c);
-    if (rc != VSPE_OK) return rc;
+    std::vector<uint64_t> nm, sm;
+    if (n_gpus > 1) {
+        VSPE_TRY(run_multi_gpu(nodes.seqs.data(), nodes.off.data(), N, (uint32_t)kmer_size + 1, f.p, f.n, r.p, r.n, n_gpus, nm, sm, stats));
+    } else {
+        vspe_ctx* c = nullptr;
+        VSPE_TRY(vspe_create(0, &c));
+        int rc = vspe_index_build(c, nodes.seqs.data(), nodes.off.data(), N, (uint32_t)kmer_size + 1);
+        if (rc == VSPE_OK) rc = vspe_count_host(c, f.p, f.n, r.p, r.n);
+        nm.assign((size_t)N * N, 0);
+        sm.assign((size_t)N * N, 0);
+        if (rc == VSPE_OK) rc = vspe_matrices_host(c, nm.data(), sm.data());
+        if (rc == VSPE_OK && stats) rc = vspe_get_stats(c, stats);
+        vspe_destroy(c);
+        if (rc != VSPE_OK) return rc;
+    }
     std::vector<const char*> idp(N);
     for (uint32_t i = 0; i < N; i++) idp[i] = nodes.ids[i].c_str();
     VSPE_TRY(vspe_write_info((dir + "/pe_info").c_str(), idp.data(), N, nm.data()));

@@ -76,3 +76,6 @@ struct Ctx {
     } while (0)
 
 }  // namespace vspe
+
+// the opaque handle of include/vspe.h is the context itself
+struct vspe_ctx : public vspe::Ctx {};
