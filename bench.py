@@ -242,6 +242,7 @@ def main():
         ix.count_device(d_f.data_ptr(), f.size, d_r.data_ptr(), r.size)
         if world > 1:
             dist.all_reduce(mats)
+            torch.cuda.synchronize()       # the library's stream does not order with torch's
 
     def barrier():
         if world > 1:
@@ -251,11 +252,20 @@ def main():
     # ---- device-resident timing ---------------------------------------------------------
     sampler = ClockSampler(local_rank)           # samples across warm-up + timed region (steps are ms-short)
     sampler.start()
-    t_w = time.perf_counter()
-    n_w = 0
-    while n_w < warmup or time.perf_counter() - t_w < 1.0:     # >= W steps and >= 1 s under load
+    for _ in range(warmup):
         step_device()
-        n_w += 1
+    barrier()
+    # keep the GPU under load for >= 1 s before timing so the clock samples mean something; the
+    # extra step count is decided on rank 0 and broadcast (every rank must run the same number
+    # of collectives)
+    t_w = time.perf_counter()
+    step_device()
+    torch.cuda.synchronize()
+    extra = torch.tensor([max(0, min(2000, int(1.0 / max(time.perf_counter() - t_w, 1e-4))))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(extra, src=0)
+    for _ in range(int(extra.item())):
+        step_device()
     barrier()
     stage = {"ms_scan": 0.0, "ms_map": 0.0, "ms_count": 0.0, "ms_total": 0.0}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -288,6 +298,7 @@ def main():
         ix.count_host_ptr(h_f.data_ptr(), f.size, h_r.data_ptr(), r.size)
         if world > 1:
             dist.all_reduce(mats)
+            torch.cuda.synchronize()
         return ix.matrices()
 
     for _ in range(2):

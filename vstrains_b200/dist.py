@@ -30,7 +30,7 @@ def merge_counts(mats, counters: Dict[str, int], group=None):
     import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return mats, dict(counters)
+        return mats, {k: int(counters[k]) for k in COUNTER_KEYS}
     dist.all_reduce(mats, op=dist.ReduceOp.SUM, group=group)
     c = torch.tensor([int(counters[k]) for k in COUNTER_KEYS], dtype=torch.int64, device=mats.device)
     dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
