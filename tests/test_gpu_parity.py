@@ -22,15 +22,15 @@ def _info(ids, mat, tmp_path, name):
         return f.read()
 
 
-@pytest.mark.parametrize("force_generic", [0, 1])
-def test_golden_fixtures_bit_exact(golden, tmp_path, force_generic):
+@pytest.mark.parametrize("force_generic,scan_mode", [(0, 0), (0, 1), (1, 1)])
+def test_golden_fixtures_bit_exact(golden, tmp_path, force_generic, scan_mode):
     if golden.status != 0:
         with pytest.raises(VspeError) as ei:
             pe_inference.pe_inference(golden.gfa, golden.fwd, golden.rve, golden.k)
         assert ei.value.code == -2
         return
     ids, node, short, stats = pe_inference.pe_inference(golden.gfa, golden.fwd, golden.rve, golden.k,
-                                                        options={"force_generic": force_generic})
+                                                        options={"force_generic": force_generic, "scan_mode": scan_mode})
     assert _info(ids, node, tmp_path, "pe_info") == golden.pe_info
     assert _info(ids, short, tmp_path, "st_info") == golden.st_info
     _, _, ostats, _ = pe_oracle.run_bytes(golden.gfa, golden.fwd, golden.rve, golden.k)
@@ -89,13 +89,14 @@ def test_record_split_edge_cases(two_pass):
                 assert fq[int(start[r]):int(start[r]) + int(length[r])].decode() == lines[4 * r + 1][:-1]
 
 
-@pytest.mark.parametrize("force_generic", [0, 1])
-def test_per_read_mapping_matches_oracle(golden, force_generic):
+@pytest.mark.parametrize("force_generic,scan_mode", [(0, 0), (0, 1), (1, 1)])
+def test_per_read_mapping_matches_oracle(golden, force_generic, scan_mode):
     if golden.status != 0:
         return
     ids, seqs = pe_inference.parse_gfa_nodes(golden.gfa)
     with pe_inference.PEIndex(seqs, golden.k) as ix:
         ix.set_option("force_generic", force_generic)
+        ix.set_option("scan_mode", scan_mode)
         for fq in (golden.fwd, golden.rve):
             off, nodes, status = ix.map_reads(fq)
             ooff, onodes, ostatus = c_oracle.map_reads(golden.gfa, fq, golden.k)
@@ -105,12 +106,12 @@ def test_per_read_mapping_matches_oracle(golden, force_generic):
 
 
 @pytest.mark.parametrize("name,pairs", [("C1", 6000), ("C2", 6000), ("C3", 4000), ("C4", 3000)])
-@pytest.mark.parametrize("force_generic", [0, 1])
-def test_synthetic_configs_match_c_oracle(name, pairs, force_generic):
+@pytest.mark.parametrize("force_generic,scan_mode", [(0, 0), (0, 1), (1, 1)])
+def test_synthetic_configs_match_c_oracle(name, pairs, force_generic, scan_mode):
     cfg = synth.CONFIGS[name]
     g, f, r = synth.generate(cfg, pairs=pairs)
     gfa = g.to_gfa()
-    ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"force_generic": force_generic})
+    ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"force_generic": force_generic, "scan_mode": scan_mode})
     onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
     assert np.array_equal(node.astype(np.int64), onode)
     assert np.array_equal(short.astype(np.int64), oshort)
@@ -124,10 +125,11 @@ def test_chunked_streaming_equals_single_chunk():
     g, f, r = synth.generate(cfg, pairs=9000)
     ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())
     res = []
-    for chunk_mb, two_pass in ((256, 0), (1, 0), (1, 1)):
+    for chunk_mb, two_pass, scan_mode in ((256, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0)):
         with pe_inference.PEIndex(seqs, cfg.k) as ix:
             ix.set_option("chunk_mb", chunk_mb)
             ix.set_option("scan_two_pass", two_pass)
+            ix.set_option("scan_mode", scan_mode)
             ix.count_host(f, r)
             res.append(ix.matrices() + (ix.stats(),))
     for other in res[1:]:
@@ -215,3 +217,42 @@ def test_cli_multi_gpu_is_byte_identical(tmp_path):
         assert p.returncode == 0, p.stderr.decode()
         outs.append(((out / "pe_info").read_bytes(), (out / "st_info").read_bytes()))
     assert outs[0] == outs[1]
+
+
+def _mk_fastq(seqs, nl=b"\n"):
+    return b"".join(b"@r" + nl + s + nl + b"+" + nl + b"I" * len(s) + nl for s in seqs)
+
+
+@pytest.mark.parametrize("scan_mode", [0, 1])
+def test_whole_path_edge_shapes(scan_mode):
+    """Shapes that stress the tiled scan: thousands of tiny records per tile (fallback path),
+    reads longer than the packed rows / the scan margin, CRLF and lone-CR files, reads that
+    straddle tile boundaries, misaligned shards."""
+    rng = np.random.default_rng(17)
+    cfg = synth.Config("edge", 1500, 3, 0.02, 150, 10, 23)
+    st = synth.make_strains(cfg.genome_len, cfg.strains, cfg.divergence, rng)
+    seqs, cov, links = synth.build_dbg(st, 31, None, seed=3)
+    gfa = b"".join(b"S\t%d\t%s\n" % (i, s) for i, s in enumerate(seqs))
+    genome = synth._ACGT[st[0]].tobytes()
+
+    def reads(n, lo, hi):
+        out = []
+        for _ in range(n):
+            ln = int(rng.integers(lo, hi))
+            a = int(rng.integers(0, len(genome) - ln))
+            out.append(genome[a:a + ln])
+        return out
+
+    cases = {
+        "tiny": (_mk_fastq(reads(30000, 1, 12)), _mk_fastq(reads(30000, 33, 40))),
+        "long": (_mk_fastq(reads(300, 300, 1400)), _mk_fastq(reads(300, 100, 700))),
+        "crlf": (_mk_fastq(reads(4000, 40, 160), b"\r\n"), _mk_fastq(reads(4000, 40, 160), b"\r")),
+        "mixed": (_mk_fastq(reads(3000, 1, 330)), _mk_fastq(reads(2990, 1, 330))[:-1]),
+    }
+    for name, (f, r) in cases.items():
+        ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, 31, options={"scan_mode": scan_mode, "chunk_mb": 1})
+        onode, oshort, ostats = c_oracle.run(gfa, f, r, 31)
+        assert np.array_equal(node.astype(np.int64), onode), name
+        assert np.array_equal(short.astype(np.int64), oshort), name
+        for k, v in ostats.items():
+            assert stats[k] == v, (name, k)

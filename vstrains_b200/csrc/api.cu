@@ -28,6 +28,10 @@ int map_reads_generic_list(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
                            const uint32_t* d_worklist, uint64_t n_items, ReadSlot* d_slots);
 int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                    uint64_t n_reads, ReadSlot* d_slots);
+int map_reads_packed(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                     const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
+                     uint64_t n_reads, ReadSlot* d_slots);
+uint32_t map_fast_cap(uint32_t hint);
 int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len,
                   const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve, int n_gpus,
                   std::vector<uint64_t>& node_mat, std::vector<uint64_t>& short_mat, vspe_stats* stats);
@@ -67,13 +71,42 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     const uint64_t lb = ms.line_base;
     const uint64_t rec_first = seq_lines_before(lb);
     uint64_t n_seq = 0;
-    if (c->opt_scan_two_pass) {
+    c->cur_buf_n = n;
+    const uint32_t cap = map_fast_cap(c->read_len_hint);
+    const uint32_t row_words = cap <= 160 ? 12 : cap <= 256 ? 16 : 20;
+    int mode = (int)c->opt_scan_mode;
+    if (c->opt_scan_two_pass) mode = 2;
+    if (c->opt_force_generic || c->index.split_len > 320) mode = std::max(mode, 1);
+    bool packed = false;
+    if (mode == 0) {
+        // fused TMA scan + pack with a guessed table size (from the read length of the first
+        // records); if a tile owns too many records or the guess was too small, fall through
+        uint64_t guess = n / (2ull * std::max<uint32_t>(c->read_len_hint, 20) + 8) * 21 / 20 + 4096;
+        unsigned long long flags = 0;
+        VSPE_TRY(mb.rec.seq_start.reserve(guess + 2));
+        VSPE_TRY(mb.rec.seq_end.reserve(guess + 2));
+        VSPE_TRY(mb.rec.hdr.reserve(guess + 2));
+        VSPE_TRY(mb.rec.rows.reserve((guess + 2) * row_words));
+        VSPE_TRY(scan_pack(c, d_buf, n, lb, rec_first, guess, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p,
+                           row_words, cap, &n_terms, &flags));
+        n_seq = seq_lines_before(lb + n_terms) - rec_first;
+        if ((flags & ERRF_SLOTS_FULL) && !(flags & ERRF_TILE_FULL)) {
+            VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
+            VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
+            VSPE_TRY(mb.rec.hdr.reserve(n_seq + 2));
+            VSPE_TRY(mb.rec.rows.reserve((n_seq + 2) * row_words));
+            VSPE_TRY(scan_pack(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p,
+                               row_words, cap, &n_terms, &flags));
+        }
+        if (flags & (ERRF_TILE_FULL | ERRF_SLOTS_FULL)) mode = 1; else packed = true;
+    }
+    if (mode == 2) {
         VSPE_TRY(scan_count_lines(c, d_buf, n, &n_terms));
         n_seq = seq_lines_before(lb + n_terms) - rec_first;
         VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
         VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
         VSPE_TRY(scan_index_records(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p));
-    } else {
+    } else if (mode == 1) {
         // one pass with a guessed table size (a FASTQ record is rarely under 48 bytes); if the
         // guess was too small the pass is repeated once with the exact size
         uint64_t guess = n / 48 + 1024;
@@ -92,7 +125,10 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     VSPE_TRY(mb.slots.reserve(rec_first + n_seq + 1, true, c->stream));
     VSPE_CUDA(cudaEventRecord(e1, c->stream));
     if (n_seq) {
-        if (c->opt_force_generic)
+        if (packed)
+            VSPE_TRY(map_reads_packed(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p, row_words, cap, n_seq,
+                                      mb.slots.p + rec_first));
+        else if (c->opt_force_generic)
             VSPE_TRY(map_reads_generic_list(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, nullptr, n_seq, mb.slots.p + rec_first));
         else
             VSPE_TRY(map_reads_fast(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, n_seq, mb.slots.p + rec_first));
@@ -710,6 +746,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "force_generic")) c->opt_force_generic = value;
     else if (!strcmp(name, "chunk_mb")) c->opt_chunk_mb = value;
     else if (!strcmp(name, "scan_two_pass")) c->opt_scan_two_pass = value;
+    else if (!strcmp(name, "scan_mode")) c->opt_scan_mode = value;
     else { set_error("unknown option %s", name); return VSPE_ERR_ARG; }
     return VSPE_OK;
 }

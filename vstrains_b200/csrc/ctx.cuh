@@ -14,7 +14,7 @@ enum Counter {
     CNT_BAILED,              // reads the fast tier handed to the exhaustive tier
     CNT_COUNT_
 };
-static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8;
+static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16;
 
 struct MateBuf {
     Records rec;
@@ -44,6 +44,7 @@ struct Ctx {
     DevBuf<unsigned long long> bucket;   // [3][n_buckets + 1]: histogram, start, cursor
     DevBuf<unsigned long long> block_sums;
     bool count_attr_set = false;
+    bool scan_pack_attr_set = false;
     // staging for host-input entry points
     uint8_t* pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;
@@ -56,6 +57,8 @@ struct Ctx {
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
     int64_t opt_scan_two_pass = 0;     // K1 as count + index passes (cross-check of the look-back kernel)
+    uint64_t cur_buf_n = 0;            // bytes of the chunk being mapped (exhaustive tier bound)
+    int64_t opt_scan_mode = 0;         // 0: fused TMA scan+pack, 1: look-back scan + raw-byte map, 2: two-pass scan
     uint32_t read_len_hint = 320;      // longest sequence line among the first records of the input
     // accounting
     vspe_stats stats = {};

@@ -191,10 +191,13 @@ __device__ __forceinline__ uint32_t run_pass(const IndexView& ix, const uint32_t
     return limit;
 }
 
-template <int STRIDE, int LPR>
+// PACKED: phase 1 loads the 2-bit rows written by k_scan_pack (scan_pack.cu) instead of packing
+// the raw bytes itself.
+template <int STRIDE, int LPR, bool PACKED>
 __global__ void __launch_bounds__(MF_THREADS)
 k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
-           const uint64_t* __restrict__ seq_end, uint64_t n_reads, ReadSlot* __restrict__ slots,
+           const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr,
+           uint32_t row_words, uint64_t n_reads, ReadSlot* __restrict__ slots,
            uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters) {
     constexpr uint32_t CAP = (STRIDE - 3) * 16;                   // bases per packed row
     constexpr uint32_t GROUPS = 32 / LPR;                          // reads packed per warp step
@@ -219,13 +222,24 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
             uint32_t* rrow = s_rc + t * STRIDE;
             uint64_t s = 0, len64 = 0;
             const bool live = r < n_reads;
-            if (live) { s = seq_start[r]; len64 = seq_end[r] - s; }
+            uint32_t h = 0;
+            if (PACKED) {
+                if (live) h = __ldg(hdr + r);
+                len64 = (h & PH_LONG) ? (uint64_t)CAP + 1 : (h & 0xFFFFFF);
+            } else if (live) {
+                s = seq_start[r];
+                len64 = seq_end[r] - s;
+            }
             const bool fits = live && len64 <= CAP;
             const uint32_t rlen = fits ? (uint32_t)len64 : 0;
             const uint32_t nwords = (rlen + 15) >> 4;
             uint32_t packed = 0;
             bool hasN = false, bad = false;
-            if (gl < nwords) {
+            if (PACKED) {
+                if (gl < nwords) packed = __ldg(rows + r * row_words + gl);
+                hasN = (h & PH_N) != 0;
+                bad = (h & PH_BAD) != 0;
+            } else if (gl < nwords) {
                 // first byte of this lane's 16 bases, as an ABSOLUTE address (shards may be misaligned)
                 const uintptr_t a = reinterpret_cast<uintptr_t>(buf) + s + 16ull * gl;
                 const uint32_t nb = min(16u, rlen - 16 * gl);
@@ -390,30 +404,42 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
 int map_reads_generic_dev(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                           const uint32_t* d_worklist, const unsigned long long* d_n_items, ReadSlot* d_slots);
 
-int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
-                   uint64_t n_reads, ReadSlot* d_slots) {
+static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                           const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
+                           uint64_t n_reads, ReadSlot* d_slots) {
     if (n_reads == 0) return VSPE_OK;
     if (n_reads > 0xFFFFFFFFull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
-    const uint32_t L = c->index.split_len;
-    if (L > 320) return map_reads_generic(c, d_buf, d_seq_start, d_seq_end, n_reads, d_slots);
     VSPE_TRY(c->worklist.reserve(n_reads));
     VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
     const uint32_t grid = (uint32_t)((n_reads + MF_THREADS - 1) / MF_THREADS);
-    // packed-row capacity by the read length seen in the first record; longer reads bail
-    const uint32_t hint = c->read_len_hint;
-    if (hint <= 160)
-        k_map_fast<13, 16><<<grid, MF_THREADS, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, n_reads, d_slots,
-                                                               c->worklist.p, c->counters.p);
-    else if (hint <= 256)
-        k_map_fast<19, 16><<<grid, MF_THREADS, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, n_reads, d_slots,
-                                                               c->worklist.p, c->counters.p);
-    else
-        k_map_fast<23, 32><<<grid, MF_THREADS, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, n_reads, d_slots,
-                                                               c->worklist.p, c->counters.p);
+    IndexView v = c->index.view();
+#define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
+                                                                               row_words, n_reads, d_slots, c->worklist.p, c->counters.p)
+    if (d_rows) {
+        if (cap <= 160) VSPE_MF(13, 16, true); else if (cap <= 256) VSPE_MF(19, 16, true); else VSPE_MF(23, 32, true);
+    } else {
+        if (cap <= 160) VSPE_MF(13, 16, false); else if (cap <= 256) VSPE_MF(19, 16, false); else VSPE_MF(23, 32, false);
+    }
+#undef VSPE_MF
     VSPE_LAUNCH_CHECK(c);
     // the exhaustive tier consumes the worklist; its length stays on the device
     VSPE_TRY(map_reads_generic_dev(c, d_buf, d_seq_start, d_seq_end, c->worklist.p, c->counters.p + CNT_WORK, d_slots));
     return VSPE_OK;
+}
+
+// packed-row capacity (bases) by the read length seen in the first records; longer reads bail
+uint32_t map_fast_cap(uint32_t hint) { return hint <= 160 ? 160 : hint <= 256 ? 256 : 320; }
+
+int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                   uint64_t n_reads, ReadSlot* d_slots) {
+    if (c->index.split_len > 320) return map_reads_generic(c, d_buf, d_seq_start, d_seq_end, n_reads, d_slots);
+    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, nullptr, nullptr, 0, map_fast_cap(c->read_len_hint), n_reads, d_slots);
+}
+
+int map_reads_packed(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                     const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
+                     uint64_t n_reads, ReadSlot* d_slots) {
+    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, row_words, cap, n_reads, d_slots);
 }
 
 }  // namespace vspe

@@ -28,7 +28,7 @@ __device__ __forceinline__ bool keep_node(uint32_t v, uint32_t kmin, uint32_t le
 __global__ void __launch_bounds__(MG_WARPS * 32)
 k_map_generic(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
               const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ worklist, uint64_t n_items_arg,
-              const unsigned long long* __restrict__ n_items_dev, ReadSlot* __restrict__ slots, uint32_t* __restrict__ scratch, uint64_t scratch_stride,
+              const unsigned long long* __restrict__ n_items_dev, uint64_t buf_n, ReadSlot* __restrict__ slots, uint32_t* __restrict__ scratch, uint64_t scratch_stride,
               uint32_t* __restrict__ spill, uint64_t spill_cap, unsigned long long* __restrict__ counters) {
     __shared__ uint32_t s_ntouch[MG_WARPS];
     __shared__ uint8_t s_seq[MG_WARPS][G_STAGE];
@@ -43,7 +43,18 @@ k_map_generic(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __r
 
     for (uint64_t item = gwarp; item < n_items; item += nwarps) {
         const uint64_t r = worklist ? worklist[item] : item;
-        const uint64_t s = seq_start[r], e = seq_end[r];
+        const uint64_t s = seq_start[r];
+        uint64_t e = seq_end[r];
+        if (e == ~0ull) {
+            // the scan kernel did not see the end of this (very long) line: first '\n' or '\r'
+            e = buf_n;
+            for (uint64_t q = s; q < buf_n; q += 32) {
+                const uint64_t i = q + lane;
+                const bool hit = i < buf_n && (buf[i] == '\n' || buf[i] == '\r');
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+                if (m) { e = q + (uint32_t)(__ffs((int)m) - 1); break; }
+            }
+        }
         const uint64_t rlen64 = e - s;
         const uint8_t* seq = buf + s;
         // stage the read in shared memory (coalesced) so the per-window loops hit LDS, and test
@@ -231,7 +242,7 @@ int map_reads_generic_list(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     if (!c->spill.p) VSPE_TRY(c->spill.reserve(4u << 20));
     uint64_t want = (n_items + MG_WARPS - 1) / MG_WARPS;
     uint32_t grid = (uint32_t)(want < nb ? want : nb);
-    k_map_generic<<<grid, MG_WARPS * 32, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, d_worklist, n_items, nullptr,
+    k_map_generic<<<grid, MG_WARPS * 32, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, d_worklist, n_items, nullptr, c->cur_buf_n,
                                                          d_slots, c->warp_scratch.p, stride, c->spill.p, c->spill.cap, c->counters.p);
     VSPE_LAUNCH_CHECK(c);
     return VSPE_OK;
@@ -249,7 +260,7 @@ int map_reads_generic_dev(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_st
     uint64_t stride;
     VSPE_TRY(prepare_scratch(c, nb, &stride));
     if (!c->spill.p) VSPE_TRY(c->spill.reserve(4u << 20));
-    k_map_generic<<<nb, MG_WARPS * 32, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, d_worklist, 0, d_n_items,
+    k_map_generic<<<nb, MG_WARPS * 32, 0, c->stream>>>(c->index.view(), d_buf, d_seq_start, d_seq_end, d_worklist, 0, d_n_items, c->cur_buf_n,
                                                        d_slots, c->warp_scratch.p, stride, c->spill.p, c->spill.cap, c->counters.p);
     VSPE_LAUNCH_CHECK(c);
     return VSPE_OK;

@@ -1,0 +1,369 @@
+// scan_pack.cu -- K1 + K2 fused: one pass over the raw FASTQ bytes.
+//
+// Replaces `readlines()` + `[s[:-1] ...]` (reference utils/VStrains_PE_Inference.py:149-159) and
+// the per-character work of `fseq.count("N")` / k-mer slicing (:160, :25).
+//
+// Per 64 KiB tile (one CTA, 3 CTAs per SM):
+//   1. one elected thread issues TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of the
+//      tile + a 16-byte front margin + a 512-byte back margin into shared memory;
+//   2. every lane builds terminator bitmasks of its 16-byte vectors from shared memory
+//      (universal newlines: '\n', "\r\n" once, lone '\r');
+//   3. warp reductions + one block exchange give the tile's terminator count, published for
+//      the decoupled look-back that yields the global line number of the tile's first line;
+//   4. terminators with line%4==0 start a sequence line, line%4==1 end it -> per-tile read
+//      table in shared memory (+ seq_start/seq_end in HBM for the exhaustive tier);
+//   5. half-warps pack each read the tile owns (its sequence line STARTS here) to 2 bits/base
+//      straight from the tile: 64-byte rows in HBM + one header word (length | flags).
+// The map kernel then never touches the raw bytes again.
+#include "ctx.cuh"
+
+namespace vspe {
+
+static constexpr int SP_WARPS = 8;
+static constexpr int SP_ITERS = 16;                              // 512-byte warp rows per warp
+static constexpr int SP_TILE = SP_WARPS * SP_ITERS * 32 * 16;    // 64 KiB
+static constexpr int SP_FRONT = 16;                              // bytes kept before the tile
+static constexpr int SP_BACK = 512;                              // bytes kept after the tile (>= longest packed read + 1)
+static constexpr int SP_MAXREC = 960;                           // reads a tile may own (else fallback path)
+static constexpr uint32_t SP_SMEM = SP_FRONT + SP_TILE + SP_BACK + SP_MAXREC * 8 + 64;
+
+#define LB_AGG (1ull << 62)
+#define LB_INC (2ull << 62)
+#define LB_VAL ((1ull << 62) - 1)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t movemask4b(uint32_t cmp) { return ((cmp & 0x80808080u) * 0x00204081u) >> 28; }
+
+// terminator / crlf masks of one 16-byte vector held in registers; `valid` = bitmask of the
+// bytes that belong to the buffer; next/prev = the neighbouring bytes (0 if outside)
+__device__ __forceinline__ void masks_from_vec(uint4 v, uint32_t valid, uint32_t next_byte, uint32_t prev_byte,
+                                               bool& non_ascii, uint32_t& term, uint32_t& crlf) {
+    term = 0;
+    crlf = 0;
+    const uint32_t hx = v.x | (v.x >> 1) | (v.x >> 2) | (v.x >> 3), hy = v.y | (v.y >> 1) | (v.y >> 2) | (v.y >> 3),
+                   hz = v.z | (v.z >> 1) | (v.z >> 2) | (v.z >> 3), hw = v.w | (v.w >> 1) | (v.w >> 2) | (v.w >> 3);
+    if (valid == 0xFFFFu) {
+        if ((v.x | v.y | v.z | v.w) & 0x80808080u) non_ascii = true;
+        if (((hx & hy & hz & hw) & 0x10101010u) == 0x10101010u) return;      // every byte has a non-zero high nibble
+    }
+    uint32_t nl = movemask4b(__vcmpeq4(v.x, 0x0A0A0A0Au)) | (movemask4b(__vcmpeq4(v.y, 0x0A0A0A0Au)) << 4) |
+                  (movemask4b(__vcmpeq4(v.z, 0x0A0A0A0Au)) << 8) | (movemask4b(__vcmpeq4(v.w, 0x0A0A0A0Au)) << 12);
+    uint32_t cr = movemask4b(__vcmpeq4(v.x, 0x0D0D0D0Du)) | (movemask4b(__vcmpeq4(v.y, 0x0D0D0D0Du)) << 4) |
+                  (movemask4b(__vcmpeq4(v.z, 0x0D0D0D0Du)) << 8) | (movemask4b(__vcmpeq4(v.w, 0x0D0D0D0Du)) << 12);
+    if (valid != 0xFFFFu) {
+        const uint32_t na = movemask4b(v.x) | (movemask4b(v.y) << 4) | (movemask4b(v.z) << 8) | (movemask4b(v.w) << 12);
+        if (na & valid) non_ascii = true;
+        nl &= valid;
+        cr &= valid;
+    }
+    term = nl | (cr & ~((nl >> 1) | (next_byte == '\n' ? 0x8000u : 0u)));
+    crlf = nl & ((cr << 1) | (prev_byte == '\r' ? 1u : 0u));
+}
+
+struct ScanPackArgs {
+    const uint8_t* buf;              // chunk start (may be misaligned)
+    uint64_t n;                      // chunk bytes
+    uint32_t head;                   // address of buf mod 16
+    unsigned long long* status;      // look-back words, one per tile (zeroed)
+    unsigned int* ticket;
+    unsigned long long* total_out;   // terminators in the chunk
+    uint64_t line_base;              // lines before this chunk
+    uint64_t rec_first;              // record number of slot 0 of the outputs
+    uint64_t n_slots;                // capacity of the per-read outputs
+    uint64_t* seq_start;             // [n_slots] chunk-relative
+    uint64_t* seq_end;
+    uint32_t* rows;                  // [n_slots][row_words] packed reads
+    uint32_t* hdr;                   // [n_slots] rlen | flags << 24
+    uint32_t row_words;              // 12, 16 or 20
+    uint32_t cap;                    // longest read (bases) the map kernel's packed rows hold
+    uint32_t n_tiles;
+    unsigned long long* counters;
+};
+
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+k_scan_pack(ScanPackArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_bytes = smem;                                           // [SP_FRONT + SP_TILE + SP_BACK]
+    uint32_t* s_rs = reinterpret_cast<uint32_t*>(smem + SP_FRONT + SP_TILE + SP_BACK);   // read start (tile-relative + SP_FRONT)
+    uint32_t* s_re = s_rs + SP_MAXREC;                                 // read end
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_wtot[SP_WARPS];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_excl;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        s_tile = atomicAdd(a.ticket, 1u);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    // aligned coordinates: byte `off` of the aligned stream is buffer position off - head
+    const uint64_t A = ((uint64_t)a.head + a.n + 15) & ~15ull;         // aligned stream length
+    const uint64_t t_lo = (uint64_t)tile * SP_TILE;
+    const uint64_t ld_lo = t_lo >= SP_FRONT ? t_lo - SP_FRONT : 0;
+    const uint64_t ld_hi = min(A, t_lo + SP_TILE + SP_BACK);
+    const uint32_t s_off0 = tile == 0 ? SP_FRONT : 0;                  // where ld_lo lands in s_bytes
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(ld_hi - ld_lo);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes) : "memory");
+        const uint8_t* src = a.buf - a.head + ld_lo;
+        uint32_t done = 0;
+        while (done < bytes) {
+            const uint32_t part = min(bytes - done, 16384u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(s_bytes + s_off0 + done)),
+                         "l"(__cvta_generic_to_global(src + done)), "r"(part), "r"(smem_u32(&s_bar))
+                         : "memory");
+            done += part;
+        }
+    }
+    {   // wait for the bytes
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(smem_u32(&s_bar)), "r"(0) : "memory");
+        }
+    }
+    // tile byte j (0 <= j < SP_TILE) lives at s_bytes[SP_FRONT + j]; its buffer position is t_lo + j - head
+    const uint8_t* tb = s_bytes + SP_FRONT;
+    const int64_t pos0 = (int64_t)t_lo - a.head;                       // buffer position of tile byte 0
+    const int64_t nn = (int64_t)a.n;
+    auto byte_at = [&](int64_t j) -> uint32_t {                         // tile-relative byte, 0 outside the buffer
+        const int64_t p = pos0 + j;
+        return (p >= 0 && p < nn) ? tb[j] : 0u;
+    };
+
+    // ---- terminator masks, warp row layout: warp w owns tile bytes [w*8K, (w+1)*8K) ----------
+    uint32_t mk[SP_ITERS], cnt = 0;
+    bool bad = false;
+#pragma unroll
+    for (int it = 0; it < SP_ITERS; it++) {
+        const uint32_t j = ((wib * SP_ITERS + it) * 32 + lane) * 16;    // tile-relative byte of this vector
+        const int64_t p = pos0 + j;
+        uint32_t term = 0, crlf = 0;
+        if (p < nn && p + 16 > 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tb + j);
+            uint32_t valid = 0xFFFFu;
+            if (p < 0) valid &= 0xFFFFu << (uint32_t)(-p);
+            if (p + 16 > nn) valid &= 0xFFFFu >> (uint32_t)(p + 16 - nn);
+            masks_from_vec(v, valid, byte_at((int64_t)j + 16), byte_at((int64_t)j - 1), bad, term, crlf);
+        }
+        mk[it] = term | (crlf << 16);
+        cnt += __popc(term);
+    }
+    if (bad) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_NON_ASCII);
+    const uint32_t wtot = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane == 0) s_wtot[wib] = wtot;
+    __syncthreads();
+    uint32_t tile_total = 0, warp_base = 0;
+#pragma unroll
+    for (int w = 0; w < SP_WARPS; w++) {
+        const uint32_t x = s_wtot[w];
+        if (w < (int)wib) warp_base += x;
+        tile_total += x;
+    }
+    // ---- decoupled look-back (warp 0) --------------------------------------------------------
+    if (wib == 0) {
+        volatile unsigned long long* vs = a.status;
+        if (tile == 0) {
+            if (lane == 0) { vs[0] = LB_INC | tile_total; s_excl = 0; }
+        } else {
+            if (lane == 0) vs[tile] = LB_AGG | tile_total;
+            unsigned long long excl = 0;
+            int64_t look = (int64_t)tile - 1;
+            while (true) {
+                const int64_t idx = look - lane;
+                unsigned long long st = idx >= 0 ? vs[idx] : LB_INC;
+                while (__any_sync(0xFFFFFFFFu, (st >> 62) == 0)) {
+                    if ((st >> 62) == 0) st = vs[idx];
+                }
+                const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2);
+                const int first = inc ? __ffs((int)inc) - 1 : 32;
+                unsigned long long c = (int)lane <= first ? (st & LB_VAL) : 0ull;
+                for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+                excl += c;
+                if (inc) break;
+                look -= 32;
+            }
+            if (lane == 0) { vs[tile] = LB_INC | (excl + tile_total); s_excl = excl; }
+        }
+        if (lane == 0 && tile == a.n_tiles - 1) *a.total_out = s_excl + tile_total;
+    }
+    __syncthreads();
+    const uint64_t base = a.line_base + s_excl;                        // line number of the tile's first line
+    // reads owned by this tile: sequence lines that START here = header terminators (line%4==0)
+    // in the tile; record numbers are consecutive from r_own0
+    const uint64_t r_own0 = (base + 3) >> 2;
+    const uint64_t last_line = base + tile_total;                      // one past the tile's last terminator
+    uint32_t n_own = (uint32_t)(((last_line + 3) >> 2) - r_own0);      // #{l in [base, last_line) : l%4 == 0}
+    const bool chunk_starts_in_seq = tile == 0 && (a.line_base & 3) == 1;   // chunk begins with a sequence line
+    const uint32_t shift = chunk_starts_in_seq ? 1u : 0u;              // that read becomes local index 0
+    const uint32_t n_local = n_own + shift;
+    const bool too_many = n_local > SP_MAXREC;
+    if (too_many) {
+        if (threadIdx.x == 0) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_TILE_FULL);
+        return;
+    }
+    for (uint32_t i = threadIdx.x; i < n_local; i += blockDim.x) s_re[i] = 0xFFFFFFFFu;
+    if (chunk_starts_in_seq && threadIdx.x == 0) s_rs[0] = (uint32_t)a.head;   // buffer position 0, tile-relative
+    __syncthreads();
+    // ---- emission: ranks from warp scans ------------------------------------------------------
+    {
+        uint64_t running = base + warp_base;
+#pragma unroll
+        for (int it = 0; it < SP_ITERS; it++) {
+            uint32_t mask = mk[it] & 0xFFFFu;
+            const uint32_t crlf = mk[it] >> 16;
+            const uint32_t c = __popc(mask);
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= (uint32_t)d) inc += y;
+            }
+            const uint32_t row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            uint64_t line = running + inc - c;
+            running += row_total;
+            const uint32_t j0 = ((wib * SP_ITERS + it) * 32 + lane) * 16;
+            while (mask) {
+                const int i = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                const uint32_t j = j0 + i;                               // tile-relative terminator position
+                const uint32_t phase = (uint32_t)line & 3;
+                if (phase == 0) {
+                    s_rs[(uint32_t)((line >> 2) - r_own0) + shift] = j + 1;
+                } else if (phase == 1) {
+                    const uint64_t r = line >> 2;
+                    const uint32_t e = ((crlf >> i) & 1) ? j - 1 : j;
+                    if (r >= r_own0) s_re[(uint32_t)(r - r_own0) + shift] = e;
+                    else if (chunk_starts_in_seq && r + 1 == r_own0) s_re[0] = e;
+                    // (a sequence line that started in the previous tile is packed by that tile)
+                }
+                line++;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- pack: one half-warp per read --------------------------------------------------------
+    const uint64_t r_loc0 = r_own0 - shift;                            // record number of local index 0
+    const uint32_t RW = a.row_words;
+    const uint32_t cap = a.cap;
+    const uint32_t hw = threadIdx.x >> 4, hl = threadIdx.x & 15;       // half-warp id / lane in it
+    const uint32_t hmask = 0xFFFFu << (16 * ((threadIdx.x >> 4) & 1));
+    for (uint32_t li = hw; li < n_local; li += SP_WARPS * 2) {
+        const uint64_t r = r_loc0 + li;
+        const uint64_t slot = r - a.rec_first;
+        const uint32_t st = s_rs[li];
+        uint32_t en = s_re[li];
+        uint32_t flags = 0;
+        if (en == 0xFFFFFFFFu) {
+            // the line ends beyond the tile: first '\n' or '\r' in the back margin, if any
+            uint32_t found = 0xFFFFFFFFu;
+            for (uint32_t k = 0; k < SP_BACK && found == 0xFFFFFFFFu; k += 16) {
+                const uint32_t j = SP_TILE + k + hl;
+                const uint32_t ch = byte_at(j);
+                const int64_t p = pos0 + j;
+                const bool hit = (p < nn) && (ch == '\n' || ch == '\r');
+                const uint32_t m = (__ballot_sync(hmask, hit) >> (16 * ((threadIdx.x >> 4) & 1))) & 0xFFFFu;
+                if (m) found = SP_TILE + k + (uint32_t)(__ffs((int)m) - 1);
+            }
+            if (found == 0xFFFFFFFFu) flags |= PH_LONG; else en = found;
+        }
+        uint32_t rlen = (flags & PH_LONG) ? 0u : en - st;
+        if (rlen > cap) { flags |= PH_LONG; rlen = 0; }
+        if (slot >= a.n_slots) {                                       // output table too small: retry
+            if (hl == 0) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_SLOTS_FULL);
+            continue;
+        }
+        const uint32_t nwords = (rlen + 15) >> 4;
+        bool hasN = false, badc = false;
+        for (uint32_t w0 = 0; w0 < RW; w0 += 16) {
+            const uint32_t w = w0 + hl;
+            uint32_t packed = 0;
+            if (w < nwords) {
+                const uint32_t jb = st + 16 * w;                        // tile-relative first byte of 16 bases
+                const uint32_t nb = min(16u, rlen - 16 * w);
+                const uint32_t al = (SP_FRONT + jb) & 3;                // s_bytes is 16-byte aligned
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(s_bytes + ((SP_FRONT + jb) & ~3u));
+                const uint32_t sh = al * 8;
+                uint32_t x[5];
+#pragma unroll
+                for (int q = 0; q < 5; q++) x[q] = p[q];
+                uint32_t diff = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
+                    const int left = (int)nb - 4 * q;
+                    if (left <= 0) break;
+                    const uint32_t vm = left >= 4 ? 0xFFFFFFFFu : ((1u << (8 * left)) - 1);
+                    const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
+                    const uint32_t is2 = (c2 >> 1) & ~c2 & 0x01010101u;
+                    const uint32_t expect = 0x41414141u + 2 * c2 + 15 * is2;
+                    diff |= (expect ^ c) & vm;
+                    packed |= ((c2 * 0x01041040u) >> 24) << (8 * q);
+                }
+                if (diff) {
+                    for (uint32_t q = 0; q < nb; q++) {
+                        const uint32_t c = tb[jb + q];
+                        if (c == 'N') hasN = true;
+                        else if (!is_acgt(c)) badc = true;
+                    }
+                }
+            }
+            if (w < RW) a.rows[slot * RW + w] = packed;
+        }
+        const uint32_t bN = __ballot_sync(hmask, hasN) & hmask, bB = __ballot_sync(hmask, badc) & hmask;
+        if (hl == 0) {
+            a.hdr[slot] = rlen | flags | (bN ? PH_N : 0) | (bB ? PH_BAD : 0);
+            const uint64_t gs = (uint64_t)((int64_t)st + pos0);          // chunk-relative start
+            a.seq_start[slot] = gs;
+            a.seq_end[slot] = (flags & PH_LONG) && en == 0xFFFFFFFFu ? ~0ull : (uint64_t)((int64_t)en + pos0);
+        }
+    }
+}
+
+int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
+              uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
+              uint64_t* n_terms, unsigned long long* err_flags) {
+    *n_terms = 0;
+    *err_flags = 0;
+    if (n == 0) return VSPE_OK;
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
+    const uint64_t n_tiles = (n + head + SP_TILE - 1) / SP_TILE;
+    if (n_tiles > 0x7FFFFFFFull) { set_error("buffer too large for one scan launch"); return VSPE_ERR_LIMIT; }
+    VSPE_TRY(c->tile_base.reserve(n_tiles + 4));
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(c->tile_base.p);
+    VSPE_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 4) * 8, c->stream));
+    if (!c->scan_pack_attr_set) {
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        c->scan_pack_attr_set = true;
+    }
+    ScanPackArgs a;
+    a.buf = d_buf; a.n = n; a.head = head; a.status = status;
+    a.ticket = reinterpret_cast<unsigned int*>(status + n_tiles + 1);
+    a.total_out = status + n_tiles + 2;
+    a.line_base = line_base; a.rec_first = rec_first; a.n_slots = n_slots;
+    a.seq_start = d_seq_start; a.seq_end = d_seq_end; a.rows = d_rows; a.hdr = d_hdr; a.row_words = row_words; a.cap = cap;
+    a.n_tiles = (uint32_t)n_tiles; a.counters = c->counters.p;
+    k_scan_pack<<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
+    VSPE_LAUNCH_CHECK(c);
+    unsigned long long h_total = 0, h_err = 0;
+    VSPE_CUDA(cudaMemcpyAsync(&h_total, a.total_out, 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    *n_terms = h_total;
+    *err_flags = h_err;
+    const unsigned long long transient = ERRF_SLOTS_FULL | ERRF_TILE_FULL;
+    if (h_err & transient) {
+        unsigned long long cleared = h_err & ~transient;
+        VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_ERR, &cleared, 8, cudaMemcpyHostToDevice, c->stream));
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return VSPE_OK;
+}
+
+}  // namespace vspe

@@ -222,8 +222,11 @@ struct Index {
 // per-mate record table produced by K1 for one chunk
 struct Records {
     DevBuf<uint64_t> seq_start;   // chunk-relative byte offset of the 2nd line of each record
-    DevBuf<uint64_t> seq_end;     // one past its last content byte
+    DevBuf<uint64_t> seq_end;     // one past its last content byte (~0: beyond the scan margin)
+    DevBuf<uint32_t> rows;        // [n][row_words] 2-bit packed reads written by k_scan_pack
+    DevBuf<uint32_t> hdr;         // [n] rlen | flags << 24
 };
+static constexpr uint32_t PH_N = 1u << 24, PH_BAD = 2u << 24, PH_LONG = 4u << 24;
 
 struct Ctx;   // defined in api.cu
 
@@ -237,6 +240,10 @@ int scan_index_records(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_b
 
 int scan_records_single_pass(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first,
                              uint64_t n_slots, uint64_t* d_seq_start, uint64_t* d_seq_end, uint64_t* n_terms, bool* overflow);
+
+int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
+              uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
+              uint64_t* n_terms, unsigned long long* err_flags);
 
 // K2+K4: map reads [0, n_reads) of a chunk into slots[rec_off + r]
 int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
