@@ -19,13 +19,14 @@
 
 namespace vspe {
 
-static constexpr int SP_WARPS = 8;
+static constexpr int SP_WARPS = 6;
 static constexpr int SP_ITERS = 16;                              // 512-byte warp rows per warp
-static constexpr int SP_TILE = SP_WARPS * SP_ITERS * 32 * 16;    // 64 KiB
+static constexpr int SP_TILE = SP_WARPS * SP_ITERS * 32 * 16;    // 48 KiB
 static constexpr int SP_FRONT = 16;                              // bytes kept before the tile
 static constexpr int SP_BACK = 512;                              // bytes kept after the tile (>= longest packed read + 1)
-static constexpr int SP_MAXREC = 960;                           // reads a tile may own (else fallback path)
-static constexpr uint32_t SP_SMEM = SP_FRONT + SP_TILE + SP_BACK + SP_MAXREC * 8 + 64;
+static constexpr int SP_MAXREC = 768;                            // reads a tile may own (else fallback path)
+static constexpr int SP_QCAP = 256;                              // per warp: vectors that may hold a terminator
+static constexpr uint32_t SP_SMEM = SP_FRONT + SP_TILE + SP_BACK + SP_MAXREC * 8 + SP_WARPS * SP_QCAP * 8 + 64;
 
 #define LB_AGG (1ull << 62)
 #define LB_INC (2ull << 62)
@@ -41,12 +42,7 @@ __device__ __forceinline__ void masks_from_vec(uint4 v, uint32_t valid, uint32_t
                                                bool& non_ascii, uint32_t& term, uint32_t& crlf) {
     term = 0;
     crlf = 0;
-    const uint32_t hx = v.x | (v.x >> 1) | (v.x >> 2) | (v.x >> 3), hy = v.y | (v.y >> 1) | (v.y >> 2) | (v.y >> 3),
-                   hz = v.z | (v.z >> 1) | (v.z >> 2) | (v.z >> 3), hw = v.w | (v.w >> 1) | (v.w >> 2) | (v.w >> 3);
-    if (valid == 0xFFFFu) {
-        if ((v.x | v.y | v.z | v.w) & 0x80808080u) non_ascii = true;
-        if (((hx & hy & hz & hw) & 0x10101010u) == 0x10101010u) return;      // every byte has a non-zero high nibble
-    }
+    if (valid == 0xFFFFu && ((v.x | v.y | v.z | v.w) & 0x80808080u)) non_ascii = true;
     uint32_t nl = movemask4b(__vcmpeq4(v.x, 0x0A0A0A0Au)) | (movemask4b(__vcmpeq4(v.y, 0x0A0A0A0Au)) << 4) |
                   (movemask4b(__vcmpeq4(v.z, 0x0A0A0A0Au)) << 8) | (movemask4b(__vcmpeq4(v.w, 0x0A0A0A0Au)) << 12);
     uint32_t cr = movemask4b(__vcmpeq4(v.x, 0x0D0D0D0Du)) | (movemask4b(__vcmpeq4(v.y, 0x0D0D0D0Du)) << 4) |
@@ -88,6 +84,9 @@ k_scan_pack(ScanPackArgs a) {
     uint8_t* s_bytes = smem;                                           // [SP_FRONT + SP_TILE + SP_BACK]
     uint32_t* s_rs = reinterpret_cast<uint32_t*>(smem + SP_FRONT + SP_TILE + SP_BACK);   // read start (tile-relative + SP_FRONT)
     uint32_t* s_re = s_rs + SP_MAXREC;                                 // read end
+    uint32_t* s_qmk = s_re + SP_MAXREC;                                // [SP_WARPS][SP_QCAP] term | crlf << 16
+    uint16_t* s_qid = reinterpret_cast<uint16_t*>(s_qmk + SP_WARPS * SP_QCAP);   // vector index in the tile
+    uint16_t* s_qrk = s_qid + SP_WARPS * SP_QCAP;                      // rank of the vector's first terminator in the warp
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_wtot[SP_WARPS];
     __shared__ uint32_t s_tile;
@@ -137,34 +136,83 @@ k_scan_pack(ScanPackArgs a) {
         return (p >= 0 && p < nn) ? tb[j] : 0u;
     };
 
-    // ---- terminator masks, warp row layout: warp w owns tile bytes [w*8K, (w+1)*8K) ----------
-    uint32_t mk[SP_ITERS], cnt = 0;
-    bool bad = false;
+    // ---- M1: which 16-byte vectors can hold a terminator?  ('\n' and '\r' are < 0x10) -----------
+    // Warp w owns tile bytes [w*8K, (w+1)*8K) as 16 coalesced 512-byte rows.  Candidate vectors are
+    // appended, in (row, lane) order, to the warp's queue, so everything after this loop runs on a
+    // dense list instead of diverging on every row.
+    uint16_t* q_id = s_qid + wib * SP_QCAP;
+    uint32_t* q_mk = s_qmk + wib * SP_QCAP;
+    uint16_t* q_rk = s_qrk + wib * SP_QCAP;
+    const bool interior = pos0 >= 1 && pos0 + SP_TILE + 16 <= nn;   // CTA-uniform
+    const uint32_t lt = (1u << lane) - 1;
+    uint32_t qn = 0, ora = 0;
 #pragma unroll
     for (int it = 0; it < SP_ITERS; it++) {
-        const uint32_t j = ((wib * SP_ITERS + it) * 32 + lane) * 16;    // tile-relative byte of this vector
-        const int64_t p = pos0 + j;
+        const uint32_t vid = (wib * SP_ITERS + it) * 32 + lane;       // vector index inside the tile
+        const uint4 v = *reinterpret_cast<const uint4*>(tb + vid * 16);
+        bool cand, full = true;
+        if (!interior) {                                               // first / last tile of the chunk
+            const int64_t p = pos0 + (int64_t)vid * 16;
+            full = p >= 0 && p + 16 <= nn;
+            cand = !full && p < nn && p + 16 > 0;                      // partial vector: M2 masks the outside bytes
+        }
+        if (full) {
+            ora |= v.x | v.y | v.z | v.w;
+            const uint32_t low = ((v.x - 0x10101010u) & ~v.x) | ((v.y - 0x10101010u) & ~v.y) |
+                                 ((v.z - 0x10101010u) & ~v.z) | ((v.w - 0x10101010u) & ~v.w);
+            cand = (low & 0x80808080u) != 0;
+        }
+        const uint32_t bm = __ballot_sync(0xFFFFFFFFu, cand);
+        if (cand) {
+            const uint32_t at = qn + __popc(bm & lt);
+            if (at < SP_QCAP) q_id[at] = (uint16_t)vid;
+        }
+        qn += __popc(bm);
+    }
+    bool bad = (ora & 0x80808080u) != 0;
+    const bool q_over = qn > SP_QCAP;
+    if (q_over) qn = SP_QCAP;
+    __syncwarp();
+    // ---- M2: exact terminator / crlf masks of the candidates + their ranks inside the warp -----
+    uint32_t wcount = 0;
+    for (uint32_t i0 = 0; i0 < qn; i0 += 32) {
+        const uint32_t i = i0 + lane;
         uint32_t term = 0, crlf = 0;
-        if (p < nn && p + 16 > 0) {
+        if (i < qn) {
+            const uint32_t vid = q_id[i];
+            const uint32_t j = vid * 16;
             const uint4 v = *reinterpret_cast<const uint4*>(tb + j);
             uint32_t valid = 0xFFFFu;
-            if (p < 0) valid &= 0xFFFFu << (uint32_t)(-p);
-            if (p + 16 > nn) valid &= 0xFFFFu >> (uint32_t)(p + 16 - nn);
-            masks_from_vec(v, valid, byte_at((int64_t)j + 16), byte_at((int64_t)j - 1), bad, term, crlf);
+            if (!interior) {
+                const int64_t p = pos0 + j;
+                if (p < 0) valid &= 0xFFFFu << (uint32_t)(-p);
+                if (p + 16 > nn) valid &= 0xFFFFu >> (uint32_t)(p + 16 - nn);
+            }
+            masks_from_vec(v, valid, interior ? (uint32_t)tb[j + 16] : byte_at((int64_t)j + 16),
+                           interior ? (uint32_t)tb[(int)j - 1] : byte_at((int64_t)j - 1), bad, term, crlf);
+            q_mk[i] = term | (crlf << 16);
         }
-        mk[it] = term | (crlf << 16);
-        cnt += __popc(term);
+        const uint32_t c = __popc(term);
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        if (i < qn) q_rk[i] = (uint16_t)(wcount + inc - c);
+        wcount += __shfl_sync(0xFFFFFFFFu, inc, 31);
     }
     if (bad) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_NON_ASCII);
-    const uint32_t wtot = __reduce_add_sync(0xFFFFFFFFu, cnt);
-    if (lane == 0) s_wtot[wib] = wtot;
+    if (lane == 0) s_wtot[wib] = wcount | (q_over ? 0x80000000u : 0u);
     __syncthreads();
     uint32_t tile_total = 0, warp_base = 0;
+    bool any_over = false;
 #pragma unroll
     for (int w = 0; w < SP_WARPS; w++) {
         const uint32_t x = s_wtot[w];
-        if (w < (int)wib) warp_base += x;
-        tile_total += x;
+        any_over |= (x >> 31) != 0;
+        if (w < (int)wib) warp_base += x & 0x7FFFFFFFu;
+        tile_total += x & 0x7FFFFFFFu;
     }
     // ---- decoupled look-back (warp 0) --------------------------------------------------------
     if (wib == 0) {
@@ -203,7 +251,7 @@ k_scan_pack(ScanPackArgs a) {
     const bool chunk_starts_in_seq = tile == 0 && (a.line_base & 3) == 1;   // chunk begins with a sequence line
     const uint32_t shift = chunk_starts_in_seq ? 1u : 0u;              // that read becomes local index 0
     const uint32_t n_local = n_own + shift;
-    const bool too_many = n_local > SP_MAXREC;
+    const bool too_many = n_local > SP_MAXREC || any_over;
     if (too_many) {
         if (threadIdx.x == 0) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_TILE_FULL);
         return;
@@ -211,117 +259,107 @@ k_scan_pack(ScanPackArgs a) {
     for (uint32_t i = threadIdx.x; i < n_local; i += blockDim.x) s_re[i] = 0xFFFFFFFFu;
     if (chunk_starts_in_seq && threadIdx.x == 0) s_rs[0] = (uint32_t)a.head;   // buffer position 0, tile-relative
     __syncthreads();
-    // ---- emission: ranks from warp scans ------------------------------------------------------
-    {
-        uint64_t running = base + warp_base;
-#pragma unroll
-        for (int it = 0; it < SP_ITERS; it++) {
-            uint32_t mask = mk[it] & 0xFFFFu;
-            const uint32_t crlf = mk[it] >> 16;
-            const uint32_t c = __popc(mask);
-            uint32_t inc = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= (uint32_t)d) inc += y;
+    // ---- emission: every queue entry knows its rank -> line numbers -> read table ---------------
+    for (uint32_t i = lane; i < qn; i += 32) {
+        uint32_t mask = q_mk[i] & 0xFFFFu;
+        const uint32_t crlf = q_mk[i] >> 16;
+        const uint32_t j0 = (uint32_t)q_id[i] * 16;
+        uint64_t line = base + warp_base + q_rk[i];
+        while (mask) {
+            const int k = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            const uint32_t j = j0 + k;                                   // tile-relative terminator position
+            const uint32_t phase = (uint32_t)line & 3;
+            if (phase == 0) {
+                s_rs[(uint32_t)((line >> 2) - r_own0) + shift] = j + 1;
+            } else if (phase == 1) {
+                const uint64_t r = line >> 2;
+                const uint32_t e = ((crlf >> k) & 1) ? j - 1 : j;
+                if (r >= r_own0) s_re[(uint32_t)(r - r_own0) + shift] = e;
+                else if (chunk_starts_in_seq && r + 1 == r_own0) s_re[0] = e;
+                // (a sequence line that started in the previous tile is packed by that tile)
             }
-            const uint32_t row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            uint64_t line = running + inc - c;
-            running += row_total;
-            const uint32_t j0 = ((wib * SP_ITERS + it) * 32 + lane) * 16;
-            while (mask) {
-                const int i = __ffs((int)mask) - 1;
-                mask &= mask - 1;
-                const uint32_t j = j0 + i;                               // tile-relative terminator position
-                const uint32_t phase = (uint32_t)line & 3;
-                if (phase == 0) {
-                    s_rs[(uint32_t)((line >> 2) - r_own0) + shift] = j + 1;
-                } else if (phase == 1) {
-                    const uint64_t r = line >> 2;
-                    const uint32_t e = ((crlf >> i) & 1) ? j - 1 : j;
-                    if (r >= r_own0) s_re[(uint32_t)(r - r_own0) + shift] = e;
-                    else if (chunk_starts_in_seq && r + 1 == r_own0) s_re[0] = e;
-                    // (a sequence line that started in the previous tile is packed by that tile)
-                }
-                line++;
-            }
+            line++;
         }
     }
     __syncthreads();
-    // ---- pack: one half-warp per read --------------------------------------------------------
+    // ---- pack: LPRP lanes per read, 32 bases (two 32-bit words) per lane ---------------------------
     const uint64_t r_loc0 = r_own0 - shift;                            // record number of local index 0
     const uint32_t RW = a.row_words;
     const uint32_t cap = a.cap;
-    const uint32_t hw = threadIdx.x >> 4, hl = threadIdx.x & 15;       // half-warp id / lane in it
-    const uint32_t hmask = 0xFFFFu << (16 * ((threadIdx.x >> 4) & 1));
-    for (uint32_t li = hw; li < n_local; li += SP_WARPS * 2) {
-        const uint64_t r = r_loc0 + li;
-        const uint64_t slot = r - a.rec_first;
-        const uint32_t st = s_rs[li];
-        uint32_t en = s_re[li];
+    const uint32_t LPRP = RW > 16 ? 16u : 8u;                          // lanes per read (CTA-uniform)
+    const uint32_t gpw = 32 / LPRP;                                    // reads per warp step
+    const uint32_t grp = lane / LPRP, gl = lane % LPRP;
+    const uint32_t gmask = (LPRP == 16 ? 0xFFFFu : 0xFFu) << (grp * LPRP);
+    for (uint32_t li0 = wib * gpw; li0 < n_local; li0 += SP_WARPS * gpw) {
+        const uint32_t li = li0 + grp;
+        const bool live = li < n_local;
+        const uint64_t slot = r_loc0 + li - a.rec_first;
+        const uint32_t st = live ? s_rs[li] : 0;
+        uint32_t en = live ? s_re[li] : 0;
         uint32_t flags = 0;
-        if (en == 0xFFFFFFFFu) {
-            // the line ends beyond the tile: first '\n' or '\r' in the back margin, if any
-            uint32_t found = 0xFFFFFFFFu;
-            for (uint32_t k = 0; k < SP_BACK && found == 0xFFFFFFFFu; k += 16) {
-                const uint32_t j = SP_TILE + k + hl;
-                const uint32_t ch = byte_at(j);
-                const int64_t p = pos0 + j;
-                const bool hit = (p < nn) && (ch == '\n' || ch == '\r');
-                const uint32_t m = (__ballot_sync(hmask, hit) >> (16 * ((threadIdx.x >> 4) & 1))) & 0xFFFFu;
-                if (m) found = SP_TILE + k + (uint32_t)(__ffs((int)m) - 1);
+        if (__any_sync(0xFFFFFFFFu, live && en == 0xFFFFFFFFu)) {
+            // some line ends beyond the tile: first '\n' or '\r' in the back margin, if any
+            for (uint32_t g = 0; g < gpw; g++) {
+                const uint32_t en_g = __shfl_sync(0xFFFFFFFFu, en, g * LPRP);
+                const bool live_g = __shfl_sync(0xFFFFFFFFu, (uint32_t)live, g * LPRP) != 0;
+                if (!live_g || en_g != 0xFFFFFFFFu) continue;
+                uint32_t found = 0xFFFFFFFFu;
+                for (uint32_t k = 0; k < SP_BACK && found == 0xFFFFFFFFu; k += 32) {
+                    const uint32_t j = SP_TILE + k + lane;
+                    const uint32_t ch = tb[j];
+                    const bool hit = (pos0 + j < nn) && (ch == '\n' || ch == '\r');
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+                    if (m) found = SP_TILE + k + (uint32_t)(__ffs((int)m) - 1);
+                }
+                if (grp == g) en = found;
             }
-            if (found == 0xFFFFFFFFu) flags |= PH_LONG; else en = found;
+            if (live && en == 0xFFFFFFFFu) flags |= PH_LONG;
         }
-        uint32_t rlen = (flags & PH_LONG) ? 0u : en - st;
+        uint32_t rlen = (!live || (flags & PH_LONG)) ? 0u : en - st;
         if (rlen > cap) { flags |= PH_LONG; rlen = 0; }
-        if (slot >= a.n_slots) {                                       // output table too small: retry
-            if (hl == 0) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_SLOTS_FULL);
-            continue;
-        }
-        const uint32_t nwords = (rlen + 15) >> 4;
+        const bool fits = live && slot < a.n_slots;
+        if (live && !fits && gl == 0) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_SLOTS_FULL);
         bool hasN = false, badc = false;
-        for (uint32_t w0 = 0; w0 < RW; w0 += 16) {
-            const uint32_t w = w0 + hl;
-            uint32_t packed = 0;
-            if (w < nwords) {
-                const uint32_t jb = st + 16 * w;                        // tile-relative first byte of 16 bases
-                const uint32_t nb = min(16u, rlen - 16 * w);
-                const uint32_t al = (SP_FRONT + jb) & 3;                // s_bytes is 16-byte aligned
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(s_bytes + ((SP_FRONT + jb) & ~3u));
-                const uint32_t sh = al * 8;
-                uint32_t x[5];
+        const uint32_t b0 = 32 * gl;
+        uint32_t w0 = 0, w1 = 0;
+        if (b0 < rlen) {
+            const uint32_t nb = min(32u, rlen - b0);
+            const uint32_t jb = SP_FRONT + st + b0;                     // offset in s_bytes (16-byte aligned base)
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(s_bytes + (jb & ~3u));
+            const uint32_t sh = (jb & 3) * 8;
+            uint32_t x[9];
 #pragma unroll
-                for (int q = 0; q < 5; q++) x[q] = p[q];
-                uint32_t diff = 0;
+            for (int q = 0; q < 9; q++) x[q] = p[q];
+            uint32_t diff = 0;
+            uint32_t pk[8];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
-                    const int left = (int)nb - 4 * q;
-                    if (left <= 0) break;
-                    const uint32_t vm = left >= 4 ? 0xFFFFFFFFu : ((1u << (8 * left)) - 1);
-                    const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
-                    const uint32_t is2 = (c2 >> 1) & ~c2 & 0x01010101u;
-                    const uint32_t expect = 0x41414141u + 2 * c2 + 15 * is2;
-                    diff |= (expect ^ c) & vm;
-                    packed |= ((c2 * 0x01041040u) >> 24) << (8 * q);
-                }
-                if (diff) {
-                    for (uint32_t q = 0; q < nb; q++) {
-                        const uint32_t c = tb[jb + q];
-                        if (c == 'N') hasN = true;
-                        else if (!is_acgt(c)) badc = true;
-                    }
+            for (int q = 0; q < 8; q++) {
+                const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
+                const int left = (int)nb - 4 * q;                       // valid bytes in this word
+                const uint32_t vm = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << (8 * left)) - 1);
+                const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
+                // the only byte with code k is "ACTG"[k] = 0x41 + 2k (+15 when k == 2)
+                const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
+                diff |= (expect ^ c) & vm;
+                pk[q] = (c2 * 0x01041040u) >> 24;
+            }
+            w0 = pk[0] | (pk[1] << 8) | (pk[2] << 16) | (pk[3] << 24);
+            w1 = pk[4] | (pk[5] << 8) | (pk[6] << 16) | (pk[7] << 24);
+            if (diff) {                                                 // rare: some byte is not ACGT
+                for (uint32_t q = 0; q < nb; q++) {
+                    const uint32_t c = s_bytes[jb + q];
+                    if (c == 'N') hasN = true;
+                    else if (!is_acgt(c)) badc = true;
                 }
             }
-            if (w < RW) a.rows[slot * RW + w] = packed;
         }
-        const uint32_t bN = __ballot_sync(hmask, hasN) & hmask, bB = __ballot_sync(hmask, badc) & hmask;
-        if (hl == 0) {
+        if (fits && 2 * gl < RW) *reinterpret_cast<uint2*>(a.rows + slot * RW + 2 * gl) = make_uint2(w0, w1);
+        const uint32_t bN = __ballot_sync(0xFFFFFFFFu, hasN) & gmask, bB = __ballot_sync(0xFFFFFFFFu, badc) & gmask;
+        if (fits && gl == 0) {
             a.hdr[slot] = rlen | flags | (bN ? PH_N : 0) | (bB ? PH_BAD : 0);
-            const uint64_t gs = (uint64_t)((int64_t)st + pos0);          // chunk-relative start
-            a.seq_start[slot] = gs;
-            a.seq_end[slot] = (flags & PH_LONG) && en == 0xFFFFFFFFu ? ~0ull : (uint64_t)((int64_t)en + pos0);
+            a.seq_start[slot] = (uint64_t)((int64_t)st + pos0);          // chunk-relative start
+            a.seq_end[slot] = en == 0xFFFFFFFFu ? ~0ull : (uint64_t)((int64_t)en + pos0);
         }
     }
 }
