@@ -747,6 +747,11 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "chunk_mb")) c->opt_chunk_mb = value;
     else if (!strcmp(name, "scan_two_pass")) c->opt_scan_two_pass = value;
     else if (!strcmp(name, "scan_mode")) c->opt_scan_mode = value;
+    else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value;
+    else if (!strcmp(name, "dbg_dump")) {
+        // profiling aid: copy the per-tile stamps of the last scan to the host pointer `value`
+        if (c->dbg_tiles && value) cudaMemcpy(reinterpret_cast<void*>(value), c->dbg_times.p, c->dbg_tiles * 64, cudaMemcpyDeviceToHost);
+    }
     else { set_error("unknown option %s", name); return VSPE_ERR_ARG; }
     return VSPE_OK;
 }

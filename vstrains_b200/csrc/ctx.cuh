@@ -56,6 +56,9 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_dbg_times = 0;
+    DevBuf<unsigned long long> dbg_times;
+    uint64_t dbg_tiles = 0;
     int64_t opt_scan_two_pass = 0;     // K1 as count + index passes (cross-check of the look-back kernel)
     uint64_t cur_buf_n = 0;            // bytes of the chunk being mapped (exhaustive tier bound)
     int64_t opt_scan_mode = 0;         // 0: fused TMA scan+pack, 1: look-back scan + raw-byte map, 2: two-pass scan

@@ -19,13 +19,13 @@
 
 namespace vspe {
 
-static constexpr int SP_WARPS = 6;
-static constexpr int SP_ITERS = 16;                              // 512-byte warp rows per warp
+static constexpr int SP_WARPS = 12;
+static constexpr int SP_ITERS = 8;                               // 512-byte warp rows per warp
 static constexpr int SP_TILE = SP_WARPS * SP_ITERS * 32 * 16;    // 48 KiB
 static constexpr int SP_FRONT = 16;                              // bytes kept before the tile
 static constexpr int SP_BACK = 512;                              // bytes kept after the tile (>= longest packed read + 1)
 static constexpr int SP_MAXREC = 768;                            // reads a tile may own (else fallback path)
-static constexpr int SP_QCAP = 256;                              // per warp: vectors that may hold a terminator
+static constexpr int SP_QCAP = 128;                              // per warp: vectors that may hold a terminator
 static constexpr uint32_t SP_SMEM = SP_FRONT + SP_TILE + SP_BACK + SP_MAXREC * 8 + SP_WARPS * SP_QCAP * 8 + 64;
 
 #define LB_AGG (1ull << 62)
@@ -75,8 +75,16 @@ struct ScanPackArgs {
     uint32_t cap;                    // longest read (bases) the map kernel's packed rows hold
     uint32_t n_tiles;
     unsigned long long* counters;
+    unsigned long long* dbg;         // optional [n_tiles][8] globaltimer stamps (profiling aid)
 };
 
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define SP_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[(size_t)tile * 8 + (k)] = gtime(); } while (0)
 
 __global__ void __launch_bounds__(SP_WARPS * 32)
 k_scan_pack(ScanPackArgs a) {
@@ -100,6 +108,7 @@ k_scan_pack(ScanPackArgs a) {
     }
     __syncthreads();
     const uint32_t tile = s_tile;
+    SP_STAMP(0);
     // aligned coordinates: byte `off` of the aligned stream is buffer position off - head
     const uint64_t A = ((uint64_t)a.head + a.n + 15) & ~15ull;         // aligned stream length
     const uint64_t t_lo = (uint64_t)tile * SP_TILE;
@@ -127,6 +136,7 @@ k_scan_pack(ScanPackArgs a) {
                          : "=r"(ok) : "r"(smem_u32(&s_bar)), "r"(0) : "memory");
         }
     }
+    SP_STAMP(1);
     // tile byte j (0 <= j < SP_TILE) lives at s_bytes[SP_FRONT + j]; its buffer position is t_lo + j - head
     const uint8_t* tb = s_bytes + SP_FRONT;
     const int64_t pos0 = (int64_t)t_lo - a.head;                       // buffer position of tile byte 0
@@ -214,7 +224,10 @@ k_scan_pack(ScanPackArgs a) {
         if (w < (int)wib) warp_base += x & 0x7FFFFFFFu;
         tile_total += x & 0x7FFFFFFFu;
     }
-    // ---- decoupled look-back (warp 0) --------------------------------------------------------
+    SP_STAMP(2);
+    // ---- decoupled look-back (warp 0), 128 predecessors per hop -------------------------------
+    // The inclusive-prefix frontier can only advance by one window per L2 round trip, so the
+    // window width bounds the kernel's throughput: 4 status words per lane.
     if (wib == 0) {
         volatile unsigned long long* vs = a.status;
         if (tile == 0) {
@@ -222,26 +235,49 @@ k_scan_pack(ScanPackArgs a) {
         } else {
             if (lane == 0) vs[tile] = LB_AGG | tile_total;
             unsigned long long excl = 0;
-            int64_t look = (int64_t)tile - 1;
+            int64_t look = (int64_t)tile - 1;                      // closest predecessor not yet summed
             while (true) {
-                const int64_t idx = look - lane;
-                unsigned long long st = idx >= 0 ? vs[idx] : LB_INC;
-                while (__any_sync(0xFFFFFFFFu, (st >> 62) == 0)) {
-                    if ((st >> 62) == 0) st = vs[idx];
+                unsigned long long st[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int64_t idx = look - 4 * (int64_t)lane - k;
+                    st[k] = idx >= 0 ? vs[idx] : LB_INC;
                 }
-                const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2);
+                while (true) {
+                    bool missing = false;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if ((st[k] >> 62) == 0) {
+                            st[k] = vs[look - 4 * (int64_t)lane - k];
+                            missing |= (st[k] >> 62) == 0;
+                        }
+                    }
+                    if (!__any_sync(0xFFFFFFFFu, missing)) break;
+                }
+                // this lane: sum up to and including its closest inclusive word, if it has one
+                unsigned long long c = 0;
+                bool has_inc = false;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (!has_inc) {
+                        c += st[k] & LB_VAL;
+                        has_inc = (st[k] >> 62) == 2;
+                    }
+                }
+                const uint32_t inc = __ballot_sync(0xFFFFFFFFu, has_inc);
                 const int first = inc ? __ffs((int)inc) - 1 : 32;
-                unsigned long long c = (int)lane <= first ? (st & LB_VAL) : 0ull;
+                if ((int)lane > first) c = 0;
                 for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
                 excl += c;
                 if (inc) break;
-                look -= 32;
+                look -= 128;
             }
             if (lane == 0) { vs[tile] = LB_INC | (excl + tile_total); s_excl = excl; }
         }
         if (lane == 0 && tile == a.n_tiles - 1) *a.total_out = s_excl + tile_total;
     }
     __syncthreads();
+    SP_STAMP(3);
     const uint64_t base = a.line_base + s_excl;                        // line number of the tile's first line
     // reads owned by this tile: sequence lines that START here = header terminators (line%4==0)
     // in the tile; record numbers are consecutive from r_own0
@@ -283,6 +319,7 @@ k_scan_pack(ScanPackArgs a) {
         }
     }
     __syncthreads();
+    SP_STAMP(4);
     // ---- pack: LPRP lanes per read, 32 bases (two 32-bit words) per lane ---------------------------
     const uint64_t r_loc0 = r_own0 - shift;                            // record number of local index 0
     const uint32_t RW = a.row_words;
@@ -362,6 +399,7 @@ k_scan_pack(ScanPackArgs a) {
             a.seq_end[slot] = en == 0xFFFFFFFFu ? ~0ull : (uint64_t)((int64_t)en + pos0);
         }
     }
+    SP_STAMP(5);
 }
 
 int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
@@ -387,6 +425,13 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
     a.line_base = line_base; a.rec_first = rec_first; a.n_slots = n_slots;
     a.seq_start = d_seq_start; a.seq_end = d_seq_end; a.rows = d_rows; a.hdr = d_hdr; a.row_words = row_words; a.cap = cap;
     a.n_tiles = (uint32_t)n_tiles; a.counters = c->counters.p;
+    a.dbg = nullptr;
+    if (c->opt_dbg_times) {
+        VSPE_TRY(c->dbg_times.reserve(n_tiles * 8));
+        VSPE_CUDA(cudaMemsetAsync(c->dbg_times.p, 0, n_tiles * 64, c->stream));
+        a.dbg = c->dbg_times.p;
+        c->dbg_tiles = n_tiles;
+    }
     k_scan_pack<<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
     VSPE_LAUNCH_CHECK(c);
     unsigned long long h_total = 0, h_err = 0;
