@@ -22,15 +22,15 @@ def _info(ids, mat, tmp_path, name):
         return f.read()
 
 
-@pytest.mark.parametrize("force_generic,scan_mode", [(0, 0), (0, 1), (1, 1)])
-def test_golden_fixtures_bit_exact(golden, tmp_path, force_generic, scan_mode):
+@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0)])
+def test_golden_fixtures_bit_exact(golden, tmp_path, force_generic, scan_mode, subst):
     if golden.status != 0:
         with pytest.raises(VspeError) as ei:
             pe_inference.pe_inference(golden.gfa, golden.fwd, golden.rve, golden.k)
         assert ei.value.code == -2
         return
     ids, node, short, stats = pe_inference.pe_inference(golden.gfa, golden.fwd, golden.rve, golden.k,
-                                                        options={"force_generic": force_generic, "scan_mode": scan_mode})
+                                                        options={"force_generic": force_generic, "scan_mode": scan_mode, "subst": subst})
     assert _info(ids, node, tmp_path, "pe_info") == golden.pe_info
     assert _info(ids, short, tmp_path, "st_info") == golden.st_info
     _, _, ostats, _ = pe_oracle.run_bytes(golden.gfa, golden.fwd, golden.rve, golden.k)
@@ -106,12 +106,12 @@ def test_per_read_mapping_matches_oracle(golden, force_generic, scan_mode):
 
 
 @pytest.mark.parametrize("name,pairs", [("C1", 6000), ("C2", 6000), ("C3", 4000), ("C4", 3000)])
-@pytest.mark.parametrize("force_generic,scan_mode", [(0, 0), (0, 1), (1, 1)])
-def test_synthetic_configs_match_c_oracle(name, pairs, force_generic, scan_mode):
+@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0)])
+def test_synthetic_configs_match_c_oracle(name, pairs, force_generic, scan_mode, subst):
     cfg = synth.CONFIGS[name]
     g, f, r = synth.generate(cfg, pairs=pairs)
     gfa = g.to_gfa()
-    ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"force_generic": force_generic, "scan_mode": scan_mode})
+    ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"force_generic": force_generic, "scan_mode": scan_mode, "subst": subst})
     onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
     assert np.array_equal(node.astype(np.int64), onode)
     assert np.array_equal(short.astype(np.int64), oshort)
@@ -256,3 +256,22 @@ def test_whole_path_edge_shapes(scan_mode):
         assert np.array_equal(short.astype(np.int64), oshort), name
         for k, v in ostats.items():
             assert stats[k] == v, (name, k)
+
+
+@pytest.mark.parametrize("subst", [1, 0])
+@pytest.mark.parametrize("sub_rate", [0.01, 0.04])
+def test_noisy_reads_match_c_oracle(subst, sub_rate):
+    """1 % and 4 % substitution rates: several errors per read, errors next to node ends and to
+    each other, reads that follow another strain's bubble arm after an error."""
+    for name, pairs in (("C2", 4000), ("C3", 3000)):
+        cfg = synth.CONFIGS[name]
+        rng = np.random.default_rng(cfg.seed + 5)
+        g, genomes, ab = synth.make_graph(cfg, rng, 10.0)
+        f, r = synth.make_reads(genomes, ab, cfg.read_len, pairs, cfg.k, rng, sub_rate=sub_rate)
+        gfa = g.to_gfa()
+        ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"subst": subst})
+        onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
+        assert np.array_equal(node.astype(np.int64), onode), name
+        assert np.array_equal(short.astype(np.int64), oshort), name
+        for k, v in ostats.items():
+            assert stats[k] == v

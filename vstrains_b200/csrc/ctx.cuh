@@ -56,6 +56,7 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_subst = 1;             // build / use the substitution-hit bitmap
     int64_t opt_dbg_times = 0;
     DevBuf<unsigned long long> dbg_times;
     uint64_t dbg_tiles = 0;

@@ -124,6 +124,67 @@ k_index_succ(IndexView ix, uint32_t* __restrict__ succ) {
     succ[2 * t + 1] = res_node;
 }
 
+// --- substitution-hit bitmap -----------------------------------------------------------------
+// For every window w of every strand, every offset o and every other base b: does the k-mer
+// "window w with base o replaced by b" have a posting?  If yes, bit b of text base w+o is set.
+// The seed-and-extend tier uses a CLEAR bit as a proof that all windows covering a mismatching
+// read base miss (they equal text windows except for that one base), so it can skip probing them.
+// The polynomial hash makes each substituted hash an O(1) update of the window's accumulators.
+__global__ void __launch_bounds__(128)
+k_index_subst(IndexView ix, uint32_t* __restrict__ subst, uint32_t inv1, uint32_t inv2) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= ix.text_len) return;
+    const uint32_t L = ix.split_len;
+    const uint32_t q = strand_of(ix.strand_start, 2 * ix.n_nodes, w);
+    if ((uint64_t)w + L > ix.strand_start[q + 1]) return;
+    const uint32_t n = (L + 15) >> 4;
+    KmerHash base;
+    for (uint32_t m = 0; m < L; m += 32) base.add64(extract64(ix.text, (uint64_t)w + m), L - m);
+    // power of the multiplier that weighs 16-base word k: M^(n-1-k)
+    uint32_t p1 = 1, p2 = 1;
+    for (uint32_t k = 1; k < n; k++) { p1 *= 0x9E3779B1u; p2 *= 0x85EBCA77u; }
+    for (uint32_t o = 0; o < L; o++) {
+        if (o && (o & 15) == 0) { p1 *= inv1; p2 *= inv2; }
+        const uint32_t cur = text_base(ix.text, (uint64_t)w + o);
+        for (uint32_t b = 0; b < 4; b++) {
+            if (b == cur) continue;
+            const uint32_t delta = (b - cur) << (2 * (o & 15));
+            KmerHash hs = base;
+            hs.h1 += delta * p1;
+            hs.h2 += delta * p2;
+            const uint64_t h = hs.finish();
+            uint32_t j = slot_of(h, ix.slot_mask);
+            bool found = false;
+            while (!found) {
+                const uint2 e = __ldg(ix.slots + j);
+                if (e.x == EMPTY_TP) break;
+                if (fp_match(e.y, h, ix.node_mask)) {
+                    bool eq = true;
+                    for (uint32_t m = 0; m < L && eq; m += 32) {
+                        uint64_t x = extract64(ix.text, (uint64_t)e.x + m) ^ extract64(ix.text, (uint64_t)w + m);
+                        const uint32_t rem = L - m;
+                        if (rem < 32) x &= (1ull << (2 * rem)) - 1;
+                        const uint64_t want = (o >= m && o < m + 32) ? ((uint64_t)(cur ^ b) << (2 * (o - m))) : 0ull;
+                        eq = x == want;
+                    }
+                    found = eq;
+                }
+                j = (j + 1) & ix.slot_mask;
+            }
+            if (found) {
+                const uint32_t pos = w + o;
+                atomicOr(&subst[pos >> 3], 1u << (4 * (pos & 7) + b));
+            }
+        }
+    }
+}
+
+static uint32_t inv32(uint32_t a) {        // inverse of an odd number mod 2^32 (Newton)
+    uint32_t x = a;
+    for (int i = 0; i < 5; i++) x *= 2u - a * x;
+    return x;
+}
+
 int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len) {
     Index& ix = c->index;
     ix.built = false;
@@ -202,6 +263,16 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
     if (n_nodes) {
         k_index_succ<<<(8 * n_nodes + 127) / 128, 128, 0, st>>>(v, ix.succ.p);
         VSPE_LAUNCH_CHECK(c);
+    }
+    // the substitution-hit bitmap costs 3*L probes per window: build it for viral-scale graphs
+    // only (the map kernel probes the windows itself when it is absent)
+    ix.has_subst = false;
+    if (text_len && c->opt_subst && (double)n_kmers * split_len * 3.0 <= 6e9) {
+        VSPE_TRY(ix.subst.reserve(n_words * 4 + 8));
+        VSPE_CUDA(cudaMemsetAsync(ix.subst.p, 0, ((size_t)n_words * 4 + 8) * 4, st));
+        k_index_subst<<<(uint32_t)((text_len + 127) / 128), 128, 0, st>>>(v, ix.subst.p, inv32(0x9E3779B1u), inv32(0x85EBCA77u));
+        VSPE_LAUNCH_CHECK(c);
+        ix.has_subst = true;
     }
     VSPE_CUDA(cudaEventRecord(e1, st));
     VSPE_CUDA(cudaStreamSynchronize(st));

@@ -143,13 +143,32 @@ __device__ __forceinline__ bool list_add(uint32_t (*s_node)[MF_THREADS], uint32_
     return true;
 }
 
+// Unknown window ranges of one read (forward-read coordinates), at most two; a third one sends
+// the read to the exhaustive tier.
+struct Unk {
+    uint32_t r0 = 0, r1 = 0;         // from | count << 16 (count 0 = unused)
+    __device__ __forceinline__ bool add(uint32_t from, uint32_t cnt) {
+        if (cnt == 0) return true;
+        const uint32_t v = from | (cnt << 16);
+        if (!(r0 >> 16)) { r0 = v; return true; }
+        if (!(r1 >> 16)) { r1 = v; return true; }
+        return false;
+    }
+};
+
 // One directional pass over windows [0, limit) of a packed row.  Returns the first window whose
-// status is unknown (== limit when everything was resolved).  mirror: the row is the reverse
-// complement, so window i of the row is window npos-1-i of the read (only kmin needs that).
+// status is unknown (== limit when everything was resolved or recorded in `unk`).  mirror: the
+// row is the reverse complement, so window i of the row is window npos-1-i of the read.
+//
+// A mismatch at read base e inside a node strand is a sequencing error (a variant present in the
+// graph ends the strand instead).  The windows covering e equal the text windows on the same
+// diagonal except for that base, so
+//   * if the substitution-hit bit of (text base, read base) is clear, they all miss -- no probes;
+//   * otherwise they are recorded for the cooperative probes of phase 3;
+// and the pass RESUMES at window e+1 on the same diagonal after one direct comparison.
 __device__ __forceinline__ uint32_t run_pass(const IndexView& ix, const uint32_t* row, uint32_t rlen, uint32_t limit,
                                              bool mirror, uint32_t npos, uint32_t (*s_node)[MF_THREADS],
-                                             uint32_t (*s_vk)[MF_THREADS], uint32_t t, uint32_t& nn, bool& bail) {
-    // (node list of read t: s_node[0..nn)[t], s_vk = hits | kmin << 16)
+                                             uint32_t (*s_vk)[MF_THREADS], uint32_t t, uint32_t& nn, Unk& unk, bool& bail) {
     const uint32_t L = ix.split_len;
     uint32_t i = 0;
     uint32_t tp = NONE32, node = 0;
@@ -174,18 +193,50 @@ __device__ __forceinline__ uint32_t run_pass(const IndexView& ix, const uint32_t
         if (i + hits > limit) hits = limit - i;               // pass B must not re-count pass A's windows
         const uint32_t kminc = mirror ? npos - i - hits : i;
         if (!list_add(s_node, s_vk, t, nn, node, hits, kminc)) { bail = true; return limit; }
-        i += hits;
-        if (i >= limit) break;
-        if (ext < max_ext) return i;                          // mismatch inside the strand: unknown from here
-        if (ext == room_t) {
+        const uint32_t i_next = i + hits;                     // first window not proven yet
+        if (i_next >= limit) return limit;
+        if (ext == max_ext && ext == room_t) {
             // the strand ended exactly here: successor for the read's next base, if unique
-            const uint32_t nb = i + L - 1;
+            const uint32_t nb = i_next + L - 1;
             const uint32_t b = (row[nb >> 4] >> ((nb & 15) * 2)) & 3u;
             const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
             tp = sc.x;
             node = sc.y;
-        } else {
-            tp = NONE32;                                      // (unreachable: ext == room_r means i == npos)
+            i = i_next;
+            continue;
+        }
+        // ---- mismatch at read base e = i + L + ext (text base tp + L + ext), inside the strand ----
+        const uint32_t e = i + L + ext, te = tp + L + ext;
+        const uint32_t rb = (row[e >> 4] >> ((e & 15) * 2)) & 3u;
+        const bool clear = ix.subst && !((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u);
+        const uint32_t i_res = e + 1, t_res = te + 1;         // window right after the error, same diagonal
+        if (i_res + L <= rlen) {
+            // a whole window fits after the error: resume there if it is the unique text window
+            const bool ok = (uint64_t)t_res + L <= send && read_equals_text(row, i_res, ix.text, t_res, L) &&
+                            ((__ldg(ix.uniq + (t_res >> 5)) >> (t_res & 31)) & 1u);
+            if (!ok) return i_next;                           // second error / strand end: other pass, then phase 3
+            // unknown windows [i_next, e]: all cover e and all have an in-strand text window
+            const uint32_t hi = min(i_res, limit);
+            if (!clear) {
+                const uint32_t from = mirror ? npos - hi : i_next, cnt = hi - i_next;
+                if (!unk.add(from, cnt)) { bail = true; return limit; }
+            }
+            if (i_res >= limit) return limit;
+            i = i_res;
+            tp = t_res;
+            continue;
+        }
+        // no window starts after the error: the rest [i_next, npos) all cover e
+        {
+            const bool in_strand = room_t >= room_r;          // every remaining window has an in-strand text window
+            // ... and equals it except for base e only if the read's tail matches the text too
+            const uint32_t tail = rlen - e - 1;
+            const bool tail_ok = in_strand && match_len(row, e + 1, ix.text, te + 1, tail) == tail;
+            if (!(clear && tail_ok)) {
+                const uint32_t from = mirror ? npos - limit : i_next, cnt = limit - i_next;
+                if (!unk.add(from, cnt)) { bail = true; return limit; }
+            }
+            return limit;
         }
     }
     return limit;
@@ -302,34 +353,39 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     uint32_t lf = s_len[t];
     const uint32_t rlen = lf & 0xFFFFFF;
     const uint32_t* row = s_fwd + t * STRIDE;
-    uint32_t nn = 0, unk_from = 0, unk_cnt = 0;
+    uint32_t nn = 0;
+    Unk unk;
     bool active = !(lf & (F_NONE | F_LONG | F_BAD | F_N)) && rlen >= L;
     bool bail = (lf & (F_LONG | F_BAD)) != 0 && !(lf & F_NONE);
     if ((lf & F_BAD) && ((lf & F_N) || rlen < L)) bail = false;    // N / short win over the bail
     uint32_t npos = 0;
     if (active) {
         npos = rlen - L + 1;
-        const uint32_t uA = run_pass(ix, row, rlen, npos, false, npos, s_node, s_vk, t, nn, bail);
+        const uint32_t uA = run_pass(ix, row, rlen, npos, false, npos, s_node, s_vk, t, nn, unk, bail);
         if (!bail && uA < npos) {
             const uint32_t lim = npos - uA;
-            const uint32_t uB = run_pass(ix, s_rc + t * STRIDE, rlen, lim, true, npos, s_node, s_vk, t, nn, bail);
-            if (!bail && uB < lim) { unk_from = uA; unk_cnt = lim - uB; }
+            const uint32_t uB = run_pass(ix, s_rc + t * STRIDE, rlen, lim, true, npos, s_node, s_vk, t, nn, unk, bail);
+            if (!bail && uB < lim && !unk.add(uA, lim - uB)) bail = true;
         }
+        if (bail) { unk.r0 = 0; unk.r1 = 0; }
     }
+
     // ---- phase 3: the warp probes the unknown windows of its reads, one range at a time --------
     // Normally every one of them misses (they cover a sequencing error).  A window that does hit
-    // a unique posting (a second error further along) is one more hit for that node; a window
-    // with several postings sends the read to the exhaustive tier.
-    {
-        uint32_t m = __ballot_sync(0xFFFFFFFFu, unk_cnt > 0);
+    // a unique posting is one more hit for that node; a window with several postings sends the
+    // read to the exhaustive tier.
+#pragma unroll 1
+    for (int slot = 0; slot < 2; slot++) {
+        const uint32_t mine = slot == 0 ? unk.r0 : unk.r1;
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, (mine >> 16) != 0);
         while (m) {
             const int src = __ffs((int)m) - 1;
             m &= m - 1;
-            const uint32_t from = __shfl_sync(0xFFFFFFFFu, unk_from, src);
-            const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, unk_cnt, src);
+            const uint32_t rg = __shfl_sync(0xFFFFFFFFu, mine, src);
+            const uint32_t from = rg & 0xFFFF, cnt = rg >> 16;
             uint32_t tnn = __shfl_sync(0xFFFFFFFFu, nn, src);          // list length of read src (uniform copy)
+            bool tbail = __shfl_sync(0xFFFFFFFFu, (uint32_t)bail, src) != 0;
             const uint32_t tt = wib * 32 + src;
-            bool tbail = false;
             for (uint32_t w0 = 0; w0 < cnt && !tbail; w0 += 32) {
                 const uint32_t w = w0 + lane;
                 uint32_t tp = 0, node = 0;

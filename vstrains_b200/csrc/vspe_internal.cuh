@@ -60,6 +60,8 @@ struct IndexView {
     const uint2* slots;
     const uint32_t* uniq;           // bitmap over text positions
     const uint32_t* succ;           // [2N][4] {text position, node} of the unique successor k-mer or {NONE32, 0}
+    const uint32_t* subst;          // 4 bits per text base (or nullptr): bit b set iff some window of the strand that
+                                    // covers the base, with the base replaced by code b, has a posting
     uint32_t text_len;              // bases
     uint32_t slot_mask;
     uint32_t node_mask;             // (1 << nbits) - 1
@@ -206,13 +208,15 @@ struct Index {
     DevBuf<uint2> slots;
     DevBuf<uint32_t> uniq;
     DevBuf<uint32_t> succ;
+    DevBuf<uint32_t> subst;
+    bool has_subst = false;
     uint32_t text_len = 0, slot_mask = 0, node_mask = 0, split_len = 0, n_nodes = 0;
     uint64_t n_kmers = 0;
     bool built = false;
     IndexView view() const {
         IndexView v;
         v.text = text.p; v.strand_start = strand_start.p; v.node_len = node_len.p;
-        v.slots = slots.p; v.uniq = uniq.p; v.succ = succ.p;
+        v.slots = slots.p; v.uniq = uniq.p; v.succ = succ.p; v.subst = has_subst ? subst.p : nullptr;
         v.text_len = text_len; v.slot_mask = slot_mask; v.node_mask = node_mask;
         v.split_len = split_len; v.n_nodes = n_nodes;
         return v;
