@@ -22,7 +22,7 @@ def _info(ids, mat, tmp_path, name):
         return f.read()
 
 
-@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0)])
+@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0), (0, 0, 2)])
 def test_golden_fixtures_bit_exact(golden, tmp_path, force_generic, scan_mode, subst):
     if golden.status != 0:
         with pytest.raises(VspeError) as ei:
@@ -30,7 +30,8 @@ def test_golden_fixtures_bit_exact(golden, tmp_path, force_generic, scan_mode, s
         assert ei.value.code == -2
         return
     ids, node, short, stats = pe_inference.pe_inference(golden.gfa, golden.fwd, golden.rve, golden.k,
-                                                        options={"force_generic": force_generic, "scan_mode": scan_mode, "subst": subst})
+                                                        options={"force_generic": force_generic, "scan_mode": scan_mode,
+                                                                 "subst": subst & 1, "single_map": subst >> 1})
     assert _info(ids, node, tmp_path, "pe_info") == golden.pe_info
     assert _info(ids, short, tmp_path, "st_info") == golden.st_info
     _, _, ostats, _ = pe_oracle.run_bytes(golden.gfa, golden.fwd, golden.rve, golden.k)
@@ -106,12 +107,12 @@ def test_per_read_mapping_matches_oracle(golden, force_generic, scan_mode):
 
 
 @pytest.mark.parametrize("name,pairs", [("C1", 6000), ("C2", 6000), ("C3", 4000), ("C4", 3000)])
-@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0)])
+@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0), (0, 0, 2)])
 def test_synthetic_configs_match_c_oracle(name, pairs, force_generic, scan_mode, subst):
     cfg = synth.CONFIGS[name]
     g, f, r = synth.generate(cfg, pairs=pairs)
     gfa = g.to_gfa()
-    ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"force_generic": force_generic, "scan_mode": scan_mode, "subst": subst})
+    ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"force_generic": force_generic, "scan_mode": scan_mode, "subst": subst & 1, "single_map": subst >> 1})
     onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
     assert np.array_equal(node.astype(np.int64), onode)
     assert np.array_equal(short.astype(np.int64), oshort)

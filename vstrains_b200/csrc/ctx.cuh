@@ -12,6 +12,7 @@ enum Counter {
     CNT_FAST, CNT_GENERIC,   // reads resolved per tier
     CNT_WORK,                // generic-tier worklist length
     CNT_BAILED,              // reads the fast tier handed to the exhaustive tier
+    CNT_DEFER,               // reads k_map_first deferred to k_map_fast
     CNT_COUNT_
 };
 static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16;
@@ -39,6 +40,7 @@ struct Ctx {
     bool scratch_valid = false;       // warp_scratch initialised for the current index
     DevBuf<uint32_t> spill;
     DevBuf<uint32_t> worklist;
+    DevBuf<uint32_t> defer_list;
     // K5/K6 scratch
     DevBuf<uint32_t> keys;
     DevBuf<unsigned long long> bucket;   // [3][n_buckets + 1]: histogram, start, cursor
@@ -56,6 +58,7 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_single_map = 0;        // 1: skip k_map_first (every read through the full kernel)
     int64_t opt_subst = 1;             // build / use the substitution-hit bitmap
     int64_t opt_dbg_times = 0;
     DevBuf<unsigned long long> dbg_times;

@@ -248,8 +248,12 @@ template <int STRIDE, int LPR, bool PACKED>
 __global__ void __launch_bounds__(MF_THREADS)
 k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
            const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr,
-           uint32_t row_words, uint64_t n_reads, ReadSlot* __restrict__ slots,
+           uint32_t row_words, uint64_t n_reads_arg, const uint32_t* __restrict__ in_list,
+           const unsigned long long* __restrict__ in_count, ReadSlot* __restrict__ slots,
            uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters) {
+    // in_list != nullptr: process reads in_list[0 .. *in_count) (the reads k_map_first deferred)
+    const uint64_t n_reads = in_list ? *in_count : n_reads_arg;
+    if ((uint64_t)blockIdx.x * MF_THREADS >= n_reads) return;
     constexpr uint32_t CAP = (STRIDE - 3) * 16;                   // bases per packed row
     constexpr uint32_t GROUPS = 32 / LPR;                          // reads packed per warp step
     __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
@@ -268,11 +272,11 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
         const uint32_t gmask = LPR == 32 ? 0xFFFFFFFFu : (((1u << LPR) - 1) << (grp * LPR));
         for (uint32_t k = 0; k < 32 / GROUPS; k++) {
             const uint32_t t = wib * 32 + k * GROUPS + grp;
-            const uint64_t r = r0 + t;
+            const bool live = r0 + t < n_reads;
+            const uint64_t r = !live ? 0 : in_list ? (uint64_t)in_list[r0 + t] : r0 + t;
             uint32_t* row = s_fwd + t * STRIDE;
             uint32_t* rrow = s_rc + t * STRIDE;
             uint64_t s = 0, len64 = 0;
-            const bool live = r < n_reads;
             uint32_t h = 0;
             if (PACKED) {
                 if (live) h = __ldg(hdr + r);
@@ -349,8 +353,8 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
 
     // ---- phase 2: one thread per read, passes A and B ---------------------------------------
     const uint32_t t = threadIdx.x;
-    const uint64_t r = r0 + t;
     uint32_t lf = s_len[t];
+    const uint64_t r = (lf & F_NONE) ? 0 : in_list ? (uint64_t)in_list[r0 + t] : r0 + t;
     const uint32_t rlen = lf & 0xFFFFFF;
     const uint32_t* row = s_fwd + t * STRIDE;
     uint32_t nn = 0;
@@ -420,7 +424,7 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
 
     // ---- phase 4: finalize -----------------------------------------------------------------
     if (lf & F_NONE) return;
-    if (t == 0 && blockIdx.x == 0) atomicAdd(&counters[CNT_FAST], (unsigned long long)n_reads);
+    if (t == 0 && blockIdx.x == 0 && !in_list) atomicAdd(&counters[CNT_FAST], (unsigned long long)n_reads);
     ReadSlot* out = slots + r;
     if (!(lf & F_LONG)) {
         if (lf & F_N) { out->hdr = ST_N; return; }
@@ -457,6 +461,108 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     out->hdr = ST_OK | (n_out << 8);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_map_first: the common case only.  Packs nothing (rows come from k_scan_pack), runs ONE clean
+// forward pass -- seed window 0, extend, walk successors -- and finishes the read if that pass
+// proves every window.  Anything else (a miss, a mismatch, a repeat, too many nodes) defers the
+// read, untouched, to k_map_fast via a worklist, so the two populations never share a warp.
+// ---------------------------------------------------------------------------------------------
+template <int STRIDE, int LPR>
+__global__ void __launch_bounds__(MF_THREADS)
+k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
+            uint64_t n_reads, ReadSlot* __restrict__ slots, uint32_t* __restrict__ defer_list,
+            unsigned long long* __restrict__ counters) {
+    constexpr uint32_t GROUPS = 32 / LPR;
+    __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
+    __shared__ uint32_t s_node[MAXN][MF_THREADS];
+    __shared__ uint32_t s_vk[MAXN][MF_THREADS];
+    __shared__ uint32_t s_len[MF_THREADS];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t r0 = (uint64_t)blockIdx.x * MF_THREADS;
+    const uint32_t L = ix.split_len;
+    {
+        const uint32_t grp = lane / LPR, gl = lane % LPR;
+        for (uint32_t k = 0; k < 32 / GROUPS; k++) {
+            const uint32_t t = wib * 32 + k * GROUPS + grp;
+            const uint64_t r = r0 + t;
+            const bool live = r < n_reads;
+            const uint32_t h = live ? __ldg(hdr + r) : 0xFFFFFFFFu;
+            const uint32_t rlen = (h & PH_LONG) ? 0 : (h & 0xFFFFFF);
+            const uint32_t nwords = (rlen + 15) >> 4;
+            uint32_t* row = s_fwd + t * STRIDE;
+            for (uint32_t w = gl; w < (uint32_t)STRIDE; w += LPR) row[w] = (live && w < nwords) ? __ldg(rows + r * row_words + w) : 0u;
+            if (gl == 0) s_len[t] = h;
+        }
+    }
+    __syncwarp();
+    const uint32_t t = threadIdx.x;
+    const uint64_t r = r0 + t;
+    const uint32_t h = s_len[t];
+    if (h == 0xFFFFFFFFu) return;
+    if (t == 0 && blockIdx.x == 0) atomicAdd(&counters[CNT_FAST], (unsigned long long)n_reads);
+    ReadSlot* out = slots + r;
+    const uint32_t rlen = h & 0xFFFFFF;
+    bool defer = (h & (PH_LONG | PH_BAD)) != 0;
+    if (!(h & PH_LONG)) {
+        if (h & PH_N) { out->hdr = ST_N; return; }
+        if (rlen < L) { out->hdr = ST_SHORT; return; }
+    }
+    const uint32_t* row = s_fwd + t * STRIDE;
+    uint32_t nn = 0;
+    if (!defer) {
+        const uint32_t npos = rlen - L + 1;
+        uint32_t i = 0, tp = NONE32, node = 0;
+        if (probe_window(ix, row, 0, tp, node) != PROBE_UNIQUE) defer = true;
+        while (!defer) {
+            const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
+            const bool rcs = tp >= s1;
+            const uint32_t q = 2 * node + (rcs ? 1u : 0u);
+            const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
+            const uint32_t room_t = send - (tp + L), room_r = rlen - (i + L);
+            const uint32_t max_ext = min(room_t, room_r);
+            const uint32_t ext = match_len(row, i + L, ix.text, tp + L, max_ext);
+            if (ext < max_ext || (ext && uniq_run(ix.uniq, tp + 1, ext) < ext)) { defer = true; break; }
+            if (!list_add(s_node, s_vk, t, nn, node, 1 + ext, i)) { defer = true; break; }
+            i += 1 + ext;
+            if (i >= npos) break;
+            const uint32_t nb = i + L - 1;
+            const uint32_t b = (row[nb >> 4] >> ((nb & 15) * 2)) & 3u;
+            const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
+            if (sc.x == NONE32) { defer = true; break; }
+            tp = sc.x;
+            node = sc.y;
+        }
+    }
+    uint32_t n_out = 0;
+    if (!defer) {
+        for (uint32_t a = 1; a < nn; a++) {
+            const uint32_t kn = s_node[a][t], kv = s_vk[a][t];
+            int b = (int)a - 1;
+            while (b >= 0 && s_node[b][t] > kn) {
+                s_node[b + 1][t] = s_node[b][t];
+                s_vk[b + 1][t] = s_vk[b][t];
+                b--;
+            }
+            s_node[b + 1][t] = kn;
+            s_vk[b + 1][t] = kv;
+        }
+        for (uint32_t a = 0; a < nn; a++) {
+            const uint32_t node = s_node[a][t], vk = s_vk[a][t];
+            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) {
+                if (n_out < (uint32_t)SLOT_IDS) out->ids[n_out] = node;
+                n_out++;
+            }
+        }
+        if (n_out > (uint32_t)SLOT_IDS) defer = true;
+    }
+    if (defer) {
+        const unsigned long long idx = atomicAdd(&counters[CNT_DEFER], 1ull);
+        defer_list[idx] = (uint32_t)r;
+        return;
+    }
+    out->hdr = ST_OK | (n_out << 8);
+}
+
 int map_reads_generic_dev(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                           const uint32_t* d_worklist, const unsigned long long* d_n_items, ReadSlot* d_slots);
 
@@ -469,8 +575,23 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
     const uint32_t grid = (uint32_t)((n_reads + MF_THREADS - 1) / MF_THREADS);
     IndexView v = c->index.view();
+    const uint32_t* in_list = nullptr;
+    const unsigned long long* in_count = nullptr;
+    if (d_rows && !c->opt_single_map) {
+        // the clean-pass kernel first; what it defers goes through the full kernel
+        VSPE_TRY(c->defer_list.reserve(n_reads));
+        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER, 0, 8, c->stream));
+#define VSPE_M1(S, LP) k_map_first<S, LP><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, n_reads, d_slots, \
+                                                                        c->defer_list.p, c->counters.p)
+        if (cap <= 160) VSPE_M1(13, 16); else if (cap <= 256) VSPE_M1(19, 16); else VSPE_M1(23, 32);
+#undef VSPE_M1
+        VSPE_LAUNCH_CHECK(c);
+        in_list = c->defer_list.p;
+        in_count = c->counters.p + CNT_DEFER;
+    }
 #define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
-                                                                               row_words, n_reads, d_slots, c->worklist.p, c->counters.p)
+                                                                               row_words, n_reads, in_list, in_count, d_slots, \
+                                                                               c->worklist.p, c->counters.p)
     if (d_rows) {
         if (cap <= 160) VSPE_MF(13, 16, true); else if (cap <= 256) VSPE_MF(19, 16, true); else VSPE_MF(23, 32, true);
     } else {
