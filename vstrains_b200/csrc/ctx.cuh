@@ -13,6 +13,7 @@ enum Counter {
     CNT_WORK,                // generic-tier worklist length
     CNT_BAILED,              // reads the fast tier handed to the exhaustive tier
     CNT_DEFER,               // reads k_map_first deferred to k_map_fast
+    CNT_WORK2,               // reads k_map_windows left for the ASCII tier
     CNT_COUNT_
 };
 static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16;

@@ -30,6 +30,8 @@
 // Phase 3:      warp-cooperative confirmation probes of the unknown windows (one range at a
 //               time, 32 windows per step).
 // Phase 4:      one thread per read: sort by node index, saturation predicate, write the slot.
+#include <algorithm>
+
 #include "ctx.cuh"
 
 namespace vspe {
@@ -141,6 +143,46 @@ __device__ __forceinline__ bool list_add(uint32_t (*s_node)[MF_THREADS], uint32_
         s_vk[a][t] = ((old & 0xFFFF) + hits) | (min(old >> 16, kminc) << 16);
     }
     return true;
+}
+
+// Load the packed row of read r (row_words 16-base words, 16-byte aligned) with independent
+// 128-bit loads and store it to this thread's shared-memory row; optionally also its reverse
+// complement (reverse the 2-bit groups of every word, complement, realign by the padding).
+template <int STRIDE, bool WITH_RC>
+__device__ __forceinline__ void load_row(const uint32_t* __restrict__ rows, uint64_t r, uint32_t row_words, uint32_t rlen,
+                                         uint32_t* row, uint32_t* rrow) {
+    constexpr int NW = STRIDE - 3;                             // data words a row can hold
+    constexpr int XW = (NW + 3) / 4 * 4;
+    uint32_t x[XW];
+    const uint4* src = reinterpret_cast<const uint4*>(rows + r * row_words);
+#pragma unroll
+    for (int q = 0; q < XW / 4; q++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if ((uint32_t)(4 * q) < row_words) v = __ldg(src + q);
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int w = 0; w < NW; w++) row[w] = x[w];
+    row[NW] = 0; row[NW + 1] = 0; row[NW + 2] = 0;
+    if (WITH_RC) {
+        const uint32_t nwords = (rlen + 15) >> 4, pad = 16 * nwords - rlen;
+        // rc word j = funnel(RV[nwords-1-j], RV[nwords-2-j], 2*pad) with RV[k] = revcomp16(x[k])
+        uint32_t prev = 0;                                     // RV[nwords-1-j] of the previous (lower) step
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            // walk k downwards from NW-1: produce rc words in increasing j only for k < nwords
+            const int kk = NW - 1 - k;
+            uint32_t rv = __brev(x[kk]);
+            rv = (((rv & 0x55555555u) << 1) | ((rv >> 1) & 0x55555555u)) ^ 0xAAAAAAAAu;
+            if ((uint32_t)kk >= nwords) { continue; }
+            // RV[kk] is "a0" of rc word j = nwords-1-kk and "a1" of rc word j-1
+            const int j = (int)nwords - 1 - kk;
+            if (j > 0) rrow[j - 1] = __funnelshift_r(prev, rv, 2 * pad);
+            prev = rv;
+        }
+        if (nwords) rrow[nwords - 1] = __funnelshift_r(prev, 0u, 2 * pad);
+        for (uint32_t w = nwords; w < (uint32_t)STRIDE; w++) rrow[w] = 0;
+    }
 }
 
 // Unknown window ranges of one read (forward-read coordinates), at most two; a third one sends
@@ -266,6 +308,23 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     const uint64_t r0 = (uint64_t)blockIdx.x * MF_THREADS;
     const uint32_t L = ix.split_len;
 
+    if (PACKED) {
+        // ---- phase 1 (packed rows): each thread loads its own row + builds the reverse complement
+        const uint32_t t = threadIdx.x;
+        const bool live = r0 + t < n_reads;
+        uint32_t lfv = F_NONE;
+        if (live) {
+            const uint64_t r = in_list ? (uint64_t)in_list[r0 + t] : r0 + t;
+            const uint32_t h = __ldg(hdr + r);
+            if (h & PH_LONG) lfv = F_LONG;
+            else {
+                const uint32_t rlen = h & 0xFFFFFF;
+                load_row<STRIDE, true>(rows, r, row_words, rlen, s_fwd + t * STRIDE, s_rc + t * STRIDE);
+                lfv = rlen | ((h & PH_N) ? F_N : 0) | ((h & PH_BAD) ? F_BAD : 0);
+            }
+        }
+        s_len[t] = lfv;
+    } else
     // ---- phase 1: cooperative pack (LPR lanes per read) -------------------------------------
     {
         const uint32_t grp = lane / LPR, gl = lane % LPR;
@@ -472,27 +531,21 @@ __global__ void __launch_bounds__(MF_THREADS)
 k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
             uint64_t n_reads, ReadSlot* __restrict__ slots, uint32_t* __restrict__ defer_list,
             unsigned long long* __restrict__ counters) {
-    constexpr uint32_t GROUPS = 32 / LPR;
     __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
     __shared__ uint32_t s_node[MAXN][MF_THREADS];
     __shared__ uint32_t s_vk[MAXN][MF_THREADS];
     __shared__ uint32_t s_len[MF_THREADS];
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t r0 = (uint64_t)blockIdx.x * MF_THREADS;
     const uint32_t L = ix.split_len;
     {
-        const uint32_t grp = lane / LPR, gl = lane % LPR;
-        for (uint32_t k = 0; k < 32 / GROUPS; k++) {
-            const uint32_t t = wib * 32 + k * GROUPS + grp;
-            const uint64_t r = r0 + t;
-            const bool live = r < n_reads;
-            const uint32_t h = live ? __ldg(hdr + r) : 0xFFFFFFFFu;
-            const uint32_t rlen = (h & PH_LONG) ? 0 : (h & 0xFFFFFF);
-            const uint32_t nwords = (rlen + 15) >> 4;
-            uint32_t* row = s_fwd + t * STRIDE;
-            for (uint32_t w = gl; w < (uint32_t)STRIDE; w += LPR) row[w] = (live && w < nwords) ? __ldg(rows + r * row_words + w) : 0u;
-            if (gl == 0) s_len[t] = h;
+        const uint32_t t = threadIdx.x;
+        const uint64_t r = r0 + t;
+        uint32_t h = 0xFFFFFFFFu;
+        if (r < n_reads) {
+            h = __ldg(hdr + r);
+            if (!(h & PH_LONG)) load_row<STRIDE, false>(rows, r, row_words, h & 0xFFFFFF, s_fwd + t * STRIDE, nullptr);
         }
+        s_len[t] = h;
     }
     __syncwarp();
     const uint32_t t = threadIdx.x;
@@ -563,6 +616,108 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
     out->hdr = ST_OK | (n_out << 8);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_map_windows: the reads k_map_first deferred (sequencing errors, repeats, many nodes).
+// One warp per read, one lane per window, every window looked up -- the reference's algorithm
+// (PE_Inference.py:24-31) with no shortcuts, so every postings multiplicity is exact.  All lanes
+// stay busy; hit counts and first positions live in lane registers (lane k owns the k-th distinct
+// node of the read, up to 32), so there is no per-read scratch in memory.
+// ---------------------------------------------------------------------------------------------
+static constexpr int MW_WARPS = 4;
+
+template <int STRIDE>
+__global__ void __launch_bounds__(MW_WARPS * 32)
+k_map_windows(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
+              const uint32_t* __restrict__ in_list, const unsigned long long* __restrict__ in_count,
+              ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list, unsigned long long* __restrict__ out_count,
+              uint32_t* __restrict__ spill, uint64_t spill_cap, unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t s_row[MW_WARPS][STRIDE];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t n_items = *in_count;
+    const uint64_t gw = (uint64_t)blockIdx.x * MW_WARPS + wib, nw = (uint64_t)gridDim.x * MW_WARPS;
+    const uint32_t L = ix.split_len;
+    uint32_t* row = s_row[wib];
+    for (uint64_t item = gw; item < n_items; item += nw) {
+        const uint32_t r = in_list[item];
+        const uint32_t h = __ldg(hdr + r);
+        if (h & (PH_LONG | PH_BAD)) {                       // not representable in 2 bits: exhaustive ASCII tier
+            if (lane == 0) out_list[atomicAdd(out_count, 1ull)] = r;
+            continue;
+        }
+        const uint32_t rlen = h & 0xFFFFFF, npos = rlen - L + 1, nwords = (rlen + 15) >> 4;
+        __syncwarp();
+        for (uint32_t w = lane; w < (uint32_t)STRIDE; w += 32) row[w] = w < nwords ? __ldg(rows + (uint64_t)r * row_words + w) : 0u;
+        __syncwarp();
+        // lane k: k-th distinct node of this read
+        uint32_t acc_node = NONE32, acc_v = 0, acc_kmin = NONE32, nn = 0;
+        bool overflow = false;
+        for (uint32_t w0 = 0; w0 < npos; w0 += 32) {
+            const uint32_t w = w0 + lane;
+            bool done = w >= npos;
+            uint64_t hsh = 0;
+            uint32_t j = 0;
+            if (!done) { hsh = hash_read(row, w, L); j = slot_of(hsh, ix.slot_mask); }
+            while (true) {
+                // advance every lane to its next verified posting (or to the end of its cluster)
+                uint32_t node = NONE32;
+                while (!done) {
+                    const uint2 ent = __ldg(ix.slots + j);
+                    j = (j + 1) & ix.slot_mask;
+                    if (ent.x == EMPTY_TP) { done = true; break; }
+                    if (fp_match(ent.y, hsh, ix.node_mask) && read_equals_text(row, w, ix.text, ent.x, L)) {
+                        node = ent.y & ix.node_mask;
+                        break;
+                    }
+                }
+                uint32_t pending = __ballot_sync(0xFFFFFFFFu, node != NONE32);
+                if (!pending) break;
+                while (pending) {
+                    const int leader = __ffs((int)pending) - 1;
+                    const uint32_t lnode = __shfl_sync(0xFFFFFFFFu, node, leader);
+                    const uint32_t grp = __ballot_sync(0xFFFFFFFFu, node == lnode);
+                    const uint32_t cnt = __popc(grp), first = w0 + (uint32_t)(__ffs((int)grp) - 1);
+                    const uint32_t owner = __ballot_sync(0xFFFFFFFFu, acc_node == lnode);
+                    if (owner) {
+                        if (acc_node == lnode) { acc_v += cnt; acc_kmin = min(acc_kmin, first); }
+                    } else if (nn < 32) {
+                        if (lane == nn) { acc_node = lnode; acc_v = cnt; acc_kmin = first; }
+                        nn++;
+                    } else {
+                        overflow = true;
+                    }
+                    pending &= ~grp;
+                }
+            }
+        }
+        if (overflow) {                                       // more than 32 distinct nodes: exhaustive tier
+            if (lane == 0) out_list[atomicAdd(out_count, 1ull)] = r;
+            continue;
+        }
+        // saturation predicate per node, then ascending node order
+        const bool keep = lane < nn && keep_node_f(acc_v, acc_kmin, __ldg(ix.node_len + acc_node), rlen, L);
+        const uint32_t key = keep ? acc_node : NONE32;
+        uint32_t rank = 0;
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) rank += __shfl_sync(0xFFFFFFFFu, key, k) < key;
+        const uint32_t n_out = __popc(__ballot_sync(0xFFFFFFFFu, keep));
+        ReadSlot* out = slots + r;
+        if (n_out <= (uint32_t)SLOT_IDS) {
+            if (keep) out->ids[rank] = acc_node;
+            if (lane == 0) out->hdr = ST_OK | (n_out << 8);
+        } else {
+            unsigned long long off = 0;
+            if (lane == 0) off = atomicAdd(&counters[CNT_SPILL_CURSOR], (unsigned long long)n_out);
+            off = __shfl_sync(0xFFFFFFFFu, off, 0);
+            if (off + n_out > spill_cap) {
+                if (lane == 0) { atomicOr(&counters[CNT_ERR], (unsigned long long)ERRF_SPILL_FULL); out->hdr = ST_OK; }
+            } else {
+                if (keep) spill[off + rank] = acc_node;
+                if (lane == 0) { out->ids[0] = (uint32_t)off; out->hdr = ST_OK | (n_out << 8); }
+            }
+        }
+    }
+}
+
 int map_reads_generic_dev(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                           const uint32_t* d_worklist, const unsigned long long* d_n_items, ReadSlot* d_slots);
 
@@ -577,10 +732,15 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     IndexView v = c->index.view();
     const uint32_t* in_list = nullptr;
     const unsigned long long* in_count = nullptr;
-    if (d_rows && !c->opt_single_map) {
-        // the clean-pass kernel first; what it defers goes through the full kernel
-        VSPE_TRY(c->defer_list.reserve(n_reads));
+    const uint32_t* to_generic = c->worklist.p;                 // reads the ASCII tier must map
+    const unsigned long long* to_generic_n = c->counters.p + CNT_WORK;
+    if (d_rows) {
+        VSPE_TRY(c->defer_list.reserve(2 * n_reads));
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER, 0, 8, c->stream));
+        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK2, 0, 8, c->stream));
+    }
+    if (d_rows && !c->opt_single_map) {
+        // stage 1: the clean-pass kernel; what it defers goes through the full kernel
 #define VSPE_M1(S, LP) k_map_first<S, LP><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, n_reads, d_slots, \
                                                                         c->defer_list.p, c->counters.p)
         if (cap <= 160) VSPE_M1(13, 16); else if (cap <= 256) VSPE_M1(19, 16); else VSPE_M1(23, 32);
@@ -589,6 +749,7 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
         in_list = c->defer_list.p;
         in_count = c->counters.p + CNT_DEFER;
     }
+    // stage 2: the full seed-and-extend kernel (on the deferred reads, or on everything)
 #define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
                                                                                row_words, n_reads, in_list, in_count, d_slots, \
                                                                                c->worklist.p, c->counters.p)
@@ -599,8 +760,24 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     }
 #undef VSPE_MF
     VSPE_LAUNCH_CHECK(c);
-    // the exhaustive tier consumes the worklist; its length stays on the device
-    VSPE_TRY(map_reads_generic_dev(c, d_buf, d_seq_start, d_seq_end, c->worklist.p, c->counters.p + CNT_WORK, d_slots));
+    if (d_rows) {
+        // stage 3: what stage 2 could not prove (repeats, > 16 nodes): one warp per read, every
+        // window looked up, exact for any postings multiplicity; only reads that do not fit the
+        // 2-bit rows at all (non-ACGT, very long) are left for the ASCII tier
+        if (!c->spill.p) VSPE_TRY(c->spill.reserve(4u << 20));
+        uint32_t* list2 = c->defer_list.p + n_reads;
+        const uint32_t wgrid = (uint32_t)std::min<uint64_t>((n_reads + MW_WARPS - 1) / MW_WARPS, (uint64_t)c->sm_count * 8);
+#define VSPE_MW(S) k_map_windows<S><<<wgrid, MW_WARPS * 32, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->worklist.p, \
+                                                                      c->counters.p + CNT_WORK, d_slots, list2, \
+                                                                      c->counters.p + CNT_WORK2, c->spill.p, c->spill.cap, c->counters.p)
+        if (cap <= 160) VSPE_MW(13); else if (cap <= 256) VSPE_MW(19); else VSPE_MW(23);
+#undef VSPE_MW
+        VSPE_LAUNCH_CHECK(c);
+        to_generic = list2;
+        to_generic_n = c->counters.p + CNT_WORK2;
+    }
+    // last stage: the exhaustive ASCII tier consumes what is left; list lengths stay on the device
+    VSPE_TRY(map_reads_generic_dev(c, d_buf, d_seq_start, d_seq_end, to_generic, to_generic_n, d_slots));
     return VSPE_OK;
 }
 
