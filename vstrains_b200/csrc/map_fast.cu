@@ -563,27 +563,41 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
     const uint32_t* row = s_fwd + t * STRIDE;
     uint32_t nn = 0;
     if (!defer) {
-        const uint32_t npos = rlen - L + 1;
-        uint32_t i = 0, tp = NONE32, node = 0;
+        uint32_t tp = NONE32, node = 0;
         if (probe_window(ix, row, 0, tp, node) != PROBE_UNIQUE) defer = true;
+        // Walk the read along one diagonal per node strand: read base p sits at text position
+        // p + delta.  Each step compares 32 bases and tests the uniq bits of the 32 windows that
+        // END at those bases; the first window of a stretch is unique by construction (seed:
+        // PROBE_UNIQUE, later ones: successor table).
+        uint32_t i0 = 0, p = L;
         while (!defer) {
             const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
             const bool rcs = tp >= s1;
             const uint32_t q = 2 * node + (rcs ? 1u : 0u);
             const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
-            const uint32_t room_t = send - (tp + L), room_r = rlen - (i + L);
-            const uint32_t max_ext = min(room_t, room_r);
-            const uint32_t ext = match_len(row, i + L, ix.text, tp + L, max_ext);
-            if (ext < max_ext || (ext && uniq_run(ix.uniq, tp + 1, ext) < ext)) { defer = true; break; }
-            if (!list_add(s_node, s_vk, t, nn, node, 1 + ext, i)) { defer = true; break; }
-            i += 1 + ext;
-            if (i >= npos) break;
-            const uint32_t nb = i + L - 1;
-            const uint32_t b = (row[nb >> 4] >> ((nb & 15) * 2)) & 3u;
+            const int delta = (int)tp - (int)i0;
+            const uint32_t lim = min(rlen, (uint32_t)((int)send - delta));   // read position where the strand ends
+            while (p < lim) {
+                const uint32_t n = min(32u, lim - p);
+                uint64_t x = read64(row, p) ^ extract64(ix.text, (uint64_t)((int)p + delta));
+                const uint32_t u = (uint32_t)((int)p + delta) - L + 1;         // text position of the first window ending here
+                const uint32_t ub = __funnelshift_r(__ldg(ix.uniq + (u >> 5)), __ldg(ix.uniq + (u >> 5) + 1), u & 31);
+                const uint32_t m32 = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
+                if (n < 32) x &= (1ull << (2 * n)) - 1;
+                if (x != 0 || (ub & m32) != m32) { defer = true; break; }
+                p += n;
+            }
+            if (defer) break;
+            if (!list_add(s_node, s_vk, t, nn, node, lim - L + 1 - i0, i0)) { defer = true; break; }
+            if (lim >= rlen) break;
+            // the strand ended before the read: successor window for the read's next base
+            const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
             const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
             if (sc.x == NONE32) { defer = true; break; }
+            i0 = lim - L + 1;
             tp = sc.x;
             node = sc.y;
+            p = lim + 1;
         }
     }
     uint32_t n_out = 0;
