@@ -55,6 +55,8 @@ typedef struct vspe_stats {
     float ms_map;             /* K2+K4 pack + lookup                                        */
     float ms_count;           /* K5+K6 key emit + radix partition + run-length reduce       */
     float ms_total;           /* device time of the last vspe_count_* call                  */
+    float ms_k_scan_pack;     /* sum of k_scan_pack launch durations (CUDA events on its stream) */
+    uint32_t n_k_scan_pack;   /* ... and how many launches that was                         */
 } vspe_stats;
 
 typedef struct vspe_ctx vspe_ctx;

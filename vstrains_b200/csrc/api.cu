@@ -407,6 +407,7 @@ void vspe_destroy(vspe_ctx* c) {
         if (c->copy_stream[b]) cudaStreamDestroy(c->copy_stream[b]);
     }
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_k) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

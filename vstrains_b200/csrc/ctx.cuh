@@ -29,6 +29,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_k[2] = {};
     Index index;
     DevBuf<uint64_t> mats;            // [2][N][N] node_mat then short_mat
     DevBuf<unsigned long long> counters;

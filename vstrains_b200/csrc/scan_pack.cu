@@ -432,14 +432,22 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
         a.dbg = c->dbg_times.p;
         c->dbg_tiles = n_tiles;
     }
+    // the dominant kernel is timed on its own (CUDA events on the launching stream)
+    if (!c->ev_k[0]) { VSPE_CUDA(cudaEventCreate(&c->ev_k[0])); VSPE_CUDA(cudaEventCreate(&c->ev_k[1])); }
+    VSPE_CUDA(cudaEventRecord(c->ev_k[0], c->stream));
     k_scan_pack<<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
     VSPE_LAUNCH_CHECK(c);
+    VSPE_CUDA(cudaEventRecord(c->ev_k[1], c->stream));
     unsigned long long h_total = 0, h_err = 0;
     VSPE_CUDA(cudaMemcpyAsync(&h_total, a.total_out, 8, cudaMemcpyDeviceToHost, c->stream));
     VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     *n_terms = h_total;
     *err_flags = h_err;
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev_k[0], c->ev_k[1]) == cudaSuccess) { c->stats.ms_k_scan_pack += ms; c->stats.n_k_scan_pack++; }
+    }
     const unsigned long long transient = ERRF_SLOTS_FULL | ERRF_TILE_FULL;
     if (h_err & transient) {
         unsigned long long cleared = h_err & ~transient;
