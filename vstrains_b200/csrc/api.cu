@@ -47,26 +47,26 @@ struct MateStream {
 
 static inline uint64_t seq_lines_before(uint64_t x) { return (x + 2) / 4; }   // #{l < x : l % 4 == 1}
 
+static int report_error_flags(unsigned long long e);
 static int check_kernel_errors(Ctx* c) {
     unsigned long long e = 0;
     VSPE_CUDA(cudaMemcpyAsync(&e, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
-    if (e & ERRF_NON_ASCII) { set_error("input contains a byte >= 0x80 (non-ASCII FASTQ is outside the reference's contract)"); return VSPE_ERR_NON_ASCII; }
-    if (e & ERRF_SPILL_FULL) { set_error("node-list spill pool exhausted"); return VSPE_ERR_LIMIT; }
-    if (e & ERRF_KEYS_FULL) { set_error("key buffer exhausted"); return VSPE_ERR_LIMIT; }
-    return VSPE_OK;
+    return report_error_flags(e);
 }
 
 // One chunk of one mate's byte stream, resident on the device.  The chunk must start at a line
 // start and (unless it is the last chunk) end right after a terminator.
-static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint64_t n, bool is_last, int last_byte) {
+static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint64_t n, bool is_last, int last_byte,
+                      bool sync_after = true) {
     if (n == 0) {
         if (is_last) ms.lines = ms.line_base;
         return VSPE_OK;
     }
     MateBuf& mb = c->mate[m];
     uint64_t n_terms = 0;
-    cudaEvent_t e0 = c->ev[2], e1 = c->ev[3], e2 = c->ev[4];
+    for (auto& e : c->ev_m[m]) if (!e) VSPE_CUDA(cudaEventCreate(&e));
+    cudaEvent_t e0 = c->ev_m[m][0], e1 = c->ev_m[m][1], e2 = c->ev_m[m][2];
     VSPE_CUDA(cudaEventRecord(e0, c->stream));
     const uint64_t lb = ms.line_base;
     const uint64_t rec_first = seq_lines_before(lb);
@@ -134,12 +134,15 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
             VSPE_TRY(map_reads_fast(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, n_seq, mb.slots.p + rec_first));
     }
     VSPE_CUDA(cudaEventRecord(e2, c->stream));
-    VSPE_CUDA(cudaStreamSynchronize(c->stream));
-    float a = 0, b = 0;
-    cudaEventElapsedTime(&a, e0, e1);
-    cudaEventElapsedTime(&b, e1, e2);
-    c->stats.ms_scan += a;
-    c->stats.ms_map += b;
+    if (sync_after) {
+        // streaming callers reuse the chunk buffer next: wait, and account the stage times now
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        c->stats.ms_scan += a;
+        c->stats.ms_map += b;
+    }
     ms.n_slots = rec_first + n_seq;
     ms.line_base = lb + n_terms;
     if (is_last) {
@@ -149,16 +152,27 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     return VSPE_OK;
 }
 
+static int report_error_flags(unsigned long long e) {
+    if (e & ERRF_NON_ASCII) { set_error("input contains a byte >= 0x80 (non-ASCII FASTQ is outside the reference's contract)"); return VSPE_ERR_NON_ASCII; }
+    if (e & ERRF_SPILL_FULL) { set_error("node-list spill pool exhausted"); return VSPE_ERR_LIMIT; }
+    if (e & ERRF_KEYS_FULL) { set_error("key buffer exhausted"); return VSPE_ERR_LIMIT; }
+    return VSPE_OK;
+}
+
 static int finish_pairs(Ctx* c, const MateStream& f, const MateStream& r) {
     uint64_t total = std::min(f.lines / 4, r.lines / 4);       // PE_Inference.py:154
     cudaEvent_t e0 = c->ev[5], e1 = c->ev[6];
     VSPE_CUDA(cudaEventRecord(e0, c->stream));
+    c->err_flags_fresh = false;
     VSPE_TRY(count_pairs(c, c->mate[0].slots.p, c->mate[1].slots.p, total));
     VSPE_CUDA(cudaEventRecord(e1, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->stats.ms_count += ms;
+    // count_pairs reads the kernels' error flags together with its key count; without pairs
+    // (empty inputs) they are fetched here
+    if (c->err_flags_fresh) return report_error_flags(c->last_err_flags);
     return check_kernel_errors(c);
 }
 
@@ -434,6 +448,7 @@ int vspe_reset(vspe_ctx* c) {
     c->stats.n_kmers = keep.n_kmers;
     c->stats.table_slots = keep.table_slots;
     c->launches = 0;
+    c->keys_seen = 0;
     return VSPE_OK;
 }
 
@@ -453,28 +468,40 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
     MateStream* ms[2] = {&f, &r};
     int last[2] = {-1, -1};
     uint32_t hint = 0;
-    {   // one small D2H per mate: its last byte (does the file end with a terminator?) and a
-        // prefix to size the packed rows
-        std::vector<uint8_t> head(16384);
+    {   // one small D2H round for both mates: last byte (does the file end with a terminator?)
+        // and a prefix to size the packed rows
+        static thread_local std::vector<uint8_t> head(2 * 16384);
+        uint8_t lastb[2] = {0, 0};
+        uint64_t hn[2] = {0, 0};
         for (int m = 0; m < 2; m++) {
             if (!ns[m]) continue;
-            uint8_t b = 0;
-            uint64_t hn = std::min<uint64_t>(ns[m], head.size());
-            VSPE_CUDA(cudaMemcpyAsync(&b, bufs[m] + ns[m] - 1, 1, cudaMemcpyDeviceToHost, c->stream));
-            VSPE_CUDA(cudaMemcpyAsync(head.data(), bufs[m], hn, cudaMemcpyDeviceToHost, c->stream));
-            VSPE_CUDA(cudaStreamSynchronize(c->stream));
-            last[m] = b;
-            hint = std::max(hint, seq_len_hint(head.data(), hn));
+            hn[m] = std::min<uint64_t>(ns[m], 16384);
+            VSPE_CUDA(cudaMemcpyAsync(&lastb[m], bufs[m] + ns[m] - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+            VSPE_CUDA(cudaMemcpyAsync(head.data() + 16384 * m, bufs[m], hn[m], cudaMemcpyDeviceToHost, c->stream));
+        }
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+        for (int m = 0; m < 2; m++) {
+            if (!ns[m]) continue;
+            last[m] = lastb[m];
+            hint = std::max(hint, seq_len_hint(head.data() + 16384 * m, hn[m]));
         }
     }
     c->read_len_hint = hint;
-    for (int m = 0; m < 2; m++) VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last[m]));
+    for (int m = 0; m < 2; m++) VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last[m], false));
     VSPE_TRY(finish_pairs(c, f, r));
     VSPE_CUDA(cudaEventRecord(t1, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     float ms_total = 0;
     cudaEventElapsedTime(&ms_total, t0, t1);
     c->stats.ms_total = ms_total;
+    for (int m = 0; m < 2; m++) {
+        if (!ns[m]) continue;
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, c->ev_m[m][0], c->ev_m[m][1]);
+        cudaEventElapsedTime(&b, c->ev_m[m][1], c->ev_m[m][2]);
+        c->stats.ms_scan += a;
+        c->stats.ms_map += b;
+    }
     c->stats.bytes_fwd += n_fwd;
     c->stats.bytes_rve += n_rve;
     return VSPE_OK;

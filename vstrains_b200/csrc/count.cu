@@ -203,15 +203,19 @@ int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total
     for (uint64_t off = 0; off < total; off += BATCH) {
         uint64_t n = total - off < BATCH ? total - off : BATCH;
         uint32_t grid = (uint32_t)((n + PAIR_THREADS - 1) / PAIR_THREADS);
-        unsigned long long keys_before = 0, keys_after = 0;
-        VSPE_CUDA(cudaMemcpyAsync(&keys_before, c->counters.p + CNT_KEYS, 8, cudaMemcpyDeviceToHost, st));
+        unsigned long long h_keys = 0, h_err = 0;
         VSPE_CUDA(cudaMemsetAsync(g_hist, 0, (n_buckets + 1) * 8, st));
         k_pair_count<<<grid, PAIR_THREADS, n_buckets * 4, st>>>(d_f + off, d_r + off, n, N, c->spill.p, low_bits, n_buckets,
                                                                 g_hist, c->counters.p);
         VSPE_LAUNCH_CHECK(c);
-        VSPE_CUDA(cudaMemcpyAsync(&keys_after, c->counters.p + CNT_KEYS, 8, cudaMemcpyDeviceToHost, st));
+        // one D2H + sync per batch: the cumulative key counter and the kernels' error flags
+        VSPE_CUDA(cudaMemcpyAsync(&h_keys, c->counters.p + CNT_KEYS, 8, cudaMemcpyDeviceToHost, st));
+        VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, st));
         VSPE_CUDA(cudaStreamSynchronize(st));
-        uint64_t n_keys = keys_after - keys_before;
+        c->last_err_flags = h_err;                             // every scan / map kernel of this call ran before
+        c->err_flags_fresh = true;
+        uint64_t n_keys = h_keys - c->keys_seen;
+        c->keys_seen = h_keys;
         if (n_keys == 0) continue;
         if (n_keys > 0xFFFFFFF0ull) { set_error("key batch too large"); return VSPE_ERR_LIMIT; }
         VSPE_TRY(c->keys.reserve(n_keys));

@@ -48,6 +48,10 @@ struct Ctx {
     DevBuf<unsigned long long> bucket;   // [3][n_buckets + 1]: histogram, start, cursor
     DevBuf<unsigned long long> block_sums;
     bool count_attr_set = false;
+    uint64_t keys_seen = 0;            // host copy of CNT_KEYS after the last count batch
+    unsigned long long last_err_flags = 0;
+    bool err_flags_fresh = false;
+    cudaEvent_t ev_m[2][3] = {};       // per mate: scan start, scan end / map start, map end
     bool scan_pack_attr_set = false;
     // staging for host-input entry points
     uint8_t* pinned[2] = {nullptr, nullptr};
