@@ -121,6 +121,22 @@ int vspe_write_info(const char* path, const char* const* ids, uint32_t n, const 
 int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, int kmer_size,
              const char* out_dir, int n_gpus, vspe_stats* stats);
 
+/* Sparse counting -- for graphs whose N*N matrices cannot exist (dense counting needs
+ * 2*N*N <= 2^28 cells, N <= 11 585); switched on automatically for larger graphs or by
+ * vspe_set_option(ctx, "sparse", 1).  The context then keeps the non-zero cells as runs sorted by
+ * key = mat*N*N + i*N + j (mat 0 = node_mat, 1 = short_mat of PE_Inference.py:139-140):
+ * radix sort of the (matrix, i, j) keys + run-length reduce.
+ *   vspe_sparse_host   library-owned host copies, valid until the next call on the context
+ *   vspe_sparse_merge  add the runs of another context / rank (exact integer sums)
+ *   vspe_write_info_sparse  only the non-zero lines "id_i:id_j:count\n" of matrix `mat`; the
+ *                      consumer (VStrains_IO.py:598-612) zero-initialises every key, so it parses
+ *                      to the same dict as the dense file (opt-in: the bytes differ). */
+int vspe_is_sparse(vspe_ctx* ctx);
+int vspe_sparse_host(vspe_ctx* ctx, uint64_t* n_entries, const uint64_t** keys, const uint64_t** counts);
+int vspe_sparse_merge(vspe_ctx* ctx, const uint64_t* keys, const uint64_t* counts, uint64_t n_entries);
+int vspe_write_info_sparse(const char* path, const char* const* ids, uint32_t n, const uint64_t* keys,
+                           const uint64_t* counts, uint64_t n_entries, int mat);
+
 /* Pinned host memory for callers that want zero-copy streaming in vspe_count_host. */
 void* vspe_alloc_pinned(size_t bytes);
 void vspe_free_pinned(void* p);

@@ -276,3 +276,97 @@ def test_noisy_reads_match_c_oracle(subst, full_second, sub_rate):
         assert np.array_equal(short.astype(np.int64), oshort), name
         for k, v in ostats.items():
             assert stats[k] == v
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse (COO) counting: 64-bit keys, LSD radix sort + run-length reduce
+# ------------------------------------------------------------------------------------------------
+def _coo_from_dense(node, short):
+    n = node.shape[0]
+    flat = np.concatenate([node.reshape(-1), short.reshape(-1)]).astype(np.uint64)
+    keys = np.nonzero(flat)[0].astype(np.uint64)
+    return keys, flat[keys.astype(np.int64)]
+
+
+def test_sparse_mode_equals_dense_on_golden(golden):
+    if golden.status != 0:
+        return
+    ids, seqs = pe_inference.parse_gfa_nodes(golden.gfa)
+    with pe_inference.PEIndex(seqs, golden.k) as ix:
+        ix.count_host(golden.fwd, golden.rve)
+        dn, ds = ix.matrices()
+        ix.set_option("sparse", 1)
+        assert ix.is_sparse
+        ix.reset()
+        ix.count_host(golden.fwd, golden.rve)
+        keys, counts = ix.sparse()
+        ek, ec = _coo_from_dense(dn, ds)
+        assert np.array_equal(keys, ek) and np.array_equal(counts, ec)
+        assert np.all(np.diff(keys.astype(np.int64)) > 0)
+
+
+@pytest.mark.parametrize("name,pairs", [("C2", 30000), ("C3", 12000)])
+def test_sparse_mode_batches_and_merge_match_oracle(name, pairs):
+    cfg = synth.CONFIGS[name]
+    g, f, r = synth.generate(cfg, pairs=pairs)
+    gfa = g.to_gfa()
+    ids, seqs = pe_inference.parse_gfa_nodes(gfa)
+    onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
+    ek, ec = _coo_from_dense(onode.astype(np.uint64), oshort.astype(np.uint64))
+    from vstrains_b200 import shard
+    with pe_inference.PEIndex(seqs, cfg.k) as ix, pe_inference.PEIndex(seqs, cfg.k) as iy:
+        for i in (ix, iy):
+            i.set_option("sparse", 1)
+        ix.count_host(f, r)
+        keys, counts = ix.sparse()
+        assert np.array_equal(keys, ek) and np.array_equal(counts, ec)
+        st = ix.stats()
+        for k, v in ostats.items():
+            assert st[k] == v
+        # three shards: two accumulated on one context, one on another, then merged
+        ix.reset()
+        rng = shard.shard_ranges(f, r, 3)
+        for a, b, c_, d in rng[:2]:
+            ix.count_host(f[a:b], r[c_:d])
+        a, b, c_, d = rng[2]
+        iy.count_host(f[a:b], r[c_:d])
+        ix.sparse_merge(*iy.sparse())
+        keys, counts = ix.sparse()
+        assert np.array_equal(keys, ek) and np.array_equal(counts, ec)
+
+
+def test_large_graph_switches_to_sparse_automatically(tmp_path):
+    """N above the dense limit (11 585): no N*N matrices anywhere; checked against the Python
+    oracle's sparse dicts; the CLI writes the non-zero lines only."""
+    cfg = synth.Config("big", 10_000, 4, 0.01, 150, 2000, 77, n_genomes=28)
+    g, f, r = synth.generate(cfg)
+    gfa = g.to_gfa()
+    ids, seqs = pe_inference.parse_gfa_nodes(gfa)
+    n = len(ids)
+    assert n > 11585
+    with pe_inference.PEIndex(seqs, cfg.k) as ix:
+        assert ix.is_sparse
+        ix.count_host(f, r)
+        keys, counts = ix.sparse()
+        stats = ix.stats()
+    oids, oseqs = pe_oracle.parse_gfa(gfa)
+    table = pe_oracle.build_index(oseqs, cfg.k + 1)
+    node, short, ostats = pe_oracle.count_pairs(pe_oracle.split_lines(f.tobytes()), pe_oracle.split_lines(r.tobytes()),
+                                                table, [len(s) for s in oseqs], cfg.k + 1)
+    exp = {i * n + j: c for (i, j), c in node.items()}
+    exp.update({n * n + i * n + j: c for (i, j), c in short.items()})
+    assert dict(zip(keys.tolist(), counts.tolist())) == exp
+    for k, v in ostats.items():
+        assert stats[k] == v
+    # CLI: sparse files
+    (tmp_path / "g.gfa").write_bytes(gfa)
+    f.tofile(tmp_path / "f.fq")
+    r.tofile(tmp_path / "r.fq")
+    out = tmp_path / "aln"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "utils", "VStrains_PE_Inference.py"), "-g", str(tmp_path / "g.gfa"),
+                        "-o", str(out), "-f", str(tmp_path / "f.fq"), "-r", str(tmp_path / "r.fq"), "-k", str(cfg.k)], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    pe_lines = (out / "pe_info").read_text().splitlines()
+    st_lines = (out / "st_info").read_text().splitlines()
+    assert sorted(pe_lines) == sorted("%s:%s:%d" % (ids[i], ids[j], c) for (i, j), c in node.items())
+    assert sorted(st_lines) == sorted("%s:%s:%d" % (ids[i], ids[j], c) for (i, j), c in short.items())

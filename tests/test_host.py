@@ -97,3 +97,15 @@ def test_shims_keep_the_reference_names():
     mod = importlib.import_module("VStrains_PE_Inference")
     for name in ("main", "reverse_seq", "single_end_read_mapping"):
         assert hasattr(mod, name)
+
+
+def test_sparse_writer_emits_only_nonzero_lines(tmp_path):
+    ids = ["a", "-7", "x9"]
+    n = len(ids)
+    keys = np.array([1, 4, 8, n * n + 0, n * n + 5], dtype=np.uint64)
+    counts = np.array([3, 0, 12, 7, 2**40], dtype=np.uint64)
+    p0, p1 = str(tmp_path / "pe_info"), str(tmp_path / "st_info")
+    pe_inference.write_info_sparse(p0, ids, keys, counts, 0)
+    pe_inference.write_info_sparse(p1, ids, keys, counts, 1)
+    assert open(p0).read() == "a:-7:3\nx9:x9:12\n"
+    assert open(p1).read() == "a:a:7\n-7:x9:%d\n" % 2**40

@@ -67,6 +67,10 @@ def lib():
     L.vspe_split_records.argtypes = [P, P, u64, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(P), ctypes.POINTER(P)]
     L.vspe_write_info.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), u32, P]
     L.vspe_run.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i32, ctypes.c_char_p, i32, ctypes.POINTER(Stats)]
+    L.vspe_is_sparse.argtypes = [P]
+    L.vspe_sparse_host.argtypes = [P, ctypes.POINTER(u64), ctypes.POINTER(P), ctypes.POINTER(P)]
+    L.vspe_sparse_merge.argtypes = [P, P, P, u64]
+    L.vspe_write_info_sparse.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), u32, P, P, u64, i32]
     L.vspe_alloc_pinned.argtypes = [ctypes.c_size_t]
     L.vspe_alloc_pinned.restype = P
     L.vspe_free_pinned.argtypes = [P]

@@ -34,7 +34,8 @@ int map_reads_packed(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, 
 uint32_t map_fast_cap(uint32_t hint);
 int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len,
                   const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve, int n_gpus,
-                  std::vector<uint64_t>& node_mat, std::vector<uint64_t>& short_mat, vspe_stats* stats);
+                  std::vector<uint64_t>& node_mat, std::vector<uint64_t>& short_mat,
+                  std::vector<uint64_t>* sparse_keys, std::vector<uint64_t>* sparse_counts, vspe_stats* stats);
 
 // ---------------------------------------------------------------------------------------
 // per-mate streaming state
@@ -164,7 +165,8 @@ static int finish_pairs(Ctx* c, const MateStream& f, const MateStream& r) {
     cudaEvent_t e0 = c->ev[5], e1 = c->ev[6];
     VSPE_CUDA(cudaEventRecord(e0, c->stream));
     c->err_flags_fresh = false;
-    VSPE_TRY(count_pairs(c, c->mate[0].slots.p, c->mate[1].slots.p, total));
+    if (c->sparse.enabled) VSPE_TRY(count_pairs_sparse(c, c->mate[0].slots.p, c->mate[1].slots.p, total));
+    else VSPE_TRY(count_pairs(c, c->mate[0].slots.p, c->mate[1].slots.p, total));
     VSPE_CUDA(cudaEventRecord(e1, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0;
@@ -437,7 +439,8 @@ int vspe_index_build(vspe_ctx* c, const uint8_t* seqs, const uint64_t* seq_off, 
 int vspe_reset(vspe_ctx* c) {
     VSPE_TRY(require_index(c));
     uint64_t nn = 2ull * c->index.n_nodes * c->index.n_nodes;
-    if (nn) VSPE_CUDA(cudaMemsetAsync(c->mats.p, 0, nn * 8, c->stream));
+    if (nn && !c->sparse.enabled) VSPE_CUDA(cudaMemsetAsync(c->mats.p, 0, nn * 8, c->stream));
+    c->sparse.n_runs = 0;
     VSPE_CUDA(cudaMemsetAsync(c->counters.p, 0, CNT_COUNT_ * 8, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     vspe_stats keep = c->stats;
@@ -529,8 +532,63 @@ int vspe_count_host(vspe_ctx* c, const uint8_t* fwd, uint64_t n_fwd, const uint8
     return VSPE_OK;
 }
 
+static int require_dense(Ctx* c) {
+    if (c->sparse.enabled) { set_error("this context counts sparsely (graph too large for N*N matrices or sparse forced): use vspe_sparse_host"); return VSPE_ERR_ARG; }
+    return VSPE_OK;
+}
+
+int vspe_sparse_host(vspe_ctx* c, uint64_t* n_entries, const uint64_t** keys, const uint64_t** counts) {
+    VSPE_TRY(require_index(c));
+    if (!c->sparse.enabled) { set_error("this context counts densely: use vspe_matrices_host"); return VSPE_ERR_ARG; }
+    Sparse& sp = c->sparse;
+    sp.h_keys.resize(sp.n_runs ? sp.n_runs : 1);
+    sp.h_counts.resize(sp.n_runs ? sp.n_runs : 1);
+    if (sp.n_runs) {
+        VSPE_CUDA(cudaMemcpyAsync(sp.h_keys.data(), sp.k[0].p, sp.n_runs * 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_CUDA(cudaMemcpyAsync(sp.h_counts.data(), sp.v[0].p, sp.n_runs * 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (n_entries) *n_entries = sp.n_runs;
+    if (keys) *keys = sp.h_keys.data();
+    if (counts) *counts = sp.h_counts.data();
+    return VSPE_OK;
+}
+
+int vspe_sparse_merge(vspe_ctx* c, const uint64_t* keys, const uint64_t* counts, uint64_t n_entries) {
+    VSPE_TRY(require_index(c));
+    if (!c->sparse.enabled) { set_error("this context counts densely"); return VSPE_ERR_ARG; }
+    return sparse_merge_host(c, keys, counts, n_entries);
+}
+
+int vspe_is_sparse(vspe_ctx* c) { return c && c->sparse.enabled ? 1 : 0; }
+
+int vspe_write_info_sparse(const char* path, const char* const* ids, uint32_t n, const uint64_t* keys, const uint64_t* counts,
+                           uint64_t n_entries, int mat) {
+    if (!path || (n && !ids) || (n_entries && (!keys || !counts)) || (mat != 0 && mat != 1)) { set_error("bad arguments"); return VSPE_ERR_ARG; }
+    FILE* fh = fopen(path, "wb");
+    if (!fh) { set_error("cannot create %s: %s", path, strerror(errno)); return VSPE_ERR_IO; }
+    const uint64_t NN = (uint64_t)n * n, lo = (uint64_t)mat * NN, hi = lo + NN;
+    std::vector<char> buf;
+    buf.reserve(1 << 20);
+    for (uint64_t e = 0; e < n_entries; e++) {
+        if (keys[e] < lo || keys[e] >= hi || counts[e] == 0) continue;
+        const uint64_t cell = keys[e] - lo, i = cell / n, j = cell % n;
+        char tmp[32];
+        char* q = put_u64(tmp, counts[e]);
+        const char *a = ids[i], *b = ids[j];
+        buf.insert(buf.end(), a, a + strlen(a)); buf.push_back(':');
+        buf.insert(buf.end(), b, b + strlen(b)); buf.push_back(':');
+        buf.insert(buf.end(), tmp, q); buf.push_back('\n');
+        if (buf.size() > (1u << 20) - 256) { fwrite(buf.data(), 1, buf.size(), fh); buf.clear(); }
+    }
+    if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), fh);
+    if (fclose(fh) != 0) { set_error("write to %s failed", path); return VSPE_ERR_IO; }
+    return VSPE_OK;
+}
+
 int vspe_matrices_device(vspe_ctx* c, uint64_t** d_mats, uint64_t* n_elems) {
     VSPE_TRY(require_index(c));
+    VSPE_TRY(require_dense(c));
     if (d_mats) *d_mats = c->mats.p;
     if (n_elems) *n_elems = 2ull * c->index.n_nodes * c->index.n_nodes;
     return VSPE_OK;
@@ -538,6 +596,7 @@ int vspe_matrices_device(vspe_ctx* c, uint64_t** d_mats, uint64_t* n_elems) {
 
 int vspe_matrices_host(vspe_ctx* c, uint64_t* node_mat, uint64_t* short_mat) {
     VSPE_TRY(require_index(c));
+    VSPE_TRY(require_dense(c));
     uint64_t nn = (uint64_t)c->index.n_nodes * c->index.n_nodes;
     if (nn == 0) return VSPE_OK;
     if (node_mat) VSPE_CUDA(cudaMemcpyAsync(node_mat, c->mats.p, nn * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -740,20 +799,41 @@ int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, i
     VSPE_TRY(f.open_ro(fwd_path));
     VSPE_TRY(r.open_ro(rve_path));
     uint32_t N = (uint32_t)nodes.ids.size();
-    std::vector<uint64_t> nm, sm;
+    std::vector<uint64_t> nm, sm, sk, sc;
+    bool sparse_out = !dense_possible(N) || (getenv("VSPE_SPARSE") && atoi(getenv("VSPE_SPARSE")) != 0);
     if (n_gpus > 1) {
-        VSPE_TRY(run_multi_gpu(nodes.seqs.data(), nodes.off.data(), N, (uint32_t)kmer_size + 1, f.p, f.n, r.p, r.n, n_gpus, nm, sm, stats));
+        VSPE_TRY(run_multi_gpu(nodes.seqs.data(), nodes.off.data(), N, (uint32_t)kmer_size + 1, f.p, f.n, r.p, r.n, n_gpus, nm, sm,
+                               sparse_out ? &sk : nullptr, sparse_out ? &sc : nullptr, stats));
     } else {
         vspe_ctx* c = nullptr;
         VSPE_TRY(vspe_create(0, &c));
+        if (sparse_out) c->opt_sparse = 1;
         int rc = vspe_index_build(c, nodes.seqs.data(), nodes.off.data(), N, (uint32_t)kmer_size + 1);
         if (rc == VSPE_OK) rc = vspe_count_host(c, f.p, f.n, r.p, r.n);
-        nm.assign((size_t)N * N, 0);
-        sm.assign((size_t)N * N, 0);
-        if (rc == VSPE_OK) rc = vspe_matrices_host(c, nm.data(), sm.data());
+        if (rc == VSPE_OK && !sparse_out) {
+            nm.assign((size_t)N * N, 0);
+            sm.assign((size_t)N * N, 0);
+            rc = vspe_matrices_host(c, nm.data(), sm.data());
+        }
+        if (rc == VSPE_OK && sparse_out) {
+            uint64_t ne = 0;
+            const uint64_t *pk = nullptr, *pc = nullptr;
+            rc = vspe_sparse_host(c, &ne, &pk, &pc);
+            if (rc == VSPE_OK) { sk.assign(pk, pk + ne); sc.assign(pc, pc + ne); }
+        }
         if (rc == VSPE_OK && stats) rc = vspe_get_stats(c, stats);
         vspe_destroy(c);
         if (rc != VSPE_OK) return rc;
+    }
+    if (sparse_out) {
+        // N*N lines cannot be written for such graphs; only the non-zero lines are.  The consumer
+        // (reference utils/VStrains_IO.py:598-612) zero-initialises every key, so the parsed result
+        // is the same dict a dense file would give.
+        std::vector<const char*> idq(N);
+        for (uint32_t i = 0; i < N; i++) idq[i] = nodes.ids[i].c_str();
+        VSPE_TRY(vspe_write_info_sparse((dir + "/pe_info").c_str(), idq.data(), N, sk.data(), sc.data(), sk.size(), 0));
+        VSPE_TRY(vspe_write_info_sparse((dir + "/st_info").c_str(), idq.data(), N, sk.data(), sc.data(), sk.size(), 1));
+        return VSPE_OK;
     }
     std::vector<const char*> idp(N);
     for (uint32_t i = 0; i < N; i++) idp[i] = nodes.ids[i].c_str();
@@ -775,6 +855,19 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "chunk_mb")) c->opt_chunk_mb = value;
     else if (!strcmp(name, "scan_two_pass")) c->opt_scan_two_pass = value;
     else if (!strcmp(name, "scan_mode")) c->opt_scan_mode = value;
+    else if (!strcmp(name, "sparse")) {
+        // effective for the next index build; on a built index only switching a dense-capable graph is allowed
+        c->opt_sparse = value;
+        if (c->index.built && dense_possible(c->index.n_nodes)) {
+            c->sparse.enabled = value != 0;
+            c->sparse.n_runs = 0;
+            if (!c->sparse.enabled) {
+                uint64_t nn = 2ull * c->index.n_nodes * c->index.n_nodes;
+                VSPE_TRY(c->mats.reserve(nn ? nn : 1));
+                VSPE_CUDA(cudaMemset(c->mats.p, 0, (nn ? nn : 1) * 8));
+            }
+        }
+    }
     else if (!strcmp(name, "single_map")) c->opt_single_map = value;
     else if (!strcmp(name, "full_second")) {}
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }

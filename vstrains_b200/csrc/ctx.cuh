@@ -18,6 +18,15 @@ enum Counter {
 };
 static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16;
 
+// sparse (COO) counting state: sorted runs (key, count) at the front of k[0] / v[0]
+struct Sparse {
+    bool enabled = false;
+    uint64_t n_runs = 0;
+    DevBuf<unsigned long long> k[2], v[2], vscan, sums64, totals, m, moff;
+    DevBuf<uint32_t> hist, sums32, head;
+    std::vector<uint64_t> h_keys, h_counts;      // host copies handed out by vspe_sparse_host
+};
+
 struct MateBuf {
     Records rec;
     DevBuf<ReadSlot> slots;
@@ -31,7 +40,9 @@ struct Ctx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_k[2] = {};
     Index index;
-    DevBuf<uint64_t> mats;            // [2][N][N] node_mat then short_mat
+    DevBuf<uint64_t> mats;            // [2][N][N] node_mat then short_mat (dense mode)
+    Sparse sparse;                    // sorted (key, count) runs (sparse mode)
+    int64_t opt_sparse = 0;           // force sparse counting
     DevBuf<unsigned long long> counters;
     // K1 scratch
     DevBuf<uint32_t> tile_counts;

@@ -282,10 +282,14 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
     c->stats.n_nodes = n_nodes;
     c->stats.n_kmers = n_kmers;
     c->stats.table_slots = slots;
-    // count matrices: dense [2][N][N] u64
-    uint64_t nn = 2ull * n_nodes * n_nodes;
-    VSPE_TRY(c->mats.reserve(nn ? nn : 1));
-    VSPE_CUDA(cudaMemsetAsync(c->mats.p, 0, (nn ? nn : 1) * 8, st));
+    // count matrices: dense [2][N][N] u64, unless the graph is too large (or sparse mode is forced)
+    c->sparse.enabled = c->opt_sparse != 0 || !dense_possible(n_nodes);
+    c->sparse.n_runs = 0;
+    if (!c->sparse.enabled) {
+        uint64_t nn = 2ull * n_nodes * n_nodes;
+        VSPE_TRY(c->mats.reserve(nn ? nn : 1));
+        VSPE_CUDA(cudaMemsetAsync(c->mats.p, 0, (nn ? nn : 1) * 8, st));
+    }
     VSPE_CUDA(cudaStreamSynchronize(st));
     ix.built = true;
     return VSPE_OK;

@@ -86,10 +86,14 @@ static uint64_t count_lines_host(const uint8_t* p, uint64_t n) {
 }
 
 extern "C" int vspe_count_host(vspe_ctx* c, const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve);
+extern "C" int vspe_sparse_host(vspe_ctx* c, uint64_t* n_entries, const uint64_t** keys, const uint64_t** counts);
+extern "C" int vspe_sparse_merge(vspe_ctx* c, const uint64_t* keys, const uint64_t* counts, uint64_t n_entries);
 
 int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len,
                   const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve, int n_gpus,
-                  std::vector<uint64_t>& node_mat, std::vector<uint64_t>& short_mat, vspe_stats* stats) {
+                  std::vector<uint64_t>& node_mat, std::vector<uint64_t>& short_mat,
+                  std::vector<uint64_t>* sparse_keys, std::vector<uint64_t>* sparse_counts, vspe_stats* stats) {
+    const bool sparse = sparse_keys != nullptr;
     int have = 0;
     if (cudaGetDeviceCount(&have) != cudaSuccess || have < n_gpus) {
         set_error("asked for %d GPUs but %d are visible", n_gpus, have);
@@ -111,6 +115,7 @@ int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes
     for (int g = 0; g < n_gpus; g++) {
         th.emplace_back([&, g] {
             int r = vspe_create(g, &ctx[g]);
+            if (r == VSPE_OK && sparse) ctx[g]->opt_sparse = 1;
             if (r == VSPE_OK) r = vspe_index_build(ctx[g], seqs, seq_off, n_nodes, split_len);
             if (r == VSPE_OK) r = vspe_count_host(ctx[g], fwd + cf[g], cf[g + 1] - cf[g], rve + cr[g], cr[g + 1] - cr[g]);
             rc[g] = r;
@@ -123,7 +128,24 @@ int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes
         if (rc[g] != VSPE_OK) { set_error("GPU %d: %s", g, err[g].c_str()); result = rc[g]; break; }
 
     const uint64_t nn = (uint64_t)n_nodes * n_nodes;
-    if (result == VSPE_OK && nn) {
+    if (result == VSPE_OK && sparse) {
+        // sparse runs: host-mediated merge into device 0 (append + radix sort + run-length reduce)
+        for (int g = 1; g < n_gpus && result == VSPE_OK; g++) {
+            uint64_t ne = 0;
+            const uint64_t *pk = nullptr, *pc = nullptr;
+            cudaSetDevice(g);
+            result = vspe_sparse_host(ctx[g], &ne, &pk, &pc);
+            if (result == VSPE_OK) { cudaSetDevice(0); result = vspe_sparse_merge(ctx[0], pk, pc, ne); }
+        }
+        if (result == VSPE_OK) {
+            uint64_t ne = 0;
+            const uint64_t *pk = nullptr, *pc = nullptr;
+            cudaSetDevice(0);
+            result = vspe_sparse_host(ctx[0], &ne, &pk, &pc);
+            if (result == VSPE_OK) { sparse_keys->assign(pk, pk + ne); sparse_counts->assign(pc, pc + ne); }
+        }
+    }
+    if (result == VSPE_OK && nn && !sparse) {
         std::vector<ncclComm_t> comms(n_gpus);
         std::vector<int> devs(n_gpus);
         for (int g = 0; g < n_gpus; g++) devs[g] = g;
@@ -142,7 +164,7 @@ int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes
             for (int g = 0; g < n_gpus; g++) nccl.CommDestroy(comms[g]);
         }
     }
-    if (result == VSPE_OK) {
+    if (result == VSPE_OK && !sparse) {
         node_mat.assign(nn, 0);
         short_mat.assign(nn, 0);
         result = vspe_matrices_host(ctx[0], node_mat.data(), short_mat.data());

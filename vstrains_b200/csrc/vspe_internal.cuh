@@ -256,4 +256,9 @@ int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start,
 // K5+K6: pairs [0, total) of two slot arrays -> += into dense matrices
 int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total);
 
+int count_pairs_sparse(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total);
+int sparse_merge_host(Ctx* c, const uint64_t* keys, const uint64_t* counts, uint64_t n);
+// dense counting needs 2*N*N <= 2^32 cells in <= 8192 buckets of <= 2^15 cells
+inline bool dense_possible(uint64_t n_nodes) { return 2ull * n_nodes * n_nodes <= (8192ull << 15); }
+
 }  // namespace vspe

@@ -109,8 +109,35 @@ class PEIndex:
         """fptr/rptr: device pointers (e.g. torch ``tensor.data_ptr()``) on this context's GPU."""
         check(self._L.vspe_count_device(self._ctx, fptr, fn, rptr, rn))
 
+    @property
+    def is_sparse(self) -> bool:
+        return bool(self._L.vspe_is_sparse(self._ctx))
+
+    def sparse(self) -> Tuple[np.ndarray, np.ndarray]:
+        """Sparse mode: (keys, counts), keys ascending, key = mat*N*N + i*N + j (mat 0 node_mat, 1 short_mat)."""
+        n, pk, pc = ctypes.c_uint64(), ctypes.c_void_p(), ctypes.c_void_p()
+        check(self._L.vspe_sparse_host(self._ctx, ctypes.byref(n), ctypes.byref(pk), ctypes.byref(pc)))
+        if n.value == 0:
+            return np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+        keys = np.ctypeslib.as_array(ctypes.cast(pk, ctypes.POINTER(ctypes.c_uint64)), (n.value,)).copy()
+        counts = np.ctypeslib.as_array(ctypes.cast(pc, ctypes.POINTER(ctypes.c_uint64)), (n.value,)).copy()
+        return keys, counts
+
+    def sparse_merge(self, keys: np.ndarray, counts: np.ndarray):
+        """Add the runs of another context / rank (exact integer sums)."""
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        c = np.ascontiguousarray(counts, dtype=np.uint64)
+        check(self._L.vspe_sparse_merge(self._ctx, k.ctypes.data if k.size else None, c.ctypes.data if c.size else None, k.size))
+
     def matrices(self) -> Tuple[np.ndarray, np.ndarray]:
         n = self.n_nodes
+        if self.is_sparse:
+            if n > 20000:
+                raise VspeError(-1, "graph too large for dense matrices: use PEIndex.sparse()")
+            keys, counts = self.sparse()
+            flat = np.zeros(2 * n * n, dtype=np.uint64)
+            flat[keys.astype(np.int64)] = counts
+            return flat[: n * n].reshape(n, n), flat[n * n:].reshape(n, n)
         node = np.zeros((n, n), dtype=np.uint64)
         short = np.zeros((n, n), dtype=np.uint64)
         check(self._L.vspe_matrices_host(self._ctx, node.ctypes.data, short.ctypes.data))
@@ -171,6 +198,18 @@ def write_info(path: str, ids: Sequence[str], mat: np.ndarray):
     arr = (ctypes.c_char_p * max(n, 1))(*[i.encode() for i in ids])
     m = np.ascontiguousarray(mat, dtype=np.uint64)
     check(_lib.lib().vspe_write_info(path.encode(), arr, n, m.ctypes.data if n else None))
+
+
+def write_info_sparse(path: str, ids: Sequence[str], keys: np.ndarray, counts: np.ndarray, mat: int):
+    """Only the non-zero ``id_i:id_j:count`` lines of matrix ``mat`` (0 pe_info / node_mat, 1 st_info /
+    short_mat).  ``process_pe_info`` (reference utils/VStrains_IO.py:598-612) parses it to the same
+    dict as the dense file because it zero-initialises every key."""
+    n = len(ids)
+    arr = (ctypes.c_char_p * max(n, 1))(*[i.encode() for i in ids])
+    k = np.ascontiguousarray(keys, dtype=np.uint64)
+    c = np.ascontiguousarray(counts, dtype=np.uint64)
+    check(_lib.lib().vspe_write_info_sparse(path.encode(), arr, n, k.ctypes.data if k.size else None,
+                                            c.ctypes.data if c.size else None, k.size, mat))
 
 
 def single_end_read_mapping(seq: str, kmer_htable, index2seqlen: list, split_len: int, len_index2id: int):
