@@ -230,8 +230,28 @@ def main():
     class _Arr:                                    # torch view of the library's matrices
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-    mptr, mn = ix.matrices_device()
-    mats = torch.as_tensor(_Arr(mptr, mn), device=dev) if mn else torch.zeros(0, dtype=torch.int64, device=dev)
+    sparse = ix.is_sparse                          # graphs too large for N*N matrices (C5) keep sorted runs
+    if sparse:
+        mats = None
+    else:
+        mptr, mn = ix.matrices_device()
+        mats = torch.as_tensor(_Arr(mptr, mn), device=dev) if mn else torch.zeros(0, dtype=torch.int64, device=dev)
+
+    def merge_sparse():
+        """one exchange step: every rank's runs are gathered on rank 0 and merged there"""
+        keys, counts = ix.sparse()
+        sizes = [None] * world
+        dist.all_gather_object(sizes, int(keys.size))
+        cap = max(max(sizes), 1)
+        buf = torch.zeros(2 * cap, dtype=torch.int64, device=dev)
+        buf[: keys.size] = torch.from_numpy(keys.view(np.int64)).to(dev)
+        buf[cap: cap + keys.size] = torch.from_numpy(counts.view(np.int64)).to(dev)
+        gathered = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, gathered, dst=0)
+        if rank == 0:
+            for src in range(1, world):
+                g_ = gathered[src].cpu().numpy()
+                ix.sparse_merge(g_[: sizes[src]].view(np.uint64), g_[cap: cap + sizes[src]].view(np.uint64))
 
     d_f = torch.from_numpy(f).to(dev)
     d_r = torch.from_numpy(r).to(dev)
@@ -240,7 +260,9 @@ def main():
     def step_device():
         ix.reset()
         ix.count_device(d_f.data_ptr(), f.size, d_r.data_ptr(), r.size)
-        if world > 1:
+        if world > 1 and sparse:
+            merge_sparse()
+        elif world > 1:
             dist.all_reduce(mats)
             torch.cuda.synchronize()       # the library's stream does not order with torch's
 
@@ -298,10 +320,12 @@ def main():
     def step_e2e():
         ix.reset()
         ix.count_host_ptr(h_f.data_ptr(), f.size, h_r.data_ptr(), r.size)
-        if world > 1:
+        if world > 1 and sparse:
+            merge_sparse()
+        elif world > 1:
             dist.all_reduce(mats)
             torch.cuda.synchronize()
-        return ix.matrices()
+        return ix.sparse() if sparse else ix.matrices()
 
     for _ in range(2):
         step_e2e()
@@ -342,11 +366,12 @@ def main():
         "config": {"workload": workload, "graph_nodes": n_nodes, "bytes_per_pair": b_pair,
                    "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2; no flush needed" % (bytes_step / 1e6),
                    "index_build_ms": st["ms_index"], "keys_per_pair": st["n_keys"] / max(1, st["used_pairs"]),
-                   "reads_fast": st["reads_fast"], "reads_generic": st["reads_generic"]},
+                   "reads_fast": st["reads_fast"], "reads_generic": st["reads_generic"],
+                   "counting": "sparse runs (LSD radix sort + RLE)" if sparse else "dense matrices (radix partition + counting sort)"},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_step,
-                "d2h_bytes_per_step": int(2 * n_nodes * n_nodes * 8)},
+                "d2h_bytes_per_step": int(16 * ix.sparse()[0].size) if sparse else int(2 * n_nodes * n_nodes * 8)},
         "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
         "whole_job_hbm_frac": value / world * b_pair / 1e9 / peak,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
