@@ -19,13 +19,13 @@
 
 namespace vspe {
 
-static constexpr int SP_WARPS = 12;
+static constexpr int SP_WARPS = 10;
 static constexpr int SP_ITERS = 8;                               // 512-byte warp rows per warp
 static constexpr int SP_TILE = SP_WARPS * SP_ITERS * 32 * 16;    // 48 KiB
 static constexpr int SP_FRONT = 16;                              // bytes kept before the tile
 static constexpr int SP_BACK = 512;                              // bytes kept after the tile (>= longest packed read + 1)
-static constexpr int SP_MAXREC = 768;                            // reads a tile may own (else fallback path)
-static constexpr int SP_QCAP = 128;                              // per warp: vectors that may hold a terminator
+static constexpr int SP_MAXREC = 576;                            // reads a tile may own (else fallback path)
+static constexpr int SP_QCAP = 96;                               // per warp: vectors that may hold a terminator
 static constexpr uint32_t SP_SMEM = SP_FRONT + SP_TILE + SP_BACK + SP_MAXREC * 8 + SP_WARPS * SP_QCAP * 8 + 64;
 
 #define LB_AGG (1ull << 62)
