@@ -532,8 +532,6 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
             uint64_t n_reads, ReadSlot* __restrict__ slots, uint32_t* __restrict__ defer_list,
             unsigned long long* __restrict__ counters) {
     __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
-    __shared__ uint32_t s_node[MAXN][MF_THREADS];
-    __shared__ uint32_t s_vk[MAXN][MF_THREADS];
     __shared__ uint32_t s_len[MF_THREADS];
     const uint64_t r0 = (uint64_t)blockIdx.x * MF_THREADS;
     const uint32_t L = ix.split_len;
@@ -562,6 +560,7 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
     }
     const uint32_t* row = s_fwd + t * STRIDE;
     uint32_t nn = 0;
+    uint32_t l_node[MAXN], l_vk[MAXN];                     // per-read node list: thread-local (L1), not shared memory
     if (!defer) {
         uint32_t tp = NONE32, node = 0;
         if (probe_window(ix, row, 0, tp, node) != PROBE_UNIQUE) defer = true;
@@ -588,7 +587,20 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
                 p += n;
             }
             if (defer) break;
-            if (!list_add(s_node, s_vk, t, nn, node, lim - L + 1 - i0, i0)) { defer = true; break; }
+            {
+                // same node again (cyclic graph): sum the hits, keep the smallest position
+                const uint32_t hits = lim - L + 1 - i0;
+                uint32_t a = 0;
+                for (; a < nn; a++) if (l_node[a] == node) break;
+                if (a == nn) {
+                    if (nn == MAXN) { defer = true; break; }
+                    l_node[a] = node;
+                    l_vk[a] = hits | (i0 << 16);
+                    nn++;
+                } else {
+                    l_vk[a] += hits;
+                }
+            }
             if (lim >= rlen) break;
             // the strand ended before the read: successor window for the read's next base
             const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
@@ -603,18 +615,18 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
     uint32_t n_out = 0;
     if (!defer) {
         for (uint32_t a = 1; a < nn; a++) {
-            const uint32_t kn = s_node[a][t], kv = s_vk[a][t];
+            const uint32_t kn = l_node[a], kv = l_vk[a];
             int b = (int)a - 1;
-            while (b >= 0 && s_node[b][t] > kn) {
-                s_node[b + 1][t] = s_node[b][t];
-                s_vk[b + 1][t] = s_vk[b][t];
+            while (b >= 0 && l_node[b] > kn) {
+                l_node[b + 1] = l_node[b];
+                l_vk[b + 1] = l_vk[b];
                 b--;
             }
-            s_node[b + 1][t] = kn;
-            s_vk[b + 1][t] = kv;
+            l_node[b + 1] = kn;
+            l_vk[b + 1] = kv;
         }
         for (uint32_t a = 0; a < nn; a++) {
-            const uint32_t node = s_node[a][t], vk = s_vk[a][t];
+            const uint32_t node = l_node[a], vk = l_vk[a];
             if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) {
                 if (n_out < (uint32_t)SLOT_IDS) out->ids[n_out] = node;
                 n_out++;
