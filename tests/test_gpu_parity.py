@@ -370,3 +370,29 @@ def test_large_graph_switches_to_sparse_automatically(tmp_path):
     st_lines = (out / "st_info").read_text().splitlines()
     assert sorted(pe_lines) == sorted("%s:%s:%d" % (ids[i], ids[j], c) for (i, j), c in node.items())
     assert sorted(st_lines) == sorted("%s:%s:%d" % (ids[i], ids[j], c) for (i, j), c in short.items())
+
+
+def test_full_size_c2_matches_c_oracle_and_invariants():
+    """BASELINE.json configs[1] at full size (1 M pairs 2x250): bit-exact against the C oracle, plus
+    size-independent properties: every key is accounted for, short_mat is upper triangular, the
+    counters partition the pairs, two runs give identical matrices (determinism)."""
+    import bench
+    cfg, g, f, r = bench.make_workload("C2", 1_000_000, 0)
+    gfa = g.to_gfa()
+    ids, seqs = pe_inference.parse_gfa_nodes(gfa)
+    with pe_inference.PEIndex(seqs, cfg.k) as ix:
+        ix.count_host(f, r)
+        node, short = ix.matrices()
+        st = ix.stats()
+        ix.reset()
+        ix.count_host(f, r)
+        node2, short2 = ix.matrices()
+    assert np.array_equal(node, node2) and np.array_equal(short, short2)
+    assert st["total_pairs"] == 1_000_000 == st["n_pairs"] + st["short_pairs"] + st["used_pairs"]
+    assert int(node.sum()) + int(short.sum()) == st["n_keys"]
+    assert int(np.tril(short, -1).sum()) == 0
+    onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
+    assert np.array_equal(node.astype(np.int64), onode)
+    assert np.array_equal(short.astype(np.int64), oshort)
+    for k, v in ostats.items():
+        assert st[k] == v
