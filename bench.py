@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: the config's, capped)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (experiments)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -226,6 +227,9 @@ def main():
     b_pair = bytes_step / pairs
     ix = pe_inference.PEIndex([bytes(s) for s in g.seqs], cfg.k, device=local_rank)
     ix.set_option("force_generic", args.force_generic)
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        ix.set_option(k_, int(v_))
 
     class _Arr:                                    # torch view of the library's matrices
         def __init__(self, ptr, n):

@@ -14,6 +14,7 @@ enum Counter {
     CNT_BAILED,              // reads the fast tier handed to the exhaustive tier
     CNT_DEFER,               // reads k_map_first deferred to k_map_fast
     CNT_WORK2,               // reads k_map_windows left for the ASCII tier
+    CNT_DEFER2,              // reads k_map_second left for k_map_fast
     CNT_COUNT_
 };
 static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16;
@@ -75,6 +76,7 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_no_second = 0;         // 1: skip k_map_second
     int64_t opt_single_map = 0;        // 1: skip k_map_first (every read through the full kernel)
     int64_t opt_subst = 1;             // build / use the substitution-hit bitmap
     int64_t opt_dbg_times = 0;

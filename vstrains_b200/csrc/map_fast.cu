@@ -37,6 +37,7 @@
 namespace vspe {
 
 static constexpr int MF_THREADS = 128;
+static constexpr uint32_t LIST_SPREAD = 4;
 static constexpr int MAXN = 16;
 
 __device__ __forceinline__ bool keep_node_f(uint32_t v, uint32_t kmin, uint32_t len, uint32_t rlen, uint32_t L) {
@@ -293,9 +294,13 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
            uint32_t row_words, uint64_t n_reads_arg, const uint32_t* __restrict__ in_list,
            const unsigned long long* __restrict__ in_count, ReadSlot* __restrict__ slots,
            uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters) {
-    // in_list != nullptr: process reads in_list[0 .. *in_count) (the reads k_map_first deferred)
+    // in_list != nullptr: process reads in_list[0 .. *in_count) (the reads k_map_first deferred).
+    // Those reads are few and each is a long serial chain (passes, range probes), so the kernel
+    // is latency-bound: in list mode only every LIST_SPREAD-th thread takes a read, which spreads
+    // them over LIST_SPREAD times more warps.
+    const uint32_t spread = in_list ? LIST_SPREAD : 1u;
     const uint64_t n_reads = in_list ? *in_count : n_reads_arg;
-    if ((uint64_t)blockIdx.x * MF_THREADS >= n_reads) return;
+    if ((uint64_t)blockIdx.x * (MF_THREADS / spread) >= n_reads) return;
     constexpr uint32_t CAP = (STRIDE - 3) * 16;                   // bases per packed row
     constexpr uint32_t GROUPS = 32 / LPR;                          // reads packed per warp step
     __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
@@ -305,16 +310,16 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     __shared__ uint32_t s_len[MF_THREADS];                         // rlen | flags << 24
     constexpr uint32_t F_N = 1u << 24, F_BAD = 2u << 24, F_LONG = 4u << 24, F_NONE = 8u << 24;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t r0 = (uint64_t)blockIdx.x * MF_THREADS;
+    const uint64_t r0 = (uint64_t)blockIdx.x * (MF_THREADS / spread);
     const uint32_t L = ix.split_len;
 
     if (PACKED) {
         // ---- phase 1 (packed rows): each thread loads its own row + builds the reverse complement
         const uint32_t t = threadIdx.x;
-        const bool live = r0 + t < n_reads;
+        const bool live = (t % spread) == 0 && r0 + t / spread < n_reads;
         uint32_t lfv = F_NONE;
         if (live) {
-            const uint64_t r = in_list ? (uint64_t)in_list[r0 + t] : r0 + t;
+            const uint64_t r = in_list ? (uint64_t)in_list[r0 + t / spread] : r0 + t;
             const uint32_t h = __ldg(hdr + r);
             if (h & PH_LONG) lfv = F_LONG;
             else {
@@ -332,7 +337,7 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
         for (uint32_t k = 0; k < 32 / GROUPS; k++) {
             const uint32_t t = wib * 32 + k * GROUPS + grp;
             const bool live = r0 + t < n_reads;
-            const uint64_t r = !live ? 0 : in_list ? (uint64_t)in_list[r0 + t] : r0 + t;
+            const uint64_t r = r0 + t;                       // (raw-byte mode is never list driven)
             uint32_t* row = s_fwd + t * STRIDE;
             uint32_t* rrow = s_rc + t * STRIDE;
             uint64_t s = 0, len64 = 0;
@@ -413,7 +418,7 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     // ---- phase 2: one thread per read, passes A and B ---------------------------------------
     const uint32_t t = threadIdx.x;
     uint32_t lf = s_len[t];
-    const uint64_t r = (lf & F_NONE) ? 0 : in_list ? (uint64_t)in_list[r0 + t] : r0 + t;
+    const uint64_t r = (lf & F_NONE) ? 0 : in_list ? (uint64_t)in_list[r0 + t / spread] : r0 + t;
     const uint32_t rlen = lf & 0xFFFFFF;
     const uint32_t* row = s_fwd + t * STRIDE;
     uint32_t nn = 0;
@@ -643,6 +648,172 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_map_second: the reads k_map_first deferred, one thread per read, still one walk -- but ONE
+// mismatching base is tolerated.  The windows covering it equal text windows except for that base,
+// so a clear substitution-hit bit in every strand that holds such windows proves that they all miss
+// (exactly what the reference's look-ups would find); they are simply not counted.  If window 0
+// does not seed (error in the first split_len bases) the same walk runs on the reverse complement
+// from the other end.  A second mismatch, a set bit, a repeat or a missing successor sends the read
+// on to k_map_fast.
+// ---------------------------------------------------------------------------------------------
+template <int STRIDE>
+__global__ void __launch_bounds__(MF_THREADS)
+k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
+             const uint32_t* __restrict__ in_list, const unsigned long long* __restrict__ in_count,
+             ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list, unsigned long long* __restrict__ out_count) {
+    __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
+    const uint64_t n_items = *in_count;
+    const uint64_t item = (uint64_t)blockIdx.x * MF_THREADS + threadIdx.x;
+    if ((uint64_t)blockIdx.x * MF_THREADS >= n_items) return;
+    if (item >= n_items) return;
+    const uint32_t t = threadIdx.x, L = ix.split_len;
+    const uint32_t r = in_list[item];
+    const uint32_t h = __ldg(hdr + r);
+    bool defer = (h & (PH_LONG | PH_BAD)) != 0 || ix.subst == nullptr;
+    const uint32_t rlen = h & 0xFFFFFF;
+    uint32_t* row = s_fwd + t * STRIDE;
+    uint32_t nn = 0;
+    uint32_t l_node[MAXN], l_vk[MAXN];
+    if (!defer) {
+        load_row<STRIDE, false>(rows, r, row_words, rlen, row, nullptr);
+        const int npos = (int)(rlen - L + 1);
+        bool resolved = false;
+        for (int attempt = 0; attempt < 2 && !resolved; attempt++) {
+            const bool mirror = attempt == 1;
+            if (mirror) {
+                // reverse-complement the packed row in place
+                constexpr int NW = STRIDE - 3;
+                const uint32_t nwords = (rlen + 15) >> 4, pad = 16 * nwords - rlen;
+                uint32_t y[NW];
+                uint32_t prev = 0;
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    y[k] = 0;
+                    const int kk = NW - 1 - k;
+                    if ((uint32_t)kk >= nwords) continue;
+                    uint32_t rv = __brev(row[kk]);
+                    rv = (((rv & 0x55555555u) << 1) | ((rv >> 1) & 0x55555555u)) ^ 0xAAAAAAAAu;
+                    const int j = (int)nwords - 1 - kk;
+                    if (j > 0) y[j - 1] = __funnelshift_r(prev, rv, 2 * pad);
+                    prev = rv;
+                }
+                if (nwords) y[nwords - 1] = __funnelshift_r(prev, 0u, 2 * pad);
+#pragma unroll
+                for (int k = 0; k < NW; k++) row[k] = y[k];
+            }
+            nn = 0;
+            uint32_t tp = NONE32, node = 0;
+            const int pr = probe_window(ix, row, 0, tp, node);
+            if (pr == PROBE_MULTI) break;
+            if (pr == PROBE_MISS) continue;                      // error in this end's first window: try the other end
+            bool ok = true, err = false;
+            int e = 0;
+            uint32_t rb = 0;
+            uint32_t i0 = 0, p = L;
+            while (ok) {
+                const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
+                const bool rcs = tp >= s1;
+                const uint32_t q = 2 * node + (rcs ? 1u : 0u);
+                const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
+                const int delta = (int)tp - (int)i0;
+                const uint32_t lim = min(rlen, (uint32_t)((int)send - delta));   // read position where the strand ends
+                // a strand entered after the error still holds windows covering it if it starts at or before e
+                if (err && (int)i0 <= e) {
+                    const uint32_t te = (uint32_t)(e + delta);
+                    if ((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u) { ok = false; break; }
+                }
+                while (p < lim) {
+                    const uint32_t n = min(32u, lim - p);
+                    uint64_t x = read64(row, p) ^ extract64(ix.text, (uint64_t)((int)p + delta));
+                    if (n < 32) x &= (1ull << (2 * n)) - 1;
+                    if (x) {
+                        const uint32_t off = (uint32_t)(__ffsll((long long)x) - 1) >> 1;
+                        if (err || (x & ~(3ull << (2 * off)))) { ok = false; break; }   // second mismatch
+                        err = true;
+                        e = (int)(p + off);
+                        rb = (row[(uint32_t)e >> 4] >> (((uint32_t)e & 15) * 2)) & 3u;
+                        const uint32_t te = (uint32_t)(e + delta);
+                        if ((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u) { ok = false; break; }
+                    }
+                    const uint32_t u = (uint32_t)((int)p + delta) - L + 1;     // text position of the first window ending here
+                    const uint32_t ub = __funnelshift_r(__ldg(ix.uniq + (u >> 5)), __ldg(ix.uniq + (u >> 5) + 1), u & 31);
+                    const uint32_t m32 = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
+                    if ((ub & m32) != m32) { ok = false; break; }
+                    p += n;
+                }
+                if (!ok) break;
+                // windows [a, bw] of this node are resolved; those covering e are proven misses
+                const int a = (int)i0, bw = (int)lim - (int)L;
+                int c1 = bw - a + 1, c2 = 0, last_hit = bw, first_hit = a;
+                if (err) {
+                    c1 = min(bw, e - (int)L) - a + 1;
+                    if (c1 < 0) c1 = 0;
+                    const int a2 = max(a, e + 1);
+                    c2 = bw - a2 + 1;
+                    if (c2 < 0) c2 = 0;
+                    first_hit = c1 > 0 ? a : a2;
+                    last_hit = c2 > 0 ? bw : min(bw, e - (int)L);
+                }
+                if (c1 + c2 > 0) {
+                    if (nn == MAXN) { ok = false; break; }
+                    l_node[nn] = node;
+                    l_vk[nn] = (uint32_t)(c1 + c2) | ((uint32_t)(mirror ? npos - 1 - last_hit : first_hit) << 16);
+                    nn++;
+                }
+                if (lim >= rlen) break;
+                // the strand ended before the read: successor window for the read's next base
+                const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
+                const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
+                if (sc.x == NONE32) { ok = false; break; }
+                i0 = lim - L + 1;
+                tp = sc.x;
+                node = sc.y;
+                p = lim + 1;
+            }
+            if (!ok) break;                                      // a real complication: the full kernel decides
+            resolved = true;
+        }
+        if (!resolved) defer = true;
+    }
+    ReadSlot* out = slots + r;
+    uint32_t n_out = 0;
+    if (!defer) {
+        // a node met in two stretches (cyclic graph): sum the hits, keep the smallest position
+        for (uint32_t a = 1; a < nn; a++) {
+            for (uint32_t b = 0; b < a; b++) {
+                if (l_node[b] == l_node[a] && l_vk[b]) {
+                    const uint32_t x = l_vk[b], y = l_vk[a];
+                    l_vk[b] = ((x & 0xFFFF) + (y & 0xFFFF)) | (min(x >> 16, y >> 16) << 16);
+                    l_vk[a] = 0;
+                    break;
+                }
+            }
+        }
+        // keep flags, then ascending node order by ranks
+        uint32_t keepmask = 0;
+        for (uint32_t a = 0; a < nn; a++) {
+            const uint32_t vk = l_vk[a];
+            if (vk && keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + l_node[a]), rlen, L)) keepmask |= 1u << a;
+        }
+        n_out = __popc(keepmask);
+        if (n_out > (uint32_t)SLOT_IDS) defer = true;
+        if (!defer) {
+            for (uint32_t a = 0; a < nn; a++) {
+                if (!((keepmask >> a) & 1)) continue;
+                uint32_t rank = 0;
+                for (uint32_t b = 0; b < nn; b++) rank += ((keepmask >> b) & 1) && l_node[b] < l_node[a];
+                out->ids[rank] = l_node[a];
+            }
+        }
+    }
+    if (defer) {
+        out_list[atomicAdd(out_count, 1ull)] = r;
+        return;
+    }
+    out->hdr = ST_OK | (n_out << 8);
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_map_windows: the reads k_map_first deferred (sequencing errors, repeats, many nodes).
 // One warp per read, one lane per window, every window looked up -- the reference's algorithm
 // (PE_Inference.py:24-31) with no shortcuts, so every postings multiplicity is exact.  All lanes
@@ -761,8 +932,9 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     const uint32_t* to_generic = c->worklist.p;                 // reads the ASCII tier must map
     const unsigned long long* to_generic_n = c->counters.p + CNT_WORK;
     if (d_rows) {
-        VSPE_TRY(c->defer_list.reserve(2 * n_reads));
+        VSPE_TRY(c->defer_list.reserve(3 * n_reads));
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER, 0, 8, c->stream));
+        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER2, 0, 8, c->stream));
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK2, 0, 8, c->stream));
     }
     if (d_rows && !c->opt_single_map) {
@@ -774,9 +946,21 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
         VSPE_LAUNCH_CHECK(c);
         in_list = c->defer_list.p;
         in_count = c->counters.p + CNT_DEFER;
+        if (c->index.has_subst && !c->opt_no_second) {
+            // stage 1b: one-error-tolerant walk on the deferred reads; its leftovers go to stage 2
+            uint32_t* list1b = c->defer_list.p + 2 * n_reads;
+#define VSPE_M2(S) k_map_second<S><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->defer_list.p, \
+                                                                 c->counters.p + CNT_DEFER, d_slots, list1b, c->counters.p + CNT_DEFER2)
+            if (cap <= 160) VSPE_M2(13); else if (cap <= 256) VSPE_M2(19); else VSPE_M2(23);
+#undef VSPE_M2
+            VSPE_LAUNCH_CHECK(c);
+            in_list = list1b;
+            in_count = c->counters.p + CNT_DEFER2;
+        }
     }
     // stage 2: the full seed-and-extend kernel (on the deferred reads, or on everything)
-#define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
+    const uint32_t grid2 = in_list ? (uint32_t)std::min<uint64_t>((n_reads * LIST_SPREAD + MF_THREADS - 1) / MF_THREADS, 0x7FFFFFFFull) : grid;
+#define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid2, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
                                                                                row_words, n_reads, in_list, in_count, d_slots, \
                                                                                c->worklist.p, c->counters.p)
     if (d_rows) {
