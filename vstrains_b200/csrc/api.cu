@@ -870,6 +870,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     }
     else if (!strcmp(name, "single_map")) c->opt_single_map = value;
     else if (!strcmp(name, "full_second")) c->opt_no_second = value;
+    else if (!strcmp(name, "list_spread")) c->opt_list_spread = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value;
     else if (!strcmp(name, "dbg_dump")) {

@@ -37,7 +37,6 @@
 namespace vspe {
 
 static constexpr int MF_THREADS = 128;
-static constexpr uint32_t LIST_SPREAD = 4;
 static constexpr int MAXN = 16;
 
 __device__ __forceinline__ bool keep_node_f(uint32_t v, uint32_t kmin, uint32_t len, uint32_t rlen, uint32_t L) {
@@ -292,13 +291,13 @@ __global__ void __launch_bounds__(MF_THREADS)
 k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
            const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr,
            uint32_t row_words, uint64_t n_reads_arg, const uint32_t* __restrict__ in_list,
-           const unsigned long long* __restrict__ in_count, ReadSlot* __restrict__ slots,
+           const unsigned long long* __restrict__ in_count, uint32_t list_spread, ReadSlot* __restrict__ slots,
            uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters) {
     // in_list != nullptr: process reads in_list[0 .. *in_count) (the reads k_map_first deferred).
     // Those reads are few and each is a long serial chain (passes, range probes), so the kernel
     // is latency-bound: in list mode only every LIST_SPREAD-th thread takes a read, which spreads
     // them over LIST_SPREAD times more warps.
-    const uint32_t spread = in_list ? LIST_SPREAD : 1u;
+    const uint32_t spread = in_list ? list_spread : 1u;
     const uint64_t n_reads = in_list ? *in_count : n_reads_arg;
     if ((uint64_t)blockIdx.x * (MF_THREADS / spread) >= n_reads) return;
     constexpr uint32_t CAP = (STRIDE - 3) * 16;                   // bases per packed row
@@ -959,9 +958,10 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
         }
     }
     // stage 2: the full seed-and-extend kernel (on the deferred reads, or on everything)
-    const uint32_t grid2 = in_list ? (uint32_t)std::min<uint64_t>((n_reads * LIST_SPREAD + MF_THREADS - 1) / MF_THREADS, 0x7FFFFFFFull) : grid;
+    const uint32_t list_spread = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(32, c->opt_list_spread));
+    const uint32_t grid2 = in_list ? (uint32_t)std::min<uint64_t>((n_reads * list_spread + MF_THREADS - 1) / MF_THREADS, 0x7FFFFFFFull) : grid;
 #define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid2, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
-                                                                               row_words, n_reads, in_list, in_count, d_slots, \
+                                                                               row_words, n_reads, in_list, in_count, list_spread, d_slots, \
                                                                                c->worklist.p, c->counters.p)
     if (d_rows) {
         if (cap <= 160) VSPE_MF(13, 16, true); else if (cap <= 256) VSPE_MF(19, 16, true); else VSPE_MF(23, 32, true);
