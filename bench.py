@@ -211,6 +211,9 @@ def main():
 
     import torch
     import torch.distributed as dist
+    if not os.path.exists(os.path.join(ROOT, "vstrains_b200", "libvspe.so")) and local_rank == 0:
+        import __graft_entry__                     # clean checkout: compile the CUDA library first
+        __graft_entry__.build()
     from vstrains_b200 import pe_inference
 
     if not torch.cuda.is_available():
