@@ -211,9 +211,16 @@ def main():
 
     import torch
     import torch.distributed as dist
-    if not os.path.exists(os.path.join(ROOT, "vstrains_b200", "libvspe.so")) and local_rank == 0:
-        import __graft_entry__                     # clean checkout: compile the CUDA library first
-        __graft_entry__.build()
+    lib_path = os.path.join(ROOT, "vstrains_b200", "libvspe.so")
+    if not os.path.exists(lib_path):               # clean checkout: compile the CUDA library first
+        if local_rank == 0:
+            import __graft_entry__
+            __graft_entry__.build()
+        else:
+            t_wait = time.time()
+            while not os.path.exists(lib_path) and time.time() - t_wait < 600:
+                time.sleep(1.0)
+            time.sleep(2.0)
     from vstrains_b200 import pe_inference
 
     if not torch.cuda.is_available():
