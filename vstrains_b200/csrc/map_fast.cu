@@ -495,26 +495,24 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     }
     uint32_t n_out = 0;
     if (!bail) {
-        // sort by node index (ascending, as enumerate(nodes) does) and apply the predicate
-        for (uint32_t a = 1; a < nn; a++) {
-            const uint32_t kn = s_node[a][t], kv = s_vk[a][t];
-            int b = (int)a - 1;
-            while (b >= 0 && s_node[b][t] > kn) {
-                s_node[b + 1][t] = s_node[b][t];
-                s_vk[b + 1][t] = s_vk[b][t];
-                b--;
-            }
-            s_node[b + 1][t] = kn;
-            s_vk[b + 1][t] = kv;
-        }
+        // saturation predicate per node, then ascending node order (as enumerate(nodes) gives) from
+        // ranks instead of a data-dependent sort
+        uint32_t keepmask = 0;
         for (uint32_t a = 0; a < nn; a++) {
-            const uint32_t node = s_node[a][t], vk = s_vk[a][t];
-            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) {
-                if (n_out < (uint32_t)SLOT_IDS) out->ids[n_out] = node;
-                n_out++;
+            const uint32_t vk = s_vk[a][t];
+            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + s_node[a][t]), rlen, L)) keepmask |= 1u << a;
+        }
+        n_out = __popc(keepmask);
+        if (n_out > (uint32_t)SLOT_IDS) bail = true;           // 16 kept nodes do not fit the slot
+        else {
+            for (uint32_t a = 0; a < nn; a++) {
+                if (!((keepmask >> a) & 1)) continue;
+                const uint32_t node = s_node[a][t];
+                uint32_t rank = 0;
+                for (uint32_t b = 0; b < nn; b++) rank += ((keepmask >> b) & 1) && s_node[b][t] < node;
+                out->ids[rank] = node;
             }
         }
-        if (n_out > (uint32_t)SLOT_IDS) bail = true;           // 16 kept nodes do not fit the slot
     }
     if (bail) {
         const unsigned long long idx = atomicAdd(&counters[CNT_WORK], 1ull);
@@ -618,25 +616,25 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
     }
     uint32_t n_out = 0;
     if (!defer) {
-        for (uint32_t a = 1; a < nn; a++) {
-            const uint32_t kn = l_node[a], kv = l_vk[a];
-            int b = (int)a - 1;
-            while (b >= 0 && l_node[b] > kn) {
-                l_node[b + 1] = l_node[b];
-                l_vk[b + 1] = l_vk[b];
-                b--;
-            }
-            l_node[b + 1] = kn;
-            l_vk[b + 1] = kv;
-        }
+        // saturation predicate per node, then ascending node order from ranks (no data-dependent sort
+        // loops: most reads have one or two nodes)
+        uint32_t keepmask = 0;
         for (uint32_t a = 0; a < nn; a++) {
-            const uint32_t node = l_node[a], vk = l_vk[a];
-            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) {
-                if (n_out < (uint32_t)SLOT_IDS) out->ids[n_out] = node;
-                n_out++;
+            const uint32_t vk = l_vk[a];
+            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + l_node[a]), rlen, L)) keepmask |= 1u << a;
+        }
+        n_out = __popc(keepmask);
+        if (n_out > (uint32_t)SLOT_IDS) defer = true;
+        else if (n_out == 1) out->ids[0] = l_node[__ffs((int)keepmask) - 1];
+        else if (n_out > 1) {
+            for (uint32_t a = 0; a < nn; a++) {
+                if (!((keepmask >> a) & 1)) continue;
+                const uint32_t node = l_node[a];
+                uint32_t rank = 0;
+                for (uint32_t b = 0; b < nn; b++) rank += ((keepmask >> b) & 1) && l_node[b] < node;
+                out->ids[rank] = node;
             }
         }
-        if (n_out > (uint32_t)SLOT_IDS) defer = true;
     }
     if (defer) {
         const unsigned long long idx = atomicAdd(&counters[CNT_DEFER], 1ull);
