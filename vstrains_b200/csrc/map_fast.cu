@@ -589,20 +589,11 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
                 p += n;
             }
             if (defer) break;
-            {
-                // same node again (cyclic graph): sum the hits, keep the smallest position
-                const uint32_t hits = lim - L + 1 - i0;
-                uint32_t a = 0;
-                for (; a < nn; a++) if (l_node[a] == node) break;
-                if (a == nn) {
-                    if (nn == MAXN) { defer = true; break; }
-                    l_node[a] = node;
-                    l_vk[a] = hits | (i0 << 16);
-                    nn++;
-                } else {
-                    l_vk[a] += hits;
-                }
-            }
+            // append the stretch; a node met twice (cyclic graph) is detected at the end and deferred
+            if (nn == MAXN) { defer = true; break; }
+            l_node[nn] = node;
+            l_vk[nn] = (lim - L + 1 - i0) | (i0 << 16);
+            nn++;
             if (lim >= rlen) break;
             // the strand ended before the read: successor window for the read's next base
             const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
@@ -620,12 +611,14 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
         // loops: most reads have one or two nodes)
         uint32_t keepmask = 0;
         for (uint32_t a = 0; a < nn; a++) {
-            const uint32_t vk = l_vk[a];
-            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + l_node[a]), rlen, L)) keepmask |= 1u << a;
+            const uint32_t vk = l_vk[a], node = l_node[a];
+            for (uint32_t b = 0; b < a; b++) defer |= l_node[b] == node;      // needs merging: full kernel
+            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) keepmask |= 1u << a;
         }
         n_out = __popc(keepmask);
         if (n_out > (uint32_t)SLOT_IDS) defer = true;
-        else if (n_out == 1) out->ids[0] = l_node[__ffs((int)keepmask) - 1];
+        if (defer) n_out = 0;
+        if (n_out == 1) out->ids[0] = l_node[__ffs((int)keepmask) - 1];
         else if (n_out > 1) {
             for (uint32_t a = 0; a < nn; a++) {
                 if (!((keepmask >> a) & 1)) continue;
