@@ -60,7 +60,8 @@ __device__ __forceinline__ uint32_t pair_class(uint32_t hf, uint32_t hr) {
 __global__ void __launch_bounds__(PAIR_THREADS)
 k_pair_count(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uint64_t n_pairs, uint64_t N,
              const uint32_t* __restrict__ spill, uint32_t low_bits, uint32_t n_buckets,
-             unsigned long long* __restrict__ g_hist, unsigned long long* __restrict__ counters) {
+             unsigned long long* __restrict__ g_hist, unsigned long long* __restrict__ counters,
+             uint32_t* __restrict__ blk_hist) {
     extern __shared__ uint32_t s_hist[];
     __shared__ unsigned long long s_cnt[4];
     for (uint32_t b = threadIdx.x; b < n_buckets; b += PAIR_THREADS) s_hist[b] = 0;
@@ -83,6 +84,7 @@ k_pair_count(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uin
     for (uint32_t b = threadIdx.x; b < n_buckets; b += PAIR_THREADS) {
         uint32_t c = s_hist[b];
         if (c) atomicAdd(&g_hist[b], (unsigned long long)c);
+        if (blk_hist) blk_hist[(uint64_t)blockIdx.x * n_buckets + b] = c;     // k_pair_emit reuses it
     }
     if (threadIdx.x == 0) {
         if (s_cnt[0]) atomicAdd(&counters[CNT_USED], s_cnt[0]);
@@ -128,11 +130,13 @@ k_bucket_scan(const unsigned long long* __restrict__ hist, uint32_t n, unsigned 
 __global__ void __launch_bounds__(PAIR_THREADS)
 k_pair_emit(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uint64_t n_pairs, uint64_t N,
             const uint32_t* __restrict__ spill, uint32_t low_bits, uint32_t n_buckets,
-            unsigned long long* __restrict__ g_cursor, uint32_t* __restrict__ keys) {
+            unsigned long long* __restrict__ g_cursor, uint32_t* __restrict__ keys, const uint32_t* __restrict__ blk_hist) {
     extern __shared__ unsigned long long s_mem[];
     unsigned long long* s_base = s_mem;                              // [n_buckets]
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_mem + n_buckets);   // [n_buckets]
-    for (uint32_t b = threadIdx.x; b < n_buckets; b += PAIR_THREADS) s_hist[b] = 0;
+    // this block's keys per bucket: stored by k_pair_count (same block -> pairs mapping), or recounted
+    for (uint32_t b = threadIdx.x; b < n_buckets; b += PAIR_THREADS)
+        s_hist[b] = blk_hist ? __ldg(blk_hist + (uint64_t)blockIdx.x * n_buckets + b) : 0u;
     __syncthreads();
     uint64_t p = (uint64_t)blockIdx.x * PAIR_THREADS + threadIdx.x;
     bool used = p < n_pairs && pair_class(f[p].hdr, r[p].hdr) == 0;
@@ -140,7 +144,7 @@ k_pair_emit(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uint
     if (used) {
         l = list_of(f + p, spill);
         rr = list_of(r + p, spill);
-        for_each_key(l, rr, N, [&](uint64_t key) { atomicAdd(&s_hist[key >> low_bits], 1u); });
+        if (!blk_hist) for_each_key(l, rr, N, [&](uint64_t key) { atomicAdd(&s_hist[key >> low_bits], 1u); });
     }
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < n_buckets; b += PAIR_THREADS) {
@@ -205,8 +209,14 @@ int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total
         uint32_t grid = (uint32_t)((n + PAIR_THREADS - 1) / PAIR_THREADS);
         unsigned long long h_keys = 0, h_err = 0;
         VSPE_CUDA(cudaMemsetAsync(g_hist, 0, (n_buckets + 1) * 8, st));
+        // per-block histograms are kept for the emit kernel when they fit a modest scratch
+        uint32_t* blk_hist = nullptr;
+        if ((uint64_t)grid * n_buckets * 4 <= (256ull << 20)) {
+            VSPE_TRY(c->blk_hist.reserve((uint64_t)grid * n_buckets));
+            blk_hist = c->blk_hist.p;
+        }
         k_pair_count<<<grid, PAIR_THREADS, n_buckets * 4, st>>>(d_f + off, d_r + off, n, N, c->spill.p, low_bits, n_buckets,
-                                                                g_hist, c->counters.p);
+                                                                g_hist, c->counters.p, blk_hist);
         VSPE_LAUNCH_CHECK(c);
         // one D2H + sync per batch: the cumulative key counter and the kernels' error flags
         VSPE_CUDA(cudaMemcpyAsync(&h_keys, c->counters.p + CNT_KEYS, 8, cudaMemcpyDeviceToHost, st));
@@ -222,7 +232,7 @@ int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total
         k_bucket_scan<<<1, 1024, 0, st>>>(g_hist, n_buckets, g_start, g_cursor);
         VSPE_LAUNCH_CHECK(c);
         k_pair_emit<<<grid, PAIR_THREADS, n_buckets * 12, st>>>(d_f + off, d_r + off, n, N, c->spill.p, low_bits, n_buckets,
-                                                                g_cursor, c->keys.p);
+                                                                g_cursor, c->keys.p, blk_hist);
         VSPE_LAUNCH_CHECK(c);
         k_bucket_hist<<<n_buckets, 512, (1u << low_bits) * 4, st>>>(c->keys.p, g_start, low_bits, cells, c->mats.p);
         VSPE_LAUNCH_CHECK(c);

@@ -59,6 +59,7 @@ struct Ctx {
     DevBuf<uint32_t> keys;
     DevBuf<unsigned long long> bucket;   // [3][n_buckets + 1]: histogram, start, cursor
     DevBuf<unsigned long long> block_sums;
+    DevBuf<uint32_t> blk_hist;           // [blocks][n_buckets] per-block key histograms (count -> emit)
     bool count_attr_set = false;
     uint64_t keys_seen = 0;            // host copy of CNT_KEYS after the last count batch
     unsigned long long last_err_flags = 0;
