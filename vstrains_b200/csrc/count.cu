@@ -162,7 +162,7 @@ k_pair_emit(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uint
     }
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 k_bucket_hist(const uint32_t* __restrict__ keys, const unsigned long long* __restrict__ start, uint32_t low_bits,
               uint64_t n_cells, uint64_t* __restrict__ mats) {
     extern __shared__ uint32_t s_bins[];
@@ -171,7 +171,19 @@ k_bucket_hist(const uint32_t* __restrict__ keys, const unsigned long long* __res
     if (s == e) return;
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) s_bins[i] = 0;
     __syncthreads();
-    for (unsigned long long i = s + threadIdx.x; i < e; i += blockDim.x) atomicAdd(&s_bins[__ldg(keys + i) & mask], 1u);
+    // four independent loads per thread and step: the loop is latency-bound otherwise
+    for (unsigned long long i0 = s; i0 < e; i0 += 4ull * blockDim.x) {
+        uint32_t k[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned long long i = i0 + (unsigned long long)u * blockDim.x + threadIdx.x;
+            ok[u] = i < e;
+            k[u] = ok[u] ? __ldg(keys + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (ok[u]) atomicAdd(&s_bins[k[u] & mask], 1u);
+    }
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x << low_bits;
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
@@ -234,7 +246,7 @@ int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total
         k_pair_emit<<<grid, PAIR_THREADS, n_buckets * 12, st>>>(d_f + off, d_r + off, n, N, c->spill.p, low_bits, n_buckets,
                                                                 g_cursor, c->keys.p, blk_hist);
         VSPE_LAUNCH_CHECK(c);
-        k_bucket_hist<<<n_buckets, 512, (1u << low_bits) * 4, st>>>(c->keys.p, g_start, low_bits, cells, c->mats.p);
+        k_bucket_hist<<<n_buckets, 256, (1u << low_bits) * 4, st>>>(c->keys.p, g_start, low_bits, cells, c->mats.p);
         VSPE_LAUNCH_CHECK(c);
     }
     return VSPE_OK;
