@@ -57,6 +57,8 @@ typedef struct vspe_stats {
     float ms_total;           /* device time of the last vspe_count_* call                  */
     float ms_k_scan_pack;     /* sum of k_scan_pack launch durations (CUDA events on its stream) */
     uint32_t n_k_scan_pack;   /* ... and how many launches that was                         */
+    float ms_k_scan_count;    /* same for the terminator-count pass (two-kernel scan)       */
+    uint32_t n_k_scan_count;
 } vspe_stats;
 
 typedef struct vspe_ctx vspe_ctx;

@@ -22,7 +22,7 @@ def _info(ids, mat, tmp_path, name):
         return f.read()
 
 
-@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0), (0, 0, 2)])
+@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0), (0, 0, 2), (0, 3, 1)])
 def test_golden_fixtures_bit_exact(golden, tmp_path, force_generic, scan_mode, subst):
     if golden.status != 0:
         with pytest.raises(VspeError) as ei:
@@ -107,7 +107,7 @@ def test_per_read_mapping_matches_oracle(golden, force_generic, scan_mode):
 
 
 @pytest.mark.parametrize("name,pairs", [("C1", 6000), ("C2", 6000), ("C3", 4000), ("C4", 3000)])
-@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0), (0, 0, 2)])
+@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0), (0, 0, 2), (0, 3, 1)])
 def test_synthetic_configs_match_c_oracle(name, pairs, force_generic, scan_mode, subst):
     cfg = synth.CONFIGS[name]
     g, f, r = synth.generate(cfg, pairs=pairs)
@@ -126,7 +126,7 @@ def test_chunked_streaming_equals_single_chunk():
     g, f, r = synth.generate(cfg, pairs=9000)
     ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())
     res = []
-    for chunk_mb, two_pass, scan_mode in ((256, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0)):
+    for chunk_mb, two_pass, scan_mode in ((256, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 0, 3)):
         with pe_inference.PEIndex(seqs, cfg.k) as ix:
             ix.set_option("chunk_mb", chunk_mb)
             ix.set_option("scan_two_pass", two_pass)
@@ -224,7 +224,7 @@ def _mk_fastq(seqs, nl=b"\n"):
     return b"".join(b"@r" + nl + s + nl + b"+" + nl + b"I" * len(s) + nl for s in seqs)
 
 
-@pytest.mark.parametrize("scan_mode", [0, 1])
+@pytest.mark.parametrize("scan_mode", [0, 1, 3])
 def test_whole_path_edge_shapes(scan_mode):
     """Shapes that stress the tiled scan: thousands of tiny records per tile (fallback path),
     reads longer than the packed rows / the scan margin, CRLF and lone-CR files, reads that

@@ -77,11 +77,28 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     const uint32_t row_words = cap <= 160 ? 12 : cap <= 256 ? 16 : 20;
     int mode = (int)c->opt_scan_mode;
     if (c->opt_scan_two_pass) mode = 2;
-    if (c->opt_force_generic || c->index.split_len > 320) mode = std::max(mode, 1);
+    if ((c->opt_force_generic || c->index.split_len > 320) && (mode == 0 || mode == 3)) mode = 1;
     bool packed = false;
     if (mode == 0) {
-        // fused TMA scan + pack with a guessed table size (from the read length of the first
-        // records); if a tile owns too many records or the guess was too small, fall through
+        // count pass (terminator masks, no inter-tile dependency) + device scan, then the pack
+        // pass with exactly sized outputs
+        unsigned long long flags = 0;
+        VSPE_TRY(scan_pack_prepare(c, d_buf, n, &n_terms, &flags));
+        if (flags & ERRF_TILE_FULL) {
+            mode = 1;                                   // a warp row with too many candidates: plain path
+        } else {
+            n_seq = seq_lines_before(lb + n_terms) - rec_first;
+            VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
+            VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
+            VSPE_TRY(mb.rec.hdr.reserve(n_seq + 2));
+            VSPE_TRY(mb.rec.rows.reserve((n_seq + 2) * row_words));
+            VSPE_TRY(scan_pack_finish(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p,
+                                      mb.rec.hdr.p, row_words, cap));
+            packed = true;
+        }
+    } else if (mode == 3) {
+        // fused single pass with look-back and a guessed table size (from the read length of the
+        // first records); if a tile owns too many records or the guess was too small, fall through
         uint64_t guess = n / (2ull * std::max<uint32_t>(c->read_len_hint, 20) + 8) * 21 / 20 + 4096;
         unsigned long long flags = 0;
         VSPE_TRY(mb.rec.seq_start.reserve(guess + 2));
@@ -138,6 +155,7 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     if (sync_after) {
         // streaming callers reuse the chunk buffer next: wait, and account the stage times now
         VSPE_CUDA(cudaStreamSynchronize(c->stream));
+        scan_pack_account(c);
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, e0, e1);
         cudaEventElapsedTime(&b, e1, e2);
@@ -497,6 +515,7 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
     float ms_total = 0;
     cudaEventElapsedTime(&ms_total, t0, t1);
     c->stats.ms_total = ms_total;
+    scan_pack_account(c);
     for (int m = 0; m < 2; m++) {
         if (!ns[m]) continue;
         float a = 0, b = 0;

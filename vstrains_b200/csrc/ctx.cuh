@@ -39,7 +39,9 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_k[2] = {};
+    cudaEvent_t ev_k[4] = {};
+    bool scan_pack_pending = false;
+    DevBuf<uint8_t> scan_q;           // two-kernel scan: per (tile, warp) candidate queues
     Index index;
     DevBuf<uint64_t> mats;            // [2][N][N] node_mat then short_mat (dense mode)
     Sparse sparse;                    // sorted (key, count) runs (sparse mode)
@@ -86,7 +88,8 @@ struct Ctx {
     uint64_t dbg_tiles = 0;
     int64_t opt_scan_two_pass = 0;     // K1 as count + index passes (cross-check of the look-back kernel)
     uint64_t cur_buf_n = 0;            // bytes of the chunk being mapped (exhaustive tier bound)
-    int64_t opt_scan_mode = 0;         // 0: fused TMA scan+pack, 1: look-back scan + raw-byte map, 2: two-pass scan
+    int64_t opt_scan_mode = 0;         // 0: TMA count pass + pack pass, 3: fused TMA scan+pack with look-back,
+                                       // 1: look-back scan + raw-byte map, 2: two-pass scan
     uint32_t read_len_hint = 320;      // longest sequence line among the first records of the input
     // accounting
     vspe_stats stats = {};

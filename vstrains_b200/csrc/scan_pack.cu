@@ -26,6 +26,7 @@ static constexpr int SP_FRONT = 16;                              // bytes kept b
 static constexpr int SP_BACK = 512;                              // bytes kept after the tile (>= longest packed read + 1)
 static constexpr int SP_MAXREC = 576;                            // reads a tile may own (else fallback path)
 static constexpr int SP_QCAP = 96;                               // per warp: vectors that may hold a terminator
+static constexpr uint32_t SP_QBYTES = (4 + SP_QCAP * 6 + 15) / 16 * 16;   // header word + masks (u32) + vector ids (u16)
 static constexpr uint32_t SP_SMEM = SP_FRONT + SP_TILE + SP_BACK + SP_MAXREC * 8 + SP_WARPS * SP_QCAP * 8 + 64;
 
 #define LB_AGG (1ull << 62)
@@ -76,6 +77,9 @@ struct ScanPackArgs {
     uint32_t n_tiles;
     unsigned long long* counters;
     unsigned long long* dbg;         // optional [n_tiles][8] globaltimer stamps (profiling aid)
+    uint8_t* qbuf;                   // two-kernel mode: per (tile, warp) candidate queue, SP_QBYTES each
+    unsigned long long* tile_tot;    // two-kernel mode: terminators per tile (count pass) ...
+    const unsigned long long* tile_excl;   // ... and their exclusive prefix (pack pass)
 };
 
 
@@ -86,6 +90,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define SP_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[(size_t)tile * 8 + (k)] = gtime(); } while (0)
 
+// MODE 0: fused single pass with decoupled look-back.
+// MODE 1: count pass of the two-kernel variant -- TMA + terminator masks only; saves each warp's
+//         candidate queue and the tile's terminator count, so no tile ever waits on another.
+// MODE 2: pack pass -- TMA + saved masks + scanned tile prefix -> read table -> 2-bit rows.
+template <int MODE>
 __global__ void __launch_bounds__(SP_WARPS * 32)
 k_scan_pack(ScanPackArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -102,7 +111,7 @@ k_scan_pack(ScanPackArgs a) {
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) {
-        s_tile = atomicAdd(a.ticket, 1u);
+        s_tile = MODE == 0 ? atomicAdd(a.ticket, 1u) : blockIdx.x;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -146,16 +155,41 @@ k_scan_pack(ScanPackArgs a) {
         return (p >= 0 && p < nn) ? tb[j] : 0u;
     };
 
-    // ---- M1: which 16-byte vectors can hold a terminator?  ('\n' and '\r' are < 0x10) -----------
-    // Warp w owns tile bytes [w*8K, (w+1)*8K) as 16 coalesced 512-byte rows.  Candidate vectors are
-    // appended, in (row, lane) order, to the warp's queue, so everything after this loop runs on a
-    // dense list instead of diverging on every row.
     uint16_t* q_id = s_qid + wib * SP_QCAP;
     uint32_t* q_mk = s_qmk + wib * SP_QCAP;
     uint16_t* q_rk = s_qrk + wib * SP_QCAP;
     const bool interior = pos0 >= 1 && pos0 + SP_TILE + 16 <= nn;   // CTA-uniform
     const uint32_t lt = (1u << lane) - 1;
-    uint32_t qn = 0, ora = 0;
+    uint32_t qn = 0, wcount = 0;
+    bool bad = false, q_over = false;
+    uint8_t* gq = a.qbuf ? a.qbuf + ((uint64_t)tile * SP_WARPS + wib) * SP_QBYTES : nullptr;
+    if (MODE == 2) {
+        // the count pass already found the candidates and their exact masks
+        const uint32_t hdrw = *reinterpret_cast<const uint32_t*>(gq);
+        qn = hdrw & 0xFFFF;
+        const uint32_t* gmk = reinterpret_cast<const uint32_t*>(gq + 4);
+        const uint16_t* gid = reinterpret_cast<const uint16_t*>(gq + 4 + 4 * SP_QCAP);
+        for (uint32_t i0 = 0; i0 < qn; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t mk = 0;
+            if (i < qn) { mk = gmk[i]; q_mk[i] = mk; q_id[i] = gid[i]; }
+            const uint32_t c = __popc(mk & 0xFFFFu);
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= (uint32_t)d) inc += y;
+            }
+            if (i < qn) q_rk[i] = (uint16_t)(wcount + inc - c);
+            wcount += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        __syncwarp();
+    } else {
+    // ---- M1: which 16-byte vectors can hold a terminator?  ('\n' and '\r' are < 0x10) -----------
+    // Warp w owns tile bytes [w*8K, (w+1)*8K) as 16 coalesced 512-byte rows.  Candidate vectors are
+    // appended, in (row, lane) order, to the warp's queue, so everything after this loop runs on a
+    // dense list instead of diverging on every row.
+    uint32_t ora = 0;
 #pragma unroll
     for (int it = 0; it < SP_ITERS; it++) {
         const uint32_t vid = (wib * SP_ITERS + it) * 32 + lane;       // vector index inside the tile
@@ -179,12 +213,11 @@ k_scan_pack(ScanPackArgs a) {
         }
         qn += __popc(bm);
     }
-    bool bad = (ora & 0x80808080u) != 0;
-    const bool q_over = qn > SP_QCAP;
+    bad = (ora & 0x80808080u) != 0;
+    q_over = qn > SP_QCAP;
     if (q_over) qn = SP_QCAP;
     __syncwarp();
     // ---- M2: exact terminator / crlf masks of the candidates + their ranks inside the warp -----
-    uint32_t wcount = 0;
     for (uint32_t i0 = 0; i0 < qn; i0 += 32) {
         const uint32_t i = i0 + lane;
         uint32_t term = 0, crlf = 0;
@@ -212,6 +245,7 @@ k_scan_pack(ScanPackArgs a) {
         if (i < qn) q_rk[i] = (uint16_t)(wcount + inc - c);
         wcount += __shfl_sync(0xFFFFFFFFu, inc, 31);
     }
+    }
     if (bad) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_NON_ASCII);
     if (lane == 0) s_wtot[wib] = wcount | (q_over ? 0x80000000u : 0u);
     __syncthreads();
@@ -225,10 +259,24 @@ k_scan_pack(ScanPackArgs a) {
         tile_total += x & 0x7FFFFFFFu;
     }
     SP_STAMP(2);
+    if (MODE == 1) {
+        // count pass: save the queue (ids, masks) and the tile total; the pack pass does the rest
+        uint32_t* gmk = reinterpret_cast<uint32_t*>(gq + 4);
+        uint16_t* gid = reinterpret_cast<uint16_t*>(gq + 4 + 4 * SP_QCAP);
+        for (uint32_t i = lane; i < qn; i += 32) { gmk[i] = q_mk[i]; gid[i] = q_id[i]; }
+        if (lane == 0) *reinterpret_cast<uint32_t*>(gq) = qn;
+        if (threadIdx.x == 0) {
+            a.tile_tot[tile] = tile_total;
+            if (any_over) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_TILE_FULL);
+        }
+        return;
+    }
     // ---- decoupled look-back (warp 0), 128 predecessors per hop -------------------------------
     // The inclusive-prefix frontier can only advance by one window per L2 round trip, so the
     // window width bounds the kernel's throughput: 4 status words per lane.
-    if (wib == 0) {
+    if (MODE == 2) {
+        if (threadIdx.x == 0) s_excl = a.tile_excl[tile];
+    } else if (wib == 0) {
         volatile unsigned long long* vs = a.status;
         if (tile == 0) {
             if (lane == 0) { vs[0] = LB_INC | tile_total; s_excl = 0; }
@@ -415,7 +463,9 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
     unsigned long long* status = reinterpret_cast<unsigned long long*>(c->tile_base.p);
     VSPE_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 4) * 8, c->stream));
     if (!c->scan_pack_attr_set) {
-        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
         c->scan_pack_attr_set = true;
     }
     ScanPackArgs a;
@@ -435,7 +485,8 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
     // the dominant kernel is timed on its own (CUDA events on the launching stream)
     if (!c->ev_k[0]) { VSPE_CUDA(cudaEventCreate(&c->ev_k[0])); VSPE_CUDA(cudaEventCreate(&c->ev_k[1])); }
     VSPE_CUDA(cudaEventRecord(c->ev_k[0], c->stream));
-    k_scan_pack<<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
+    a.qbuf = nullptr; a.tile_tot = nullptr; a.tile_excl = nullptr;
+    k_scan_pack<0><<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
     VSPE_LAUNCH_CHECK(c);
     VSPE_CUDA(cudaEventRecord(c->ev_k[1], c->stream));
     unsigned long long h_total = 0, h_err = 0;
@@ -455,6 +506,89 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
         VSPE_CUDA(cudaStreamSynchronize(c->stream));
     }
     return VSPE_OK;
+}
+
+// Two-kernel variant: count pass (no inter-tile dependency) -> device scan of the tile totals ->
+// the caller sizes the outputs exactly -> pack pass.  `prepare` runs the first two steps and
+// returns the terminator count; `finish` launches the pack pass.
+void scan_pack_account(Ctx* c);
+
+int scan_pack_prepare(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms, unsigned long long* err_flags) {
+    *n_terms = 0;
+    *err_flags = 0;
+    if (n == 0) return VSPE_OK;
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
+    const uint64_t n_tiles = (n + head + SP_TILE - 1) / SP_TILE;
+    if (n_tiles > 0x7FFFFFFFull) { set_error("buffer too large for one scan launch"); return VSPE_ERR_LIMIT; }
+    VSPE_TRY(c->tile_base.reserve(2 * n_tiles + n_tiles / 1024 + 16));
+    VSPE_TRY(c->scan_q.reserve(n_tiles * SP_WARPS * SP_QBYTES + 64));
+    if (!c->scan_pack_attr_set) {
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        c->scan_pack_attr_set = true;
+    }
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(c->tile_base.p);
+    unsigned long long* excl = tot + n_tiles;
+    unsigned long long* sums = excl + n_tiles;                 // [n_tiles / 2048 + 1] scratch, then [.. + 8] the grand total
+    unsigned long long* d_total = sums + n_tiles / 1024 + 8;
+    ScanPackArgs a = {};
+    a.buf = d_buf; a.n = n; a.head = head; a.n_tiles = (uint32_t)n_tiles; a.counters = c->counters.p;
+    a.qbuf = c->scan_q.p; a.tile_tot = tot; a.tile_excl = excl;
+    a.row_words = 16; a.cap = 256;
+    if (!c->ev_k[2]) { VSPE_CUDA(cudaEventCreate(&c->ev_k[2])); VSPE_CUDA(cudaEventCreate(&c->ev_k[3])); }
+    VSPE_CUDA(cudaEventRecord(c->ev_k[2], c->stream));
+    k_scan_pack<1><<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
+    VSPE_LAUNCH_CHECK(c);
+    VSPE_CUDA(cudaEventRecord(c->ev_k[3], c->stream));
+    VSPE_TRY(device_scan_u64(c, tot, excl, n_tiles, sums, d_total));
+    unsigned long long h_total = 0, h_err = 0;
+    VSPE_CUDA(cudaMemcpyAsync(&h_total, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    *n_terms = h_total;
+    *err_flags = h_err;
+    scan_pack_account(c);                                      // a pack launch of the previous mate / chunk is done by now
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev_k[2], c->ev_k[3]) == cudaSuccess) { c->stats.ms_k_scan_count += ms; c->stats.n_k_scan_count++; }
+    }
+    if (h_err & ERRF_TILE_FULL) {
+        unsigned long long cleared = h_err & ~(unsigned long long)ERRF_TILE_FULL;
+        VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_ERR, &cleared, 8, cudaMemcpyHostToDevice, c->stream));
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return VSPE_OK;
+}
+
+int scan_pack_finish(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
+                     uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t row_words, uint32_t cap) {
+    if (n == 0) return VSPE_OK;
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
+    const uint64_t n_tiles = (n + head + SP_TILE - 1) / SP_TILE;
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(c->tile_base.p);
+    ScanPackArgs a = {};
+    a.buf = d_buf; a.n = n; a.head = head; a.n_tiles = (uint32_t)n_tiles; a.counters = c->counters.p;
+    a.qbuf = c->scan_q.p; a.tile_tot = tot; a.tile_excl = tot + n_tiles;
+    a.line_base = line_base; a.rec_first = rec_first; a.n_slots = n_slots;
+    a.seq_start = d_seq_start; a.seq_end = d_seq_end; a.rows = d_rows; a.hdr = d_hdr; a.row_words = row_words; a.cap = cap;
+    a.total_out = tot + 2 * n_tiles + n_tiles / 1024 + 9;      // unused scratch word
+    if (!c->ev_k[0]) { VSPE_CUDA(cudaEventCreate(&c->ev_k[0])); VSPE_CUDA(cudaEventCreate(&c->ev_k[1])); }
+    // account the previous pack launch (its events have completed by now: every caller syncs in between)
+    VSPE_CUDA(cudaEventRecord(c->ev_k[0], c->stream));
+    k_scan_pack<2><<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
+    VSPE_LAUNCH_CHECK(c);
+    VSPE_CUDA(cudaEventRecord(c->ev_k[1], c->stream));
+    c->scan_pack_pending = true;
+    return VSPE_OK;
+}
+
+// fold the duration of the last pack launch into the stats (call after a stream sync)
+void scan_pack_account(Ctx* c) {
+    if (!c->scan_pack_pending) return;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev_k[0], c->ev_k[1]) == cudaSuccess) { c->stats.ms_k_scan_pack += ms; c->stats.n_k_scan_pack++; }
+    c->scan_pack_pending = false;
 }
 
 }  // namespace vspe

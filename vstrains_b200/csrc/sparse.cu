@@ -116,6 +116,11 @@ static int device_exclusive_scan(Ctx* c, const T* in, T* out, uint64_t n, T* d_s
     return VSPE_OK;
 }
 
+int device_scan_u64(Ctx* c, const unsigned long long* in, unsigned long long* out, uint64_t n, unsigned long long* sums,
+                    unsigned long long* total) {
+    return device_exclusive_scan<unsigned long long>(c, in, out, n, sums, total);
+}
+
 // ---------------------------------------------------------------------------------------------
 // keys of a batch of pairs
 // ---------------------------------------------------------------------------------------------
