@@ -15,6 +15,22 @@ from vstrains_b200._lib import VspeError
 pytestmark = pytest.mark.gpu
 
 
+# kernel-path variants every parity case runs through (library options, see vspe_set_option)
+VARIANTS = [
+    {"scan_mode": 0},                                   # default path
+    {"scan_mode": 1},                                   # look-back scan + raw-byte map
+    {"scan_mode": 1, "force_generic": 1},               # exhaustive ASCII tier only
+    {"scan_mode": 0, "subst": 0},                       # no substitution-hit bitmap
+    {"scan_mode": 0, "subst": 0, "single_map": 1},      # every read through the full seed-and-extend kernel
+    {"scan_mode": 3},                                   # fused scan+pack with look-back
+    {"scan_mode": 0, "second_spread": 4, "list_spread": 8},   # deferred reads spread over more warps
+]
+
+
+def _variant_id(o):
+    return ",".join("%s=%s" % kv for kv in o.items())
+
+
 def _info(ids, mat, tmp_path, name):
     path = str(tmp_path / name)
     pe_inference.write_info(path, ids, mat)
@@ -22,16 +38,15 @@ def _info(ids, mat, tmp_path, name):
         return f.read()
 
 
-@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0), (0, 0, 2), (0, 3, 1)])
-def test_golden_fixtures_bit_exact(golden, tmp_path, force_generic, scan_mode, subst):
+@pytest.mark.parametrize("options", VARIANTS, ids=_variant_id)
+def test_golden_fixtures_bit_exact(golden, tmp_path, options):
     if golden.status != 0:
         with pytest.raises(VspeError) as ei:
             pe_inference.pe_inference(golden.gfa, golden.fwd, golden.rve, golden.k)
         assert ei.value.code == -2
         return
     ids, node, short, stats = pe_inference.pe_inference(golden.gfa, golden.fwd, golden.rve, golden.k,
-                                                        options={"force_generic": force_generic, "scan_mode": scan_mode,
-                                                                 "subst": subst & 1, "single_map": subst >> 1})
+                                                        options=options)
     assert _info(ids, node, tmp_path, "pe_info") == golden.pe_info
     assert _info(ids, short, tmp_path, "st_info") == golden.st_info
     _, _, ostats, _ = pe_oracle.run_bytes(golden.gfa, golden.fwd, golden.rve, golden.k)
@@ -107,12 +122,12 @@ def test_per_read_mapping_matches_oracle(golden, force_generic, scan_mode):
 
 
 @pytest.mark.parametrize("name,pairs", [("C1", 6000), ("C2", 6000), ("C3", 4000), ("C4", 3000)])
-@pytest.mark.parametrize("force_generic,scan_mode,subst", [(0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 0), (0, 0, 2), (0, 3, 1)])
-def test_synthetic_configs_match_c_oracle(name, pairs, force_generic, scan_mode, subst):
+@pytest.mark.parametrize("options", VARIANTS, ids=_variant_id)
+def test_synthetic_configs_match_c_oracle(name, pairs, options):
     cfg = synth.CONFIGS[name]
     g, f, r = synth.generate(cfg, pairs=pairs)
     gfa = g.to_gfa()
-    ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"force_generic": force_generic, "scan_mode": scan_mode, "subst": subst & 1, "single_map": subst >> 1})
+    ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options=options)
     onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
     assert np.array_equal(node.astype(np.int64), onode)
     assert np.array_equal(short.astype(np.int64), oshort)
@@ -260,7 +275,7 @@ def test_whole_path_edge_shapes(scan_mode):
 
 
 @pytest.mark.parametrize("subst,full_second", [(1, 0), (0, 1), (1, 1)])
-@pytest.mark.parametrize("sub_rate", [0.01, 0.04])
+@pytest.mark.parametrize("sub_rate", [0.002, 0.01, 0.04])
 def test_noisy_reads_match_c_oracle(subst, full_second, sub_rate):
     """1 % and 4 % substitution rates: several errors per read, errors next to node ends and to
     each other, reads that follow another strain's bubble arm after an error."""

@@ -890,11 +890,16 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "single_map")) c->opt_single_map = value;
     else if (!strcmp(name, "full_second")) c->opt_no_second = value;
     else if (!strcmp(name, "list_spread")) c->opt_list_spread = value;
+    else if (!strcmp(name, "second_spread")) c->opt_second_spread = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value;
     else if (!strcmp(name, "dbg_dump")) {
         // profiling aid: copy the per-tile stamps of the last scan to the host pointer `value`
         if (c->dbg_tiles && value) cudaMemcpy(reinterpret_cast<void*>(value), c->dbg_times.p, c->dbg_tiles * 64, cudaMemcpyDeviceToHost);
+    }
+    else if (!strcmp(name, "dbg_counters")) {
+        // profiling aid: copy the device counters (enum Counter order, CNT_COUNT_ words) to the host pointer `value`
+        if (value) cudaMemcpy(reinterpret_cast<void*>(value), c->counters.p, CNT_COUNT_ * 8, cudaMemcpyDeviceToHost);
     }
     else { set_error("unknown option %s", name); return VSPE_ERR_ARG; }
     return VSPE_OK;

@@ -80,6 +80,7 @@ struct Ctx {
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
     int64_t opt_list_spread = 4;       // list-driven k_map_fast: one read per this many threads (1, 2, 4, 8 ...)
+    int64_t opt_second_spread = 1;     // k_map_second: one read per this many threads (power of two <= 32)
     int64_t opt_no_second = 0;         // 1: skip k_map_second
     int64_t opt_single_map = 0;        // 1: skip k_map_first (every read through the full kernel)
     int64_t opt_subst = 1;             // build / use the substitution-hit bitmap

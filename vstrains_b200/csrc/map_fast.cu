@@ -649,13 +649,17 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
 template <int STRIDE>
 __global__ void __launch_bounds__(MF_THREADS)
 k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
-             const uint32_t* __restrict__ in_list, const unsigned long long* __restrict__ in_count,
+             const uint32_t* __restrict__ in_list, const unsigned long long* __restrict__ in_count, uint32_t spread,
              ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list, unsigned long long* __restrict__ out_count) {
+    // The deferred reads are few and each is a long serial chain: only every `spread`-th thread
+    // takes one, so they occupy `spread` times more warps (latency hiding instead of 32 diverged
+    // chains per warp).
     __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
     const uint64_t n_items = *in_count;
-    const uint64_t item = (uint64_t)blockIdx.x * MF_THREADS + threadIdx.x;
-    if ((uint64_t)blockIdx.x * MF_THREADS >= n_items) return;
-    if (item >= n_items) return;
+    const uint32_t per_block = MF_THREADS / spread;
+    const uint64_t item = (uint64_t)blockIdx.x * per_block + threadIdx.x / spread;
+    if ((uint64_t)blockIdx.x * per_block >= n_items) return;
+    if (item >= n_items || threadIdx.x % spread != 0) return;
     const uint32_t t = threadIdx.x, L = ix.split_len;
     const uint32_t r = in_list[item];
     const uint32_t h = __ldg(hdr + r);
@@ -908,6 +912,13 @@ k_map_windows(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* _
 int map_reads_generic_dev(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                           const uint32_t* d_worklist, const unsigned long long* d_n_items, ReadSlot* d_slots);
 
+// threads per deferred read in the list-driven kernels: a power of two in [1, 32]
+static uint32_t pow2_spread(int64_t v) {
+    uint32_t s = 1;
+    while (s < 32 && (int64_t)s * 2 <= v) s *= 2;
+    return s;
+}
+
 static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                            const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
                            uint64_t n_reads, ReadSlot* d_slots) {
@@ -939,8 +950,10 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
         if (c->index.has_subst && !c->opt_no_second) {
             // stage 1b: one-error-tolerant walk on the deferred reads; its leftovers go to stage 2
             uint32_t* list1b = c->defer_list.p + 2 * n_reads;
-#define VSPE_M2(S) k_map_second<S><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->defer_list.p, \
-                                                                 c->counters.p + CNT_DEFER, d_slots, list1b, c->counters.p + CNT_DEFER2)
+            const uint32_t spread2 = pow2_spread(c->opt_second_spread);
+            const uint32_t grid_s = (uint32_t)std::min<uint64_t>((n_reads * spread2 + MF_THREADS - 1) / MF_THREADS, 0x7FFFFFFFull);
+#define VSPE_M2(S) k_map_second<S><<<grid_s, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->defer_list.p, \
+                                                                   c->counters.p + CNT_DEFER, spread2, d_slots, list1b, c->counters.p + CNT_DEFER2)
             if (cap <= 160) VSPE_M2(13); else if (cap <= 256) VSPE_M2(19); else VSPE_M2(23);
 #undef VSPE_M2
             VSPE_LAUNCH_CHECK(c);
@@ -949,7 +962,7 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
         }
     }
     // stage 2: the full seed-and-extend kernel (on the deferred reads, or on everything)
-    const uint32_t list_spread = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(32, c->opt_list_spread));
+    const uint32_t list_spread = pow2_spread(c->opt_list_spread);
     const uint32_t grid2 = in_list ? (uint32_t)std::min<uint64_t>((n_reads * list_spread + MF_THREADS - 1) / MF_THREADS, 0x7FFFFFFFull) : grid;
 #define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid2, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
                                                                                row_words, n_reads, in_list, in_count, list_spread, d_slots, \
