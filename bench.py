@@ -341,6 +341,22 @@ def main():
             torch.cuda.synchronize()
         return ix.sparse() if sparse else ix.matrices()
 
+    # the end-to-end ceiling: a plain pinned host->device copy of the same bytes (PCIe), for context
+    h2d_gbs = None
+    try:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(3):
+            ev0.record()
+            d_f.copy_(h_f, non_blocking=True)
+            d_r.copy_(h_r, non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            best = min(best, ev0.elapsed_time(ev1))
+        h2d_gbs = bytes_step / (best * 1e-3) / 1e9
+    except Exception:
+        pass
+
     for _ in range(2):
         step_e2e()
     barrier()
@@ -388,7 +404,9 @@ def main():
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_step,
-                "d2h_bytes_per_step": int(16 * ix.sparse()[0].size) if sparse else int(2 * n_nodes * n_nodes * 8)},
+                "d2h_bytes_per_step": int(16 * ix.sparse()[0].size) if sparse else int(2 * n_nodes * n_nodes * 8),
+                "pinned_h2d_copy_gbs": h2d_gbs,
+                "frac_of_h2d_copy": (e2e_value / world * b_pair / 1e9 / h2d_gbs) if h2d_gbs else None},
         "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
         "whole_job_hbm_frac": value / world * b_pair / 1e9 / peak,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -24,6 +24,7 @@ VARIANTS = [
     {"scan_mode": 0, "subst": 0, "single_map": 1},      # every read through the full seed-and-extend kernel
     {"scan_mode": 3},                                   # fused scan+pack with look-back
     {"scan_mode": 0, "second_spread": 4, "list_spread": 8},   # deferred reads spread over more warps
+    {"scan_mode": 0, "flat_walk": 0},                   # nested walk loops in k_map_first
 ]
 
 

@@ -58,8 +58,16 @@ static int check_kernel_errors(Ctx* c) {
 
 // One chunk of one mate's byte stream, resident on the device.  The chunk must start at a line
 // start and (unless it is the last chunk) end right after a terminator.
+static int scan_mode_of(Ctx* c) {
+    int mode = (int)c->opt_scan_mode;
+    if (c->opt_scan_two_pass) mode = 2;
+    if ((c->opt_force_generic || c->index.split_len > 320) && (mode == 0 || mode == 3)) mode = 1;
+    return mode;
+}
+
+// prepared: the count pass of this chunk was already queued (scan_pack_prepare_launch)
 static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint64_t n, bool is_last, int last_byte,
-                      bool sync_after = true) {
+                      bool sync_after = true, bool prepared = false) {
     if (n == 0) {
         if (is_last) ms.lines = ms.line_base;
         return VSPE_OK;
@@ -75,15 +83,14 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     c->cur_buf_n = n;
     const uint32_t cap = map_fast_cap(c->read_len_hint);
     const uint32_t row_words = cap <= 160 ? 12 : cap <= 256 ? 16 : 20;
-    int mode = (int)c->opt_scan_mode;
-    if (c->opt_scan_two_pass) mode = 2;
-    if ((c->opt_force_generic || c->index.split_len > 320) && (mode == 0 || mode == 3)) mode = 1;
+    int mode = scan_mode_of(c);
     bool packed = false;
     if (mode == 0) {
         // count pass (terminator masks, no inter-tile dependency) + device scan, then the pack
         // pass with exactly sized outputs
         unsigned long long flags = 0;
-        VSPE_TRY(scan_pack_prepare(c, d_buf, n, &n_terms, &flags));
+        if (!prepared) VSPE_TRY(scan_pack_prepare_launch(c, m, d_buf, n));
+        VSPE_TRY(scan_pack_prepare_collect(c, m, d_buf, n, &n_terms, &flags));
         if (flags & ERRF_TILE_FULL) {
             mode = 1;                                   // a warp row with too many candidates: plain path
         } else {
@@ -92,7 +99,7 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
             VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
             VSPE_TRY(mb.rec.hdr.reserve(n_seq + 2));
             VSPE_TRY(mb.rec.rows.reserve((n_seq + 2) * row_words));
-            VSPE_TRY(scan_pack_finish(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p,
+            VSPE_TRY(scan_pack_finish(c, m, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p,
                                       mb.rec.hdr.p, row_words, cap));
             packed = true;
         }
@@ -175,6 +182,7 @@ static int report_error_flags(unsigned long long e) {
     if (e & ERRF_NON_ASCII) { set_error("input contains a byte >= 0x80 (non-ASCII FASTQ is outside the reference's contract)"); return VSPE_ERR_NON_ASCII; }
     if (e & ERRF_SPILL_FULL) { set_error("node-list spill pool exhausted"); return VSPE_ERR_LIMIT; }
     if (e & ERRF_KEYS_FULL) { set_error("key buffer exhausted"); return VSPE_ERR_LIMIT; }
+    if (e & ERRF_TILE_FULL) { set_error("internal: a scan tile overflowed after its count pass accepted it"); return VSPE_ERR_LIMIT; }
     return VSPE_OK;
 }
 
@@ -255,31 +263,38 @@ static bool is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
-// Stream one mate's host buffer through the device in line-aligned chunks with two staging
-// buffers: the copy of chunk i+1 overlaps the kernels of chunk i.
-static int stream_mate_host(Ctx* c, int m, MateStream& ms, const uint8_t* src, uint64_t n) {
-    if (n == 0) return feed_chunk(c, m, ms, nullptr, 0, true, -1);
+// Stream both mates' host buffers through the device in line-aligned chunks with two staging
+// buffers: the copy of chunk i+1 overlaps the kernels of chunk i, and the first chunk of the
+// second mate is already on its way while the last chunk of the first mate is processed.
+static int stream_mates_host(Ctx* c, MateStream* ms, const uint8_t* const* srcs, const uint64_t* ns) {
     const uint64_t chunk = (uint64_t)std::max<int64_t>(1, c->opt_chunk_mb) << 20;
-    const bool pinned_src = is_pinned(src);
-    struct Piece { uint64_t lo, hi; };
+    struct Piece { int m; uint64_t lo, hi; bool last; };
     std::vector<Piece> pieces;
-    for (uint64_t lo = 0; lo < n;) {
-        uint64_t hi = std::min(n, lo + chunk);
-        if (hi < n) {
-            uint64_t cut = cut_at_line(src, lo, hi, n);
-            while (cut == lo && hi < n) {                 // a line longer than the chunk: extend
-                hi = std::min(n, hi + chunk);
-                cut = hi == n ? n : cut_at_line(src, lo, hi, n);
+    bool pinned_src[2] = {true, true};
+    for (int m = 0; m < 2; m++) {
+        const uint8_t* src = srcs[m];
+        const uint64_t n = ns[m];
+        if (n == 0) { VSPE_TRY(feed_chunk(c, m, ms[m], nullptr, 0, true, -1)); continue; }
+        pinned_src[m] = is_pinned(src);
+        for (uint64_t lo = 0; lo < n;) {
+            uint64_t hi = std::min(n, lo + chunk);
+            if (hi < n) {
+                uint64_t cut = cut_at_line(src, lo, hi, n);
+                while (cut == lo && hi < n) {                 // a line longer than the chunk: extend
+                    hi = std::min(n, hi + chunk);
+                    cut = hi == n ? n : cut_at_line(src, lo, hi, n);
+                }
+                hi = cut;
             }
-            hi = cut;
+            pieces.push_back({m, lo, hi, hi == n});
+            lo = hi;
         }
-        pieces.push_back({lo, hi});
-        lo = hi;
     }
+    if (pieces.empty()) return VSPE_OK;
     uint64_t max_piece = 0;
     for (auto& p : pieces) max_piece = std::max(max_piece, p.hi - p.lo);
     for (int b = 0; b < 2; b++) VSPE_TRY(c->dev_in[b].reserve(max_piece + 64));
-    if (!pinned_src && c->pinned_bytes < max_piece) {
+    if (!(pinned_src[0] && pinned_src[1]) && c->pinned_bytes < max_piece) {
         for (int b = 0; b < 2; b++) {
             if (c->pinned[b]) cudaFreeHost(c->pinned[b]);
             c->pinned[b] = nullptr;
@@ -292,8 +307,8 @@ static int stream_mate_host(Ctx* c, int m, MateStream& ms, const uint8_t* src, u
     auto issue_copy = [&](size_t i) -> int {
         int b = (int)(i & 1);
         const Piece& p = pieces[i];
-        const uint8_t* from = src + p.lo;
-        if (!pinned_src) { parallel_memcpy(c->pinned[b], from, p.hi - p.lo); from = c->pinned[b]; }
+        const uint8_t* from = srcs[p.m] + p.lo;
+        if (!pinned_src[p.m]) { parallel_memcpy(c->pinned[b], from, p.hi - p.lo); from = c->pinned[b]; }
         VSPE_CUDA(cudaMemcpyAsync(c->dev_in[b].p, from, p.hi - p.lo, cudaMemcpyHostToDevice, c->copy_stream[b]));
         VSPE_CUDA(cudaEventRecord(copied[b], c->copy_stream[b]));
         return VSPE_OK;
@@ -306,8 +321,8 @@ static int stream_mate_host(Ctx* c, int m, MateStream& ms, const uint8_t* src, u
         if (i + 1 < pieces.size()) rc = issue_copy(i + 1);
         if (rc != VSPE_OK) break;
         if (cudaStreamWaitEvent(c->stream, copied[b], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); rc = VSPE_ERR_CUDA; break; }
-        bool last = i + 1 == pieces.size();
-        rc = feed_chunk(c, m, ms, c->dev_in[b].p, pieces[i].hi - pieces[i].lo, last, last ? src[n - 1] : -1);
+        const Piece& p = pieces[i];
+        rc = feed_chunk(c, p.m, ms[p.m], c->dev_in[b].p, p.hi - p.lo, p.last, p.last ? srcs[p.m][ns[p.m] - 1] : -1);
     }
     cudaStreamSynchronize(c->copy_stream[0]);
     cudaStreamSynchronize(c->copy_stream[1]);
@@ -441,7 +456,7 @@ void vspe_destroy(vspe_ctx* c) {
         if (c->copy_stream[b]) cudaStreamDestroy(c->copy_stream[b]);
     }
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
-    for (auto& ev : c->ev_k) if (ev) cudaEventDestroy(ev);
+    for (auto& evs : c->ev_scan) for (auto& ev : evs) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -459,8 +474,7 @@ int vspe_reset(vspe_ctx* c) {
     uint64_t nn = 2ull * c->index.n_nodes * c->index.n_nodes;
     if (nn && !c->sparse.enabled) VSPE_CUDA(cudaMemsetAsync(c->mats.p, 0, nn * 8, c->stream));
     c->sparse.n_runs = 0;
-    VSPE_CUDA(cudaMemsetAsync(c->counters.p, 0, CNT_COUNT_ * 8, c->stream));
-    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    VSPE_CUDA(cudaMemsetAsync(c->counters.p, 0, CNT_COUNT_ * 8, c->stream));   // stream-ordered: no host sync needed
     vspe_stats keep = c->stats;
     c->stats = {};
     c->stats_overridden = false;
@@ -489,6 +503,10 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
     MateStream* ms[2] = {&f, &r};
     int last[2] = {-1, -1};
     uint32_t hint = 0;
+    // the count passes of both mates need nothing from the host: queue them before the first sync
+    const bool prelaunch = scan_mode_of(c) == 0;
+    if (prelaunch)
+        for (int m = 0; m < 2; m++) VSPE_TRY(scan_pack_prepare_launch(c, m, bufs[m], ns[m]));
     {   // one small D2H round for both mates: last byte (does the file end with a terminator?)
         // and a prefix to size the packed rows
         static thread_local std::vector<uint8_t> head(2 * 16384);
@@ -508,7 +526,7 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
         }
     }
     c->read_len_hint = hint;
-    for (int m = 0; m < 2; m++) VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last[m], false));
+    for (int m = 0; m < 2; m++) VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last[m], false, prelaunch));
     VSPE_TRY(finish_pairs(c, f, r));
     VSPE_CUDA(cudaEventRecord(t1, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
@@ -516,6 +534,11 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
     cudaEventElapsedTime(&ms_total, t0, t1);
     c->stats.ms_total = ms_total;
     scan_pack_account(c);
+    if (prelaunch && c->ev_m[0][0] && ns[0]) {
+        // the count passes of both mates ran between the start of the call and mate 0's first event
+        float pre = 0;
+        if (cudaEventElapsedTime(&pre, t0, c->ev_m[0][0]) == cudaSuccess) c->stats.ms_scan += pre;
+    }
     for (int m = 0; m < 2; m++) {
         if (!ns[m]) continue;
         float a = 0, b = 0;
@@ -537,8 +560,12 @@ int vspe_count_host(vspe_ctx* c, const uint8_t* fwd, uint64_t n_fwd, const uint8
     VSPE_CUDA(cudaEventRecord(t0, c->stream));
     MateStream f, r;
     c->read_len_hint = std::max(seq_len_hint(fwd, std::min<uint64_t>(n_fwd, 16384)), seq_len_hint(rve, std::min<uint64_t>(n_rve, 16384)));
-    VSPE_TRY(stream_mate_host(c, 0, f, fwd, n_fwd));
-    VSPE_TRY(stream_mate_host(c, 1, r, rve, n_rve));
+    MateStream ms[2];
+    const uint8_t* srcs[2] = {fwd, rve};
+    const uint64_t ns[2] = {n_fwd, n_rve};
+    VSPE_TRY(stream_mates_host(c, ms, srcs, ns));
+    f = ms[0];
+    r = ms[1];
     VSPE_TRY(finish_pairs(c, f, r));
     cudaEvent_t t1 = c->ev[1];
     VSPE_CUDA(cudaEventRecord(t1, c->stream));
@@ -708,9 +735,14 @@ int vspe_map_reads(vspe_ctx* c, const uint8_t* fq, uint64_t n_bytes, uint64_t* n
                    const uint32_t** nodes, const uint8_t** status) {
     VSPE_TRY(require_index(c));
     begin_call(c);
-    MateStream ms;
+    MateStream both[2];
     c->read_len_hint = seq_len_hint(fq, std::min<uint64_t>(n_bytes, 16384));
-    VSPE_TRY(stream_mate_host(c, 0, ms, fq, n_bytes));
+    {
+        const uint8_t* srcs[2] = {fq, nullptr};
+        const uint64_t ns[2] = {n_bytes, 0};
+        VSPE_TRY(stream_mates_host(c, both, srcs, ns));
+    }
+    const MateStream& ms = both[0];
     VSPE_TRY(check_kernel_errors(c));
     uint64_t recs = ms.lines / 4;
     std::vector<ReadSlot> slots(recs);
@@ -891,6 +923,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "full_second")) c->opt_no_second = value;
     else if (!strcmp(name, "list_spread")) c->opt_list_spread = value;
     else if (!strcmp(name, "second_spread")) c->opt_second_spread = value;
+    else if (!strcmp(name, "flat_walk")) c->opt_flat_walk = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value;
     else if (!strcmp(name, "dbg_dump")) {

@@ -39,9 +39,12 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_k[4] = {};
-    bool scan_pack_pending = false;
-    DevBuf<uint8_t> scan_q;           // two-kernel scan: per (tile, warp) candidate queues
+    // two-kernel scan, per mate: events around the pack pass [0..1] and the count pass [2..3],
+    // candidate queues per (tile, warp), tile totals + their scan
+    cudaEvent_t ev_scan[2][4] = {};
+    bool scan_pack_pending[2] = {false, false}, scan_count_pending[2] = {false, false};
+    DevBuf<uint8_t> scan_q[2];
+    DevBuf<uint64_t> scan_tiles[2];
     Index index;
     DevBuf<uint64_t> mats;            // [2][N][N] node_mat then short_mat (dense mode)
     Sparse sparse;                    // sorted (key, count) runs (sparse mode)
@@ -79,7 +82,8 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
-    int64_t opt_list_spread = 4;       // list-driven k_map_fast: one read per this many threads (1, 2, 4, 8 ...)
+    int64_t opt_list_spread = 2;       // list-driven k_map_fast: one read per this many threads (1, 2, 4, 8 ...)
+    int64_t opt_flat_walk = 1;         // k_map_first: flat walk loop (0: nested stretch / chunk loops)
     int64_t opt_second_spread = 1;     // k_map_second: one read per this many threads (power of two <= 32)
     int64_t opt_no_second = 0;         // 1: skip k_map_second
     int64_t opt_single_map = 0;        // 1: skip k_map_first (every read through the full kernel)

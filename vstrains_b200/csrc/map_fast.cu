@@ -287,19 +287,17 @@ __device__ __forceinline__ uint32_t run_pass(const IndexView& ix, const uint32_t
 // PACKED: phase 1 loads the 2-bit rows written by k_scan_pack (scan_pack.cu) instead of packing
 // the raw bytes itself.
 template <int STRIDE, int LPR, bool PACKED>
-__global__ void __launch_bounds__(MF_THREADS)
-k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
-           const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr,
-           uint32_t row_words, uint64_t n_reads_arg, const uint32_t* __restrict__ in_list,
-           const unsigned long long* __restrict__ in_count, uint32_t list_spread, ReadSlot* __restrict__ slots,
-           uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters) {
-    // in_list != nullptr: process reads in_list[0 .. *in_count) (the reads k_map_first deferred).
-    // Those reads are few and each is a long serial chain (passes, range probes), so the kernel
-    // is latency-bound: in list mode only every LIST_SPREAD-th thread takes a read, which spreads
-    // them over LIST_SPREAD times more warps.
-    const uint32_t spread = in_list ? list_spread : 1u;
-    const uint64_t n_reads = in_list ? *in_count : n_reads_arg;
-    if ((uint64_t)blockIdx.x * (MF_THREADS / spread) >= n_reads) return;
+__device__ __forceinline__ void
+map_fast_block(const IndexView& ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
+               const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr,
+               uint32_t row_words, uint64_t n_reads, const uint32_t* __restrict__ in_list, uint32_t spread,
+               ReadSlot* __restrict__ slots, uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters,
+               const uint32_t block_id) {
+    // One block's worth of reads: MF_THREADS / spread of them, read block_id * that onwards.
+    // in_list != nullptr: they are in_list[...] (the reads the first tiers deferred).  Those are
+    // few and each is a long serial chain (passes, range probes): only every spread-th thread
+    // takes a read, which spreads them over `spread` times more warps.
+    if ((uint64_t)block_id * (MF_THREADS / spread) >= n_reads) return;
     constexpr uint32_t CAP = (STRIDE - 3) * 16;                   // bases per packed row
     constexpr uint32_t GROUPS = 32 / LPR;                          // reads packed per warp step
     __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
@@ -309,7 +307,7 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     __shared__ uint32_t s_len[MF_THREADS];                         // rlen | flags << 24
     constexpr uint32_t F_N = 1u << 24, F_BAD = 2u << 24, F_LONG = 4u << 24, F_NONE = 8u << 24;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t r0 = (uint64_t)blockIdx.x * (MF_THREADS / spread);
+    const uint64_t r0 = (uint64_t)block_id * (MF_THREADS / spread);
     const uint32_t L = ix.split_len;
 
     if (PACKED) {
@@ -487,7 +485,7 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
 
     // ---- phase 4: finalize -----------------------------------------------------------------
     if (lf & F_NONE) return;
-    if (t == 0 && blockIdx.x == 0 && !in_list) atomicAdd(&counters[CNT_FAST], (unsigned long long)n_reads);
+    if (t == 0 && block_id == 0 && !in_list) atomicAdd(&counters[CNT_FAST], (unsigned long long)n_reads);
     ReadSlot* out = slots + r;
     if (!(lf & F_LONG)) {
         if (lf & F_N) { out->hdr = ST_N; return; }
@@ -522,13 +520,106 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     out->hdr = ST_OK | (n_out << 8);
 }
 
+// Direct mode (in_list == nullptr): one block per MF_THREADS reads.  List mode: a fixed grid walks
+// the device-side worklist (its length is only known on the device), so no empty blocks are launched.
+template <int STRIDE, int LPR, bool PACKED>
+__global__ void __launch_bounds__(MF_THREADS)
+k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
+           const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr,
+           uint32_t row_words, uint64_t n_reads_arg, const uint32_t* __restrict__ in_list,
+           const unsigned long long* __restrict__ in_count, uint32_t list_spread, ReadSlot* __restrict__ slots,
+           uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters) {
+    if (!in_list) {
+        map_fast_block<STRIDE, LPR, PACKED>(ix, buf, seq_start, seq_end, rows, hdr, row_words, n_reads_arg, nullptr, 1u, slots, worklist,
+                                            counters, blockIdx.x);
+        return;
+    }
+    const uint64_t n_items = *in_count;
+    const uint64_t per_block = MF_THREADS / list_spread;
+    const uint64_t n_blocks = (n_items + per_block - 1) / per_block;
+    for (uint64_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        map_fast_block<STRIDE, LPR, PACKED>(ix, buf, seq_start, seq_end, rows, hdr, row_words, n_items, in_list, list_spread, slots,
+                                            worklist, counters, (uint32_t)b);
+        __syncthreads();                                   // the block's shared-memory rows are reused by the next round
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-read node list of the walk kernels, in REGISTERS: up to FL_MAX entries (node << 32 | v | kmin << 16),
+// empty = all ones.  Appends are predicated register writes; one fixed 12-exchange network sorts
+// the list by node index at the end, so duplicates become neighbours and the output rank of a kept
+// node is a popcount -- no data-dependent loops, every thread of the warp runs the same code.
+// ---------------------------------------------------------------------------------------------
+static constexpr int FL_MAX = 6;
+static constexpr uint64_t FL_EMPTY = ~0ull;
+
+struct FlatList {
+    uint64_t e[FL_MAX];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < FL_MAX; i++) e[i] = FL_EMPTY;
+    }
+    __device__ __forceinline__ void set(uint32_t at, uint32_t node, uint32_t vk) {
+        const uint64_t x = ((uint64_t)node << 32) | vk;
+#pragma unroll
+        for (int i = 0; i < FL_MAX; i++) if (at == (uint32_t)i) e[i] = x;
+    }
+    __device__ __forceinline__ void cex(int i, int j) {
+        const uint64_t a = e[i], b = e[j];
+        e[i] = a < b ? a : b;
+        e[j] = a < b ? b : a;
+    }
+    __device__ __forceinline__ void sort() {
+        cex(0, 5); cex(1, 3); cex(2, 4);
+        cex(1, 2); cex(3, 4);
+        cex(0, 3); cex(2, 5);
+        cex(0, 1); cex(2, 3); cex(4, 5);
+        cex(1, 2); cex(3, 4);
+    }
+    // sorted list: fold every run of equal nodes into its last entry (hits add up, smallest position wins)
+    __device__ __forceinline__ void merge_repeats() {
+#pragma unroll
+        for (int i = 0; i + 1 < FL_MAX; i++) {
+            if (e[i + 1] != FL_EMPTY && (uint32_t)(e[i] >> 32) == (uint32_t)(e[i + 1] >> 32)) {
+                const uint32_t x = (uint32_t)e[i], y = (uint32_t)e[i + 1];
+                const uint32_t vk = ((x & 0xFFFF) + (y & 0xFFFF)) | (min(x >> 16, y >> 16) << 16);
+                e[i + 1] = (e[i + 1] & 0xFFFFFFFF00000000ull) | vk;
+                e[i] = FL_EMPTY;
+            }
+        }
+    }
+    // two stretches of the same node (cyclic graph)?
+    __device__ __forceinline__ bool has_repeat() const {
+        bool r = false;
+#pragma unroll
+        for (int i = 0; i + 1 < FL_MAX; i++) r |= e[i + 1] != FL_EMPTY && (uint32_t)(e[i] >> 32) == (uint32_t)(e[i + 1] >> 32);
+        return r;
+    }
+};
+
+// saturation predicate over a sorted list; writes the kept node indices in ascending order
+__device__ __forceinline__ uint32_t flat_finalize(const FlatList& fl, const IndexView& ix, uint32_t rlen, uint32_t L, ReadSlot* out) {
+    uint32_t keepmask = 0;
+#pragma unroll
+    for (int i = 0; i < FL_MAX; i++) {
+        if (fl.e[i] != FL_EMPTY) {
+            const uint32_t node = (uint32_t)(fl.e[i] >> 32), vk = (uint32_t)fl.e[i];
+            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) keepmask |= 1u << i;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < FL_MAX; i++)
+        if ((keepmask >> i) & 1) out->ids[__popc(keepmask & ((1u << i) - 1))] = (uint32_t)(fl.e[i] >> 32);
+    return (uint32_t)__popc(keepmask);
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_map_first: the common case only.  Packs nothing (rows come from k_scan_pack), runs ONE clean
 // forward pass -- seed window 0, extend, walk successors -- and finishes the read if that pass
 // proves every window.  Anything else (a miss, a mismatch, a repeat, too many nodes) defers the
 // read, untouched, to k_map_fast via a worklist, so the two populations never share a warp.
 // ---------------------------------------------------------------------------------------------
-template <int STRIDE, int LPR>
+template <int STRIDE, int LPR, bool FLAT>
 __global__ void __launch_bounds__(MF_THREADS)
 k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
             uint64_t n_reads, ReadSlot* __restrict__ slots, uint32_t* __restrict__ defer_list,
@@ -562,7 +653,8 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
     }
     const uint32_t* row = s_fwd + t * STRIDE;
     uint32_t nn = 0;
-    uint32_t l_node[MAXN], l_vk[MAXN];                     // per-read node list: thread-local (L1), not shared memory
+    FlatList fl;                                           // per-read node list in registers
+    fl.clear();
     if (!defer) {
         uint32_t tp = NONE32, node = 0;
         if (probe_window(ix, row, 0, tp, node) != PROBE_UNIQUE) defer = true;
@@ -570,64 +662,84 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
         // p + delta.  Each step compares 32 bases and tests the uniq bits of the 32 windows that
         // END at those bases; the first window of a stretch is unique by construction (seed:
         // PROBE_UNIQUE, later ones: successor table).
-        uint32_t i0 = 0, p = L;
-        while (!defer) {
+        // FLAT: one loop whose every turn is "compare up to 32 bases, then -- if the stretch is complete --
+        // append it and step to the successor strand", so the threads of a warp stay in step however
+        // their reads are cut into stretches (the nested form runs max-stretches x max-chunks turns).
+        uint32_t i0 = 0, p = L, q = 0, lim = 0;
+        int delta = 0;
+        auto enter = [&]() {                                   // strand of window i0 = text position tp
             const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
             const bool rcs = tp >= s1;
-            const uint32_t q = 2 * node + (rcs ? 1u : 0u);
+            q = 2 * node + (rcs ? 1u : 0u);
             const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
-            const int delta = (int)tp - (int)i0;
-            const uint32_t lim = min(rlen, (uint32_t)((int)send - delta));   // read position where the strand ends
-            while (p < lim) {
-                const uint32_t n = min(32u, lim - p);
-                uint64_t x = read64(row, p) ^ extract64(ix.text, (uint64_t)((int)p + delta));
-                const uint32_t u = (uint32_t)((int)p + delta) - L + 1;         // text position of the first window ending here
-                const uint32_t ub = __funnelshift_r(__ldg(ix.uniq + (u >> 5)), __ldg(ix.uniq + (u >> 5) + 1), u & 31);
-                const uint32_t m32 = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
-                if (n < 32) x &= (1ull << (2 * n)) - 1;
-                if (x != 0 || (ub & m32) != m32) { defer = true; break; }
-                p += n;
+            delta = (int)tp - (int)i0;
+            lim = min(rlen, (uint32_t)((int)send - delta));    // read position where the strand ends
+        };
+        auto chunk = [&]() -> bool {                           // bases [p, p + n) and the windows ending there
+            const uint32_t n = min(32u, lim - p);
+            uint64_t x = read64(row, p) ^ extract64(ix.text, (uint64_t)((int)p + delta));
+            const uint32_t u = (uint32_t)((int)p + delta) - L + 1;             // text position of the first window ending here
+            const uint32_t ub = __funnelshift_r(__ldg(ix.uniq + (u >> 5)), __ldg(ix.uniq + (u >> 5) + 1), u & 31);
+            const uint32_t m32 = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
+            if (n < 32) x &= (1ull << (2 * n)) - 1;
+            if (x != 0 || (ub & m32) != m32) return false;
+            p += n;
+            return true;
+        };
+        if (FLAT) {
+            bool running = !defer;
+            if (running) enter();
+            while (running) {
+                if (p < lim && !chunk()) { defer = true; running = false; }
+                if (running && p >= lim) {
+                    // append the stretch; a node met twice (cyclic graph) is detected at the end and deferred
+                    if (nn == (uint32_t)FL_MAX) { defer = true; running = false; }
+                    else {
+                        fl.set(nn, node, (lim - L + 1 - i0) | (i0 << 16));
+                        nn++;
+                        if (lim >= rlen) running = false;
+                        else {
+                            // the strand ended before the read: successor window for the read's next base
+                            const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
+                            const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
+                            if (sc.x == NONE32) { defer = true; running = false; }
+                            else {
+                                i0 = lim - L + 1;
+                                tp = sc.x;
+                                node = sc.y;
+                                p = lim + 1;
+                                enter();
+                            }
+                        }
+                    }
+                }
             }
-            if (defer) break;
-            // append the stretch; a node met twice (cyclic graph) is detected at the end and deferred
-            if (nn == MAXN) { defer = true; break; }
-            l_node[nn] = node;
-            l_vk[nn] = (lim - L + 1 - i0) | (i0 << 16);
-            nn++;
-            if (lim >= rlen) break;
-            // the strand ended before the read: successor window for the read's next base
-            const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
-            const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
-            if (sc.x == NONE32) { defer = true; break; }
-            i0 = lim - L + 1;
-            tp = sc.x;
-            node = sc.y;
-            p = lim + 1;
+        } else {
+            while (!defer) {
+                enter();
+                while (p < lim) {
+                    if (!chunk()) { defer = true; break; }
+                }
+                if (defer) break;
+                if (nn == (uint32_t)FL_MAX) { defer = true; break; }
+                fl.set(nn, node, (lim - L + 1 - i0) | (i0 << 16));
+                nn++;
+                if (lim >= rlen) break;
+                const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
+                const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
+                if (sc.x == NONE32) { defer = true; break; }
+                i0 = lim - L + 1;
+                tp = sc.x;
+                node = sc.y;
+                p = lim + 1;
+            }
         }
     }
     uint32_t n_out = 0;
     if (!defer) {
-        // saturation predicate per node, then ascending node order from ranks (no data-dependent sort
-        // loops: most reads have one or two nodes)
-        uint32_t keepmask = 0;
-        for (uint32_t a = 0; a < nn; a++) {
-            const uint32_t vk = l_vk[a], node = l_node[a];
-            for (uint32_t b = 0; b < a; b++) defer |= l_node[b] == node;      // needs merging: full kernel
-            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) keepmask |= 1u << a;
-        }
-        n_out = __popc(keepmask);
-        if (n_out > (uint32_t)SLOT_IDS) defer = true;
-        if (defer) n_out = 0;
-        if (n_out == 1) out->ids[0] = l_node[__ffs((int)keepmask) - 1];
-        else if (n_out > 1) {
-            for (uint32_t a = 0; a < nn; a++) {
-                if (!((keepmask >> a) & 1)) continue;
-                const uint32_t node = l_node[a];
-                uint32_t rank = 0;
-                for (uint32_t b = 0; b < nn; b++) rank += ((keepmask >> b) & 1) && l_node[b] < node;
-                out->ids[rank] = node;
-            }
-        }
+        fl.sort();
+        if (fl.has_repeat()) defer = true;                 // needs merging: full kernel
+        else n_out = flat_finalize(fl, ix, rlen, L, out);
     }
     if (defer) {
         const unsigned long long idx = atomicAdd(&counters[CNT_DEFER], 1ull);
@@ -647,27 +759,16 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
 // on to k_map_fast.
 // ---------------------------------------------------------------------------------------------
 template <int STRIDE>
-__global__ void __launch_bounds__(MF_THREADS)
-k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
-             const uint32_t* __restrict__ in_list, const unsigned long long* __restrict__ in_count, uint32_t spread,
-             ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list, unsigned long long* __restrict__ out_count) {
-    // The deferred reads are few and each is a long serial chain: only every `spread`-th thread
-    // takes one, so they occupy `spread` times more warps (latency hiding instead of 32 diverged
-    // chains per warp).
-    __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
-    const uint64_t n_items = *in_count;
-    const uint32_t per_block = MF_THREADS / spread;
-    const uint64_t item = (uint64_t)blockIdx.x * per_block + threadIdx.x / spread;
-    if ((uint64_t)blockIdx.x * per_block >= n_items) return;
-    if (item >= n_items || threadIdx.x % spread != 0) return;
-    const uint32_t t = threadIdx.x, L = ix.split_len;
-    const uint32_t r = in_list[item];
+__device__ __forceinline__ void
+map_second_read(const IndexView& ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
+                const uint32_t r, uint32_t* row, ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list,
+                unsigned long long* __restrict__ out_count) {
+    const uint32_t L = ix.split_len;
     const uint32_t h = __ldg(hdr + r);
     bool defer = (h & (PH_LONG | PH_BAD)) != 0 || ix.subst == nullptr;
     const uint32_t rlen = h & 0xFFFFFF;
-    uint32_t* row = s_fwd + t * STRIDE;
     uint32_t nn = 0;
-    uint32_t l_node[MAXN], l_vk[MAXN];
+    FlatList fl;                                           // per-read node list in registers
     if (!defer) {
         load_row<STRIDE, false>(rows, r, row_words, rlen, row, nullptr);
         const int npos = (int)(rlen - L + 1);
@@ -696,6 +797,7 @@ k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __
                 for (int k = 0; k < NW; k++) row[k] = y[k];
             }
             nn = 0;
+            fl.clear();
             uint32_t tp = NONE32, node = 0;
             const int pr = probe_window(ix, row, 0, tp, node);
             if (pr == PROBE_MULTI) break;
@@ -749,9 +851,8 @@ k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __
                     last_hit = c2 > 0 ? bw : min(bw, e - (int)L);
                 }
                 if (c1 + c2 > 0) {
-                    if (nn == MAXN) { ok = false; break; }
-                    l_node[nn] = node;
-                    l_vk[nn] = (uint32_t)(c1 + c2) | ((uint32_t)(mirror ? npos - 1 - last_hit : first_hit) << 16);
+                    if (nn == (uint32_t)FL_MAX) { ok = false; break; }
+                    fl.set(nn, node, (uint32_t)(c1 + c2) | ((uint32_t)(mirror ? npos - 1 - last_hit : first_hit) << 16));
                     nn++;
                 }
                 if (lim >= rlen) break;
@@ -772,39 +873,35 @@ k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __
     ReadSlot* out = slots + r;
     uint32_t n_out = 0;
     if (!defer) {
-        // a node met in two stretches (cyclic graph): sum the hits, keep the smallest position
-        for (uint32_t a = 1; a < nn; a++) {
-            for (uint32_t b = 0; b < a; b++) {
-                if (l_node[b] == l_node[a] && l_vk[b]) {
-                    const uint32_t x = l_vk[b], y = l_vk[a];
-                    l_vk[b] = ((x & 0xFFFF) + (y & 0xFFFF)) | (min(x >> 16, y >> 16) << 16);
-                    l_vk[a] = 0;
-                    break;
-                }
-            }
-        }
-        // keep flags, then ascending node order by ranks
-        uint32_t keepmask = 0;
-        for (uint32_t a = 0; a < nn; a++) {
-            const uint32_t vk = l_vk[a];
-            if (vk && keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + l_node[a]), rlen, L)) keepmask |= 1u << a;
-        }
-        n_out = __popc(keepmask);
-        if (n_out > (uint32_t)SLOT_IDS) defer = true;
-        if (!defer) {
-            for (uint32_t a = 0; a < nn; a++) {
-                if (!((keepmask >> a) & 1)) continue;
-                uint32_t rank = 0;
-                for (uint32_t b = 0; b < nn; b++) rank += ((keepmask >> b) & 1) && l_node[b] < l_node[a];
-                out->ids[rank] = l_node[a];
-            }
-        }
+        // a node met in two stretches (cyclic graph): after the sort they are neighbours; the last
+        // of a run takes the sum of the hits and the smallest position
+        fl.sort();
+        fl.merge_repeats();
+        n_out = flat_finalize(fl, ix, rlen, L, out);
     }
     if (defer) {
         out_list[atomicAdd(out_count, 1ull)] = r;
         return;
     }
     out->hdr = ST_OK | (n_out << 8);
+}
+
+// A fixed grid walks the device-side worklist (its length is only known on the device).  The
+// deferred reads are few and each is a long serial chain: only every `spread`-th thread takes one.
+template <int STRIDE>
+__global__ void __launch_bounds__(MF_THREADS)
+k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
+             const uint32_t* __restrict__ in_list, const unsigned long long* __restrict__ in_count, uint32_t spread,
+             ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list, unsigned long long* __restrict__ out_count) {
+    __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
+    const uint64_t n_items = *in_count;
+    const uint32_t per_block = MF_THREADS / spread;
+    if (threadIdx.x % spread != 0) return;
+    for (uint64_t base = (uint64_t)blockIdx.x * per_block; base < n_items; base += (uint64_t)gridDim.x * per_block) {
+        const uint64_t item = base + threadIdx.x / spread;
+        if (item < n_items)
+            map_second_read<STRIDE>(ix, rows, hdr, row_words, in_list[item], s_fwd + threadIdx.x * STRIDE, slots, out_list, out_count);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -940,9 +1037,13 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     }
     if (d_rows && !c->opt_single_map) {
         // stage 1: the clean-pass kernel; what it defers goes through the full kernel
-#define VSPE_M1(S, LP) k_map_first<S, LP><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, n_reads, d_slots, \
-                                                                        c->defer_list.p, c->counters.p)
-        if (cap <= 160) VSPE_M1(13, 16); else if (cap <= 256) VSPE_M1(19, 16); else VSPE_M1(23, 32);
+#define VSPE_M1(S, LP, FL) k_map_first<S, LP, FL><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, n_reads, d_slots, \
+                                                                                c->defer_list.p, c->counters.p)
+        if (c->opt_flat_walk) {
+            if (cap <= 160) VSPE_M1(13, 16, true); else if (cap <= 256) VSPE_M1(19, 16, true); else VSPE_M1(23, 32, true);
+        } else {
+            if (cap <= 160) VSPE_M1(13, 16, false); else if (cap <= 256) VSPE_M1(19, 16, false); else VSPE_M1(23, 32, false);
+        }
 #undef VSPE_M1
         VSPE_LAUNCH_CHECK(c);
         in_list = c->defer_list.p;
@@ -951,7 +1052,7 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
             // stage 1b: one-error-tolerant walk on the deferred reads; its leftovers go to stage 2
             uint32_t* list1b = c->defer_list.p + 2 * n_reads;
             const uint32_t spread2 = pow2_spread(c->opt_second_spread);
-            const uint32_t grid_s = (uint32_t)std::min<uint64_t>((n_reads * spread2 + MF_THREADS - 1) / MF_THREADS, 0x7FFFFFFFull);
+            const uint32_t grid_s = (uint32_t)std::min<uint64_t>((n_reads * spread2 + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 16);
 #define VSPE_M2(S) k_map_second<S><<<grid_s, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->defer_list.p, \
                                                                    c->counters.p + CNT_DEFER, spread2, d_slots, list1b, c->counters.p + CNT_DEFER2)
             if (cap <= 160) VSPE_M2(13); else if (cap <= 256) VSPE_M2(19); else VSPE_M2(23);
@@ -963,7 +1064,7 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     }
     // stage 2: the full seed-and-extend kernel (on the deferred reads, or on everything)
     const uint32_t list_spread = pow2_spread(c->opt_list_spread);
-    const uint32_t grid2 = in_list ? (uint32_t)std::min<uint64_t>((n_reads * list_spread + MF_THREADS - 1) / MF_THREADS, 0x7FFFFFFFull) : grid;
+    const uint32_t grid2 = in_list ? (uint32_t)std::min<uint64_t>((n_reads * list_spread + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 8) : grid;
 #define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid2, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
                                                                                row_words, n_reads, in_list, in_count, list_spread, d_slots, \
                                                                                c->worklist.p, c->counters.p)

@@ -80,6 +80,7 @@ struct ScanPackArgs {
     uint8_t* qbuf;                   // two-kernel mode: per (tile, warp) candidate queue, SP_QBYTES each
     unsigned long long* tile_tot;    // two-kernel mode: terminators per tile (count pass) ...
     const unsigned long long* tile_excl;   // ... and their exclusive prefix (pack pass)
+    unsigned long long* tile_full;   // two-kernel mode: set by the count pass when a warp queue overflows
 };
 
 
@@ -267,7 +268,7 @@ k_scan_pack(ScanPackArgs a) {
         if (lane == 0) *reinterpret_cast<uint32_t*>(gq) = qn;
         if (threadIdx.x == 0) {
             a.tile_tot[tile] = tile_total;
-            if (any_over) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_TILE_FULL);
+            if (any_over) atomicOr(a.tile_full, 1ull);
         }
         return;
     }
@@ -450,6 +451,8 @@ k_scan_pack(ScanPackArgs a) {
     SP_STAMP(5);
 }
 
+static int scan_pack_setup(Ctx* c);
+
 int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
               uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
               uint64_t* n_terms, unsigned long long* err_flags) {
@@ -462,12 +465,6 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
     VSPE_TRY(c->tile_base.reserve(n_tiles + 4));
     unsigned long long* status = reinterpret_cast<unsigned long long*>(c->tile_base.p);
     VSPE_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 4) * 8, c->stream));
-    if (!c->scan_pack_attr_set) {
-        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-        VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-        c->scan_pack_attr_set = true;
-    }
     ScanPackArgs a;
     a.buf = d_buf; a.n = n; a.head = head; a.status = status;
     a.ticket = reinterpret_cast<unsigned int*>(status + n_tiles + 1);
@@ -483,12 +480,12 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
         c->dbg_tiles = n_tiles;
     }
     // the dominant kernel is timed on its own (CUDA events on the launching stream)
-    if (!c->ev_k[0]) { VSPE_CUDA(cudaEventCreate(&c->ev_k[0])); VSPE_CUDA(cudaEventCreate(&c->ev_k[1])); }
-    VSPE_CUDA(cudaEventRecord(c->ev_k[0], c->stream));
+    VSPE_TRY(scan_pack_setup(c));
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[0][0], c->stream));
     a.qbuf = nullptr; a.tile_tot = nullptr; a.tile_excl = nullptr;
     k_scan_pack<0><<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
     VSPE_LAUNCH_CHECK(c);
-    VSPE_CUDA(cudaEventRecord(c->ev_k[1], c->stream));
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[0][1], c->stream));
     unsigned long long h_total = 0, h_err = 0;
     VSPE_CUDA(cudaMemcpyAsync(&h_total, a.total_out, 8, cudaMemcpyDeviceToHost, c->stream));
     VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -497,7 +494,7 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
     *err_flags = h_err;
     {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, c->ev_k[0], c->ev_k[1]) == cudaSuccess) { c->stats.ms_k_scan_pack += ms; c->stats.n_k_scan_pack++; }
+        if (cudaEventElapsedTime(&ms, c->ev_scan[0][0], c->ev_scan[0][1]) == cudaSuccess) { c->stats.ms_k_scan_pack += ms; c->stats.n_k_scan_pack++; }
     }
     const unsigned long long transient = ERRF_SLOTS_FULL | ERRF_TILE_FULL;
     if (h_err & transient) {
@@ -509,86 +506,104 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
 }
 
 // Two-kernel variant: count pass (no inter-tile dependency) -> device scan of the tile totals ->
-// the caller sizes the outputs exactly -> pack pass.  `prepare` runs the first two steps and
-// returns the terminator count; `finish` launches the pack pass.
+// the caller sizes the outputs exactly -> pack pass.  `prepare_launch` queues the first two steps
+// (no host synchronisation, so the count passes of both mates can be queued back to back),
+// `prepare_collect` returns the terminator count, `finish` launches the pack pass.  Scratch and
+// timing events are per mate: mate 1's count pass may run before mate 0's pack pass.
 void scan_pack_account(Ctx* c);
 
-int scan_pack_prepare(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms, unsigned long long* err_flags) {
-    *n_terms = 0;
-    *err_flags = 0;
-    if (n == 0) return VSPE_OK;
-    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
-    const uint64_t n_tiles = (n + head + SP_TILE - 1) / SP_TILE;
-    if (n_tiles > 0x7FFFFFFFull) { set_error("buffer too large for one scan launch"); return VSPE_ERR_LIMIT; }
-    VSPE_TRY(c->tile_base.reserve(2 * n_tiles + n_tiles / 1024 + 16));
-    VSPE_TRY(c->scan_q.reserve(n_tiles * SP_WARPS * SP_QBYTES + 64));
+static int scan_pack_setup(Ctx* c) {
     if (!c->scan_pack_attr_set) {
         VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
         VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
         VSPE_CUDA(cudaFuncSetAttribute(k_scan_pack<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
         c->scan_pack_attr_set = true;
     }
-    unsigned long long* tot = reinterpret_cast<unsigned long long*>(c->tile_base.p);
+    for (int m = 0; m < 2; m++)
+        for (int k = 0; k < 4; k++)
+            if (!c->ev_scan[m][k]) VSPE_CUDA(cudaEventCreate(&c->ev_scan[m][k]));
+    return VSPE_OK;
+}
+
+int scan_pack_prepare_launch(Ctx* c, int m, const uint8_t* d_buf, uint64_t n) {
+    if (n == 0) return VSPE_OK;
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
+    const uint64_t n_tiles = (n + head + SP_TILE - 1) / SP_TILE;
+    if (n_tiles > 0x7FFFFFFFull) { set_error("buffer too large for one scan launch"); return VSPE_ERR_LIMIT; }
+    VSPE_TRY(c->scan_tiles[m].reserve(2 * n_tiles + n_tiles / 1024 + 16));
+    VSPE_TRY(c->scan_q[m].reserve(n_tiles * SP_WARPS * SP_QBYTES + 64));
+    VSPE_TRY(scan_pack_setup(c));
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(c->scan_tiles[m].p);
     unsigned long long* excl = tot + n_tiles;
     unsigned long long* sums = excl + n_tiles;                 // [n_tiles / 2048 + 1] scratch, then [.. + 8] the grand total
     unsigned long long* d_total = sums + n_tiles / 1024 + 8;
     ScanPackArgs a = {};
     a.buf = d_buf; a.n = n; a.head = head; a.n_tiles = (uint32_t)n_tiles; a.counters = c->counters.p;
-    a.qbuf = c->scan_q.p; a.tile_tot = tot; a.tile_excl = excl;
+    a.qbuf = c->scan_q[m].p; a.tile_tot = tot; a.tile_excl = excl;
     a.row_words = 16; a.cap = 256;
-    if (!c->ev_k[2]) { VSPE_CUDA(cudaEventCreate(&c->ev_k[2])); VSPE_CUDA(cudaEventCreate(&c->ev_k[3])); }
-    VSPE_CUDA(cudaEventRecord(c->ev_k[2], c->stream));
+    a.tile_full = d_total + 2;
+    VSPE_CUDA(cudaMemsetAsync(a.tile_full, 0, 8, c->stream));
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[m][2], c->stream));
     k_scan_pack<1><<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
     VSPE_LAUNCH_CHECK(c);
-    VSPE_CUDA(cudaEventRecord(c->ev_k[3], c->stream));
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[m][3], c->stream));
     VSPE_TRY(device_scan_u64(c, tot, excl, n_tiles, sums, d_total));
-    unsigned long long h_total = 0, h_err = 0;
-    VSPE_CUDA(cudaMemcpyAsync(&h_total, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
-    VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
-    VSPE_CUDA(cudaStreamSynchronize(c->stream));
-    *n_terms = h_total;
-    *err_flags = h_err;
-    scan_pack_account(c);                                      // a pack launch of the previous mate / chunk is done by now
-    {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, c->ev_k[2], c->ev_k[3]) == cudaSuccess) { c->stats.ms_k_scan_count += ms; c->stats.n_k_scan_count++; }
-    }
-    if (h_err & ERRF_TILE_FULL) {
-        unsigned long long cleared = h_err & ~(unsigned long long)ERRF_TILE_FULL;
-        VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_ERR, &cleared, 8, cudaMemcpyHostToDevice, c->stream));
-        VSPE_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    c->scan_count_pending[m] = true;
     return VSPE_OK;
 }
 
-int scan_pack_finish(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
+int scan_pack_prepare_collect(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms, unsigned long long* err_flags) {
+    *n_terms = 0;
+    *err_flags = 0;
+    if (n == 0) return VSPE_OK;
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
+    const uint64_t n_tiles = (n + head + SP_TILE - 1) / SP_TILE;
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(c->scan_tiles[m].p);
+    unsigned long long* d_total = tot + 2 * n_tiles + n_tiles / 1024 + 8;
+    unsigned long long h[3] = {0, 0, 0};                       // grand total, (unused), queue-overflow flag of this mate's count pass
+    VSPE_CUDA(cudaMemcpyAsync(h, d_total, 24, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    *n_terms = h[0];
+    *err_flags = h[2] ? ERRF_TILE_FULL : 0;
+    scan_pack_account(c);                                      // everything queued before is done by now
+    return VSPE_OK;
+}
+
+int scan_pack_finish(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
                      uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t row_words, uint32_t cap) {
     if (n == 0) return VSPE_OK;
     const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
     const uint64_t n_tiles = (n + head + SP_TILE - 1) / SP_TILE;
-    unsigned long long* tot = reinterpret_cast<unsigned long long*>(c->tile_base.p);
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(c->scan_tiles[m].p);
     ScanPackArgs a = {};
     a.buf = d_buf; a.n = n; a.head = head; a.n_tiles = (uint32_t)n_tiles; a.counters = c->counters.p;
-    a.qbuf = c->scan_q.p; a.tile_tot = tot; a.tile_excl = tot + n_tiles;
+    a.qbuf = c->scan_q[m].p; a.tile_tot = tot; a.tile_excl = tot + n_tiles;
     a.line_base = line_base; a.rec_first = rec_first; a.n_slots = n_slots;
     a.seq_start = d_seq_start; a.seq_end = d_seq_end; a.rows = d_rows; a.hdr = d_hdr; a.row_words = row_words; a.cap = cap;
     a.total_out = tot + 2 * n_tiles + n_tiles / 1024 + 9;      // unused scratch word
-    if (!c->ev_k[0]) { VSPE_CUDA(cudaEventCreate(&c->ev_k[0])); VSPE_CUDA(cudaEventCreate(&c->ev_k[1])); }
-    // account the previous pack launch (its events have completed by now: every caller syncs in between)
-    VSPE_CUDA(cudaEventRecord(c->ev_k[0], c->stream));
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[m][0], c->stream));
     k_scan_pack<2><<<(uint32_t)n_tiles, SP_WARPS * 32, SP_SMEM, c->stream>>>(a);
     VSPE_LAUNCH_CHECK(c);
-    VSPE_CUDA(cudaEventRecord(c->ev_k[1], c->stream));
-    c->scan_pack_pending = true;
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[m][1], c->stream));
+    c->scan_pack_pending[m] = true;
     return VSPE_OK;
 }
 
-// fold the duration of the last pack launch into the stats (call after a stream sync)
+// fold the durations of the scan launches whose events have completed into the stats (call after
+// a stream sync; a launch still in flight stays pending)
 void scan_pack_account(Ctx* c) {
-    if (!c->scan_pack_pending) return;
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, c->ev_k[0], c->ev_k[1]) == cudaSuccess) { c->stats.ms_k_scan_pack += ms; c->stats.n_k_scan_pack++; }
-    c->scan_pack_pending = false;
+    for (int m = 0; m < 2; m++) {
+        float ms = 0;
+        if (c->scan_count_pending[m] && cudaEventQuery(c->ev_scan[m][3]) == cudaSuccess) {
+            if (cudaEventElapsedTime(&ms, c->ev_scan[m][2], c->ev_scan[m][3]) == cudaSuccess) { c->stats.ms_k_scan_count += ms; c->stats.n_k_scan_count++; }
+            c->scan_count_pending[m] = false;
+        }
+        if (c->scan_pack_pending[m] && cudaEventQuery(c->ev_scan[m][1]) == cudaSuccess) {
+            if (cudaEventElapsedTime(&ms, c->ev_scan[m][0], c->ev_scan[m][1]) == cudaSuccess) { c->stats.ms_k_scan_pack += ms; c->stats.n_k_scan_pack++; }
+            c->scan_pack_pending[m] = false;
+        }
+    }
+    cudaGetLastError();                                        // cudaEventQuery on an unfinished event is not an error here
 }
 
 }  // namespace vspe

@@ -249,8 +249,9 @@ int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint
               uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
               uint64_t* n_terms, unsigned long long* err_flags);
 
-int scan_pack_prepare(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms, unsigned long long* err_flags);
-int scan_pack_finish(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
+int scan_pack_prepare_launch(Ctx* c, int mate, const uint8_t* d_buf, uint64_t n);
+int scan_pack_prepare_collect(Ctx* c, int mate, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms, unsigned long long* err_flags);
+int scan_pack_finish(Ctx* c, int mate, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
                      uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t row_words, uint32_t cap);
 void scan_pack_account(Ctx* c);
 int device_scan_u64(Ctx* c, const unsigned long long* in, unsigned long long* out, uint64_t n, unsigned long long* sums,
