@@ -240,6 +240,16 @@ def _mk_fastq(seqs, nl=b"\n"):
     return b"".join(b"@r" + nl + s + nl + b"+" + nl + b"I" * len(s) + nl for s in seqs)
 
 
+def _decoy_fastq(seqs, seq_prefix):
+    out = []
+    for i, q in enumerate(seqs):
+        if seq_prefix:
+            out.append(b"@r%d\n" % i + seq_prefix + q + b"\n+\n@" + b"I" * len(q) + b"\n")
+        else:                                   # no '@' / '+' anywhere
+            out.append(b"r%d\n" % i + q + b"\n-\n" + b"I" * len(q) + b"\n")
+    return b"".join(out)
+
+
 @pytest.mark.parametrize("scan_mode", [0, 1, 3])
 def test_whole_path_edge_shapes(scan_mode):
     """Shapes that stress the tiled scan: thousands of tiny records per tile (fallback path),
@@ -265,6 +275,9 @@ def test_whole_path_edge_shapes(scan_mode):
         "long": (_mk_fastq(reads(300, 300, 1400)), _mk_fastq(reads(300, 100, 700))),
         "crlf": (_mk_fastq(reads(4000, 40, 160), b"\r\n"), _mk_fastq(reads(4000, 40, 160), b"\r")),
         "mixed": (_mk_fastq(reads(3000, 1, 330)), _mk_fastq(reads(2990, 1, 330))[:-1]),
+        # text that would fool any guess of the line phase: quality lines that start with '@' followed,
+        # two lines on, by "sequence" lines that start with '+'; and headers without '@'
+        "decoy": (_decoy_fastq(reads(25000, 35, 90), b"+"), _decoy_fastq(reads(25000, 35, 90), b"")),
     }
     for name, (f, r) in cases.items():
         ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, 31, options={"scan_mode": scan_mode, "chunk_mb": 1})

@@ -39,20 +39,21 @@ __device__ __forceinline__ ListRef list_of(const uint32_t* s, const uint32_t* __
     return r;
 }
 
+// keys are dense offsets < 2 * N * N <= 2^32 (count_pairs checks), so 32-bit arithmetic is exact
 template <class F>
-__device__ __forceinline__ void for_each_key(const ListRef& l, const ListRef& r, uint64_t N, F fn) {
-    const uint64_t NN = N * N;
+__device__ __forceinline__ void for_each_key(const ListRef& l, const ListRef& r, uint32_t N, F fn) {
+    const uint32_t NN = N * N;
     for (uint32_t a = 0; a < l.n; a++) {
-        uint64_t ia = l.ids[a];
-        for (uint32_t b = a; b < l.n; b++) fn(NN + ia * N + l.ids[b]);
+        const uint32_t row = NN + l.ids[a] * N;
+        for (uint32_t b = a; b < l.n; b++) fn(row + l.ids[b]);
     }
     for (uint32_t a = 0; a < r.n; a++) {
-        uint64_t ia = r.ids[a];
-        for (uint32_t b = a; b < r.n; b++) fn(NN + ia * N + r.ids[b]);
+        const uint32_t row = NN + r.ids[a] * N;
+        for (uint32_t b = a; b < r.n; b++) fn(row + r.ids[b]);
     }
     for (uint32_t a = 0; a < l.n; a++) {
-        uint64_t ia = l.ids[a];
-        for (uint32_t b = 0; b < r.n; b++) fn(ia * N + r.ids[b]);
+        const uint32_t row = l.ids[a] * N;
+        for (uint32_t b = 0; b < r.n; b++) fn(row + r.ids[b]);
     }
 }
 
@@ -116,7 +117,7 @@ k_pair_count(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uin
             if (cls == 0) {
                 ListRef l = list_of(sf, spill), rr = list_of(sr, spill);
                 uint32_t m = 0;
-                for_each_key(l, rr, N, [&](uint64_t key) { atomicAdd(&s_hist[key >> low_bits], 1u); m++; });
+                for_each_key(l, rr, (uint32_t)N, [&](uint32_t key) { atomicAdd(&s_hist[key >> low_bits], 1u); m++; });
                 c_keys += m;
                 c_used++;
             } else if (cls == 1) {
@@ -213,10 +214,10 @@ k_pair_emit(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uint
             const uint32_t* sr = st + (32 + lane) * STAGE_STRIDE;
             if (pair_class(sf[0], sr[0]) == 0) {
                 ListRef l = list_of(sf, spill), rr = list_of(sr, spill);
-                for_each_key(l, rr, N, [&](uint64_t key) {
-                    const uint32_t b = (uint32_t)(key >> low_bits);
+                for_each_key(l, rr, (uint32_t)N, [&](uint32_t key) {
+                    const uint32_t b = key >> low_bits;
                     const uint32_t o = atomicAdd(&s_hist[b], 1u);
-                    keys[s_base[b] + o] = (uint32_t)key;
+                    keys[s_base[b] + o] = key;
                 });
             }
         }
@@ -282,8 +283,8 @@ int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total
     c->stats.total_pairs += total;
     if (total == 0) return VSPE_OK;
     const uint64_t cells = 2 * N * N;
-    if (cells > (1ull << 32)) { set_error("dense count matrices need 2*N*N <= 2^32 (N=%llu); sparse mode not built yet", (unsigned long long)N); return VSPE_ERR_LIMIT; }
-    uint32_t low_bits = 7;
+    if (cells >= (1ull << 32)) { set_error("dense count matrices need 2*N*N <= 2^32 (N=%llu); sparse mode not built yet", (unsigned long long)N); return VSPE_ERR_LIMIT; }
+    uint32_t low_bits = (uint32_t)std::max<int64_t>(7, std::min<int64_t>(15, c->opt_count_low_bits));
     while (((cells + (1ull << low_bits) - 1) >> low_bits) > 2048 && low_bits < 15) low_bits++;
     uint64_t nbk = cells ? ((cells + (1ull << low_bits) - 1) >> low_bits) : 1;
     if (nbk == 0) nbk = 1;
