@@ -25,6 +25,8 @@ VARIANTS = [
     {"scan_mode": 3},                                   # fused scan+pack with look-back
     {"scan_mode": 0, "second_spread": 4, "list_spread": 8},   # deferred reads spread over more warps
     {"scan_mode": 0, "flat_walk": 0},                   # nested walk loops in k_map_first
+    {"scan_mode": 0, "fast_tier": 0},                   # deferred reads straight to the all-windows kernel
+    {"scan_mode": 0, "fast_tier": 0, "subst": 0},
 ]
 
 
@@ -288,9 +290,9 @@ def test_whole_path_edge_shapes(scan_mode):
             assert stats[k] == v, (name, k)
 
 
-@pytest.mark.parametrize("subst,full_second", [(1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("subst,full_second,fast_tier", [(1, 0, 1), (0, 1, 1), (1, 1, 1), (1, 0, 0), (0, 0, 0)])
 @pytest.mark.parametrize("sub_rate", [0.002, 0.01, 0.04])
-def test_noisy_reads_match_c_oracle(subst, full_second, sub_rate):
+def test_noisy_reads_match_c_oracle(subst, full_second, fast_tier, sub_rate):
     """1 % and 4 % substitution rates: several errors per read, errors next to node ends and to
     each other, reads that follow another strain's bubble arm after an error."""
     for name, pairs in (("C2", 4000), ("C3", 3000)):
@@ -299,7 +301,7 @@ def test_noisy_reads_match_c_oracle(subst, full_second, sub_rate):
         g, genomes, ab = synth.make_graph(cfg, rng, 10.0)
         f, r = synth.make_reads(genomes, ab, cfg.read_len, pairs, cfg.k, rng, sub_rate=sub_rate)
         gfa = g.to_gfa()
-        ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"subst": subst, "full_second": full_second})
+        ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"subst": subst, "full_second": full_second, "fast_tier": fast_tier})
         onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
         assert np.array_equal(node.astype(np.int64), onode), name
         assert np.array_equal(short.astype(np.int64), oshort), name

@@ -84,6 +84,7 @@ struct Ctx {
     int64_t opt_chunk_mb = 256;
     int64_t opt_list_spread = 2;       // list-driven k_map_fast: one read per this many threads (1, 2, 4, 8 ...)
     int64_t opt_count_low_bits = 7;    // dense counting: log2 of the matrix cells per radix bucket (7..15; raised for large graphs)
+    int64_t opt_fast_tier = 1;         // 0: reads the walk kernels defer go straight to k_map_windows (no k_map_fast)
     int64_t opt_flat_walk = 1;         // k_map_first: flat walk loop (0: nested stretch / chunk loops)
     int64_t opt_second_spread = 1;     // k_map_second: one read per this many threads (power of two <= 32)
     int64_t opt_no_second = 0;         // 1: skip k_map_second

@@ -772,72 +772,85 @@ map_second_read(const IndexView& ix, const uint32_t* __restrict__ rows, const ui
     if (!defer) {
         load_row<STRIDE, false>(rows, r, row_words, rlen, row, nullptr);
         const int npos = (int)(rlen - L + 1);
-        bool resolved = false;
-        for (int attempt = 0; attempt < 2 && !resolved; attempt++) {
-            const bool mirror = attempt == 1;
-            if (mirror) {
-                // reverse-complement the packed row in place
-                constexpr int NW = STRIDE - 3;
-                const uint32_t nwords = (rlen + 15) >> 4, pad = 16 * nwords - rlen;
-                uint32_t y[NW];
-                uint32_t prev = 0;
+        // Which end seeds?  Window 0 of the read, else (error in the first split_len bases) window 0 of
+        // its reverse complement.  The walk itself then runs ONCE, for all threads of the warp together.
+        bool resolved = false, mirror = false;
+        uint32_t tp = NONE32, node = 0;
+        int pr = probe_window(ix, row, 0, tp, node);
+        if (pr == PROBE_MISS) {
+            // reverse-complement the packed row in place
+            constexpr int NW = STRIDE - 3;
+            const uint32_t nwords = (rlen + 15) >> 4, pad = 16 * nwords - rlen;
+            uint32_t y[NW];
+            uint32_t prev = 0;
 #pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    y[k] = 0;
-                    const int kk = NW - 1 - k;
-                    if ((uint32_t)kk >= nwords) continue;
-                    uint32_t rv = __brev(row[kk]);
-                    rv = (((rv & 0x55555555u) << 1) | ((rv >> 1) & 0x55555555u)) ^ 0xAAAAAAAAu;
-                    const int j = (int)nwords - 1 - kk;
-                    if (j > 0) y[j - 1] = __funnelshift_r(prev, rv, 2 * pad);
-                    prev = rv;
-                }
-                if (nwords) y[nwords - 1] = __funnelshift_r(prev, 0u, 2 * pad);
-#pragma unroll
-                for (int k = 0; k < NW; k++) row[k] = y[k];
+            for (int k = 0; k < NW; k++) {
+                y[k] = 0;
+                const int kk = NW - 1 - k;
+                if ((uint32_t)kk >= nwords) continue;
+                uint32_t rv = __brev(row[kk]);
+                rv = (((rv & 0x55555555u) << 1) | ((rv >> 1) & 0x55555555u)) ^ 0xAAAAAAAAu;
+                const int j = (int)nwords - 1 - kk;
+                if (j > 0) y[j - 1] = __funnelshift_r(prev, rv, 2 * pad);
+                prev = rv;
             }
-            nn = 0;
-            fl.clear();
-            uint32_t tp = NONE32, node = 0;
-            const int pr = probe_window(ix, row, 0, tp, node);
-            if (pr == PROBE_MULTI) break;
-            if (pr == PROBE_MISS) continue;                      // error in this end's first window: try the other end
-            bool ok = true, err = false;
-            int e = 0;
-            uint32_t rb = 0;
-            uint32_t i0 = 0, p = L;
-            while (ok) {
-                const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
-                const bool rcs = tp >= s1;
-                const uint32_t q = 2 * node + (rcs ? 1u : 0u);
-                const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
-                const int delta = (int)tp - (int)i0;
-                const uint32_t lim = min(rlen, (uint32_t)((int)send - delta));   // read position where the strand ends
-                // a strand entered after the error still holds windows covering it if it starts at or before e
-                if (err && (int)i0 <= e) {
-                    const uint32_t te = (uint32_t)(e + delta);
-                    if ((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u) { ok = false; break; }
-                }
-                while (p < lim) {
-                    const uint32_t n = min(32u, lim - p);
-                    uint64_t x = read64(row, p) ^ extract64(ix.text, (uint64_t)((int)p + delta));
-                    if (n < 32) x &= (1ull << (2 * n)) - 1;
-                    if (x) {
-                        const uint32_t off = (uint32_t)(__ffsll((long long)x) - 1) >> 1;
-                        if (err || (x & ~(3ull << (2 * off)))) { ok = false; break; }   // second mismatch
+            if (nwords) y[nwords - 1] = __funnelshift_r(prev, 0u, 2 * pad);
+#pragma unroll
+            for (int k = 0; k < NW; k++) row[k] = y[k];
+            mirror = true;
+            pr = probe_window(ix, row, 0, tp, node);
+        }
+        fl.clear();
+        // (PROBE_MULTI, or both ends miss: a real complication, the full kernel decides)
+        bool running = pr == PROBE_UNIQUE;
+        bool err = false;
+        int e = 0;
+        uint32_t rb = 0;
+        uint32_t i0 = 0, p = L, q = 0, lim = 0;
+        int delta = 0;
+        // strand of window i0 = text position tp; false if the error's windows cannot be proven to miss there
+        auto enter = [&]() -> bool {
+            const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
+            const bool rcs = tp >= s1;
+            q = 2 * node + (rcs ? 1u : 0u);
+            const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
+            delta = (int)tp - (int)i0;
+            lim = min(rlen, (uint32_t)((int)send - delta));      // read position where the strand ends
+            // a strand entered after the error still holds windows covering it if it starts at or before e
+            if (err && (int)i0 <= e) {
+                const uint32_t te = (uint32_t)(e + delta);
+                if ((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u) return false;
+            }
+            return true;
+        };
+        if (running && !enter()) running = false;
+        // flat loop: every turn compares up to 32 bases and, when the stretch is complete, books it and
+        // steps to the successor strand
+        while (running) {
+            if (p < lim) {
+                const uint32_t n = min(32u, lim - p);
+                uint64_t x = read64(row, p) ^ extract64(ix.text, (uint64_t)((int)p + delta));
+                if (n < 32) x &= (1ull << (2 * n)) - 1;
+                bool ok = true;
+                if (x) {
+                    const uint32_t off = (uint32_t)(__ffsll((long long)x) - 1) >> 1;
+                    if (err || (x & ~(3ull << (2 * off)))) ok = false;          // second mismatch
+                    else {
                         err = true;
                         e = (int)(p + off);
                         rb = (row[(uint32_t)e >> 4] >> (((uint32_t)e & 15) * 2)) & 3u;
                         const uint32_t te = (uint32_t)(e + delta);
-                        if ((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u) { ok = false; break; }
+                        if ((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u) ok = false;
                     }
-                    const uint32_t u = (uint32_t)((int)p + delta) - L + 1;     // text position of the first window ending here
-                    const uint32_t ub = __funnelshift_r(__ldg(ix.uniq + (u >> 5)), __ldg(ix.uniq + (u >> 5) + 1), u & 31);
-                    const uint32_t m32 = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
-                    if ((ub & m32) != m32) { ok = false; break; }
-                    p += n;
                 }
-                if (!ok) break;
+                const uint32_t u = (uint32_t)((int)p + delta) - L + 1;     // text position of the first window ending here
+                const uint32_t ub = __funnelshift_r(__ldg(ix.uniq + (u >> 5)), __ldg(ix.uniq + (u >> 5) + 1), u & 31);
+                const uint32_t m32 = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
+                if ((ub & m32) != m32) ok = false;
+                if (!ok) { running = false; break; }
+                p += n;
+            }
+            if (p >= lim) {
                 // windows [a, bw] of this node are resolved; those covering e are proven misses
                 const int a = (int)i0, bw = (int)lim - (int)L;
                 int c1 = bw - a + 1, c2 = 0, last_hit = bw, first_hit = a;
@@ -851,22 +864,21 @@ map_second_read(const IndexView& ix, const uint32_t* __restrict__ rows, const ui
                     last_hit = c2 > 0 ? bw : min(bw, e - (int)L);
                 }
                 if (c1 + c2 > 0) {
-                    if (nn == (uint32_t)FL_MAX) { ok = false; break; }
+                    if (nn == (uint32_t)FL_MAX) { running = false; break; }
                     fl.set(nn, node, (uint32_t)(c1 + c2) | ((uint32_t)(mirror ? npos - 1 - last_hit : first_hit) << 16));
                     nn++;
                 }
-                if (lim >= rlen) break;
+                if (lim >= rlen) { resolved = true; running = false; break; }
                 // the strand ended before the read: successor window for the read's next base
                 const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
                 const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
-                if (sc.x == NONE32) { ok = false; break; }
+                if (sc.x == NONE32) { running = false; break; }
                 i0 = lim - L + 1;
                 tp = sc.x;
                 node = sc.y;
                 p = lim + 1;
+                if (!enter()) { running = false; break; }
             }
-            if (!ok) break;                                      // a real complication: the full kernel decides
-            resolved = true;
         }
         if (!resolved) defer = true;
     }
@@ -1062,28 +1074,39 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
             in_count = c->counters.p + CNT_DEFER2;
         }
     }
+    // what stage 3 reads: the reads stage 2 gave up on -- or, without stage 2, everything stage 1 deferred
+    const uint32_t* win_list = c->worklist.p;
+    const unsigned long long* win_count = c->counters.p + CNT_WORK;
+    const bool skip_fast = d_rows && in_list && !c->opt_fast_tier;
+    if (skip_fast) {
+        win_list = in_list;
+        win_count = in_count;
+    }
     // stage 2: the full seed-and-extend kernel (on the deferred reads, or on everything)
     const uint32_t list_spread = pow2_spread(c->opt_list_spread);
     const uint32_t grid2 = in_list ? (uint32_t)std::min<uint64_t>((n_reads * list_spread + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 8) : grid;
 #define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid2, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
                                                                                row_words, n_reads, in_list, in_count, list_spread, d_slots, \
                                                                                c->worklist.p, c->counters.p)
-    if (d_rows) {
+    if (skip_fast) {
+        // (stage 2 skipped: the deferred reads go straight to the all-windows kernel)
+    } else if (d_rows) {
         if (cap <= 160) VSPE_MF(13, 16, true); else if (cap <= 256) VSPE_MF(19, 16, true); else VSPE_MF(23, 32, true);
+        VSPE_LAUNCH_CHECK(c);
     } else {
         if (cap <= 160) VSPE_MF(13, 16, false); else if (cap <= 256) VSPE_MF(19, 16, false); else VSPE_MF(23, 32, false);
+        VSPE_LAUNCH_CHECK(c);
     }
 #undef VSPE_MF
-    VSPE_LAUNCH_CHECK(c);
     if (d_rows) {
         // stage 3: what stage 2 could not prove (repeats, > 16 nodes): one warp per read, every
         // window looked up, exact for any postings multiplicity; only reads that do not fit the
         // 2-bit rows at all (non-ACGT, very long) are left for the ASCII tier
         if (!c->spill.p) VSPE_TRY(c->spill.reserve(4u << 20));
         uint32_t* list2 = c->defer_list.p + n_reads;
-        const uint32_t wgrid = (uint32_t)std::min<uint64_t>((n_reads + MW_WARPS - 1) / MW_WARPS, (uint64_t)c->sm_count * 8);
-#define VSPE_MW(S) k_map_windows<S><<<wgrid, MW_WARPS * 32, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->worklist.p, \
-                                                                      c->counters.p + CNT_WORK, d_slots, list2, \
+        const uint32_t wgrid = (uint32_t)std::min<uint64_t>((n_reads + MW_WARPS - 1) / MW_WARPS, (uint64_t)c->sm_count * 16);
+#define VSPE_MW(S) k_map_windows<S><<<wgrid, MW_WARPS * 32, 0, c->stream>>>(v, d_rows, d_hdr, row_words, win_list, \
+                                                                      win_count, d_slots, list2, \
                                                                       c->counters.p + CNT_WORK2, c->spill.p, c->spill.cap, c->counters.p)
         if (cap <= 160) VSPE_MW(13); else if (cap <= 256) VSPE_MW(19); else VSPE_MW(23);
 #undef VSPE_MW

@@ -422,8 +422,8 @@ k_scan_pack(ScanPackArgs a) {
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
-                const int left = (int)nb - 4 * q;                       // valid bytes in this word
-                const uint32_t vm = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << (8 * left)) - 1);
+                // mask of the valid bytes of this word: 4 + 4q - nb of its top bytes lie beyond the lane's bases
+                const uint32_t vm = __funnelshift_rc(0xFFFFFFFFu, 0u, 8u * (uint32_t)max(4 + 4 * q - (int)nb, 0));
                 const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
                 // the only byte with code k is "ACTG"[k] = 0x41 + 2k (+15 when k == 2)
                 const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
