@@ -25,6 +25,8 @@ VARIANTS = [
     {"scan_mode": 3},                                   # fused scan+pack with look-back
     {"scan_mode": 0, "second_spread": 4, "list_spread": 8},   # deferred reads spread over more warps
     {"scan_mode": 0, "flat_walk": 0},                   # nested walk loops in k_map_first
+    {"scan_mode": 0, "map_general": 0},                 # lean walk kernels (reads with > 6 stretches deferred)
+    {"scan_mode": 0, "map_general": 1},                 # general walk kernels (up to 16 stretches in place)
     {"scan_mode": 0, "fast_tier": 0},                   # deferred reads straight to the all-windows kernel
     {"scan_mode": 0, "fast_tier": 0, "subst": 0},
 ]

@@ -326,6 +326,7 @@ int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total
         VSPE_CUDA(cudaMemcpyAsync(&h_keys, c->counters.p + CNT_KEYS, 8, cudaMemcpyDeviceToHost, st));
         VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, st));
         VSPE_CUDA(cudaStreamSynchronize(st));
+        VSPE_TRY(adapt_map_variant(c));
         c->last_err_flags = h_err;                             // every scan / map kernel of this call ran before
         c->err_flags_fresh = true;
         uint64_t n_keys = h_keys - c->keys_seen;

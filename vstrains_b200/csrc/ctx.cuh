@@ -15,6 +15,7 @@ enum Counter {
     CNT_DEFER,               // reads k_map_first deferred to k_map_fast
     CNT_WORK2,               // reads k_map_windows left for the ASCII tier
     CNT_DEFER2,              // reads k_map_second left for k_map_fast
+    CNT_BIG,                 // sampled reads of the last k_map_first launch with more than FL_MAX stretches
     CNT_COUNT_
 };
 static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16;
@@ -84,6 +85,10 @@ struct Ctx {
     int64_t opt_chunk_mb = 256;
     int64_t opt_list_spread = 2;       // list-driven k_map_fast: one read per this many threads (1, 2, 4, 8 ...)
     int64_t opt_count_low_bits = 7;    // dense counting: log2 of the matrix cells per radix bucket (7..15; raised for large graphs)
+    int64_t opt_map_general = -1;      // walk kernels: -1 adaptive, 0 lean (defer reads with > 6 stretches), 1 general
+    bool map_general = false;          // adaptive choice for the next launch
+    bool big_pending = false;          // CNT_BIG of the last k_map_first launch has not been looked at yet
+    uint64_t big_sampled = 0;          // reads that launch sampled
     int64_t opt_fast_tier = 1;         // 0: reads the walk kernels defer go straight to k_map_windows (no k_map_fast)
     int64_t opt_flat_walk = 1;         // k_map_first: flat walk loop (0: nested stretch / chunk loops)
     int64_t opt_second_spread = 1;     // k_map_second: one read per this many threads (power of two <= 32)

@@ -46,6 +46,113 @@ __device__ __forceinline__ bool keep_node_f(uint32_t v, uint32_t kmin, uint32_t 
     return (int)v >= sat || (long long)v * rlen >= ab;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-read node list of the walk kernels, in REGISTERS: up to FL_MAX entries (node << 32 | v | kmin << 16),
+// empty = all ones.  Appends are predicated register writes; one fixed 12-exchange network sorts
+// the list by node index at the end, so duplicates become neighbours and the output rank of a kept
+// node is a popcount -- no data-dependent loops, every thread of the warp runs the same code.
+// ---------------------------------------------------------------------------------------------
+static constexpr int FL_MAX = 6;
+static constexpr uint32_t BIG_SAMPLE_BLOCKS = 64;          // k_map_first blocks that report reads with > FL_MAX stretches
+static constexpr uint64_t FL_EMPTY = ~0ull;
+
+struct FlatList {
+    uint64_t e[FL_MAX];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < FL_MAX; i++) e[i] = FL_EMPTY;
+    }
+    __device__ __forceinline__ void set(uint32_t at, uint32_t node, uint32_t vk) {
+        const uint64_t x = ((uint64_t)node << 32) | vk;
+#pragma unroll
+        for (int i = 0; i < FL_MAX; i++) if (at == (uint32_t)i) e[i] = x;
+    }
+    __device__ __forceinline__ void cex(int i, int j) {
+        const uint64_t a = e[i], b = e[j];
+        e[i] = a < b ? a : b;
+        e[j] = a < b ? b : a;
+    }
+    __device__ __forceinline__ void sort() {
+        cex(0, 5); cex(1, 3); cex(2, 4);
+        cex(1, 2); cex(3, 4);
+        cex(0, 3); cex(2, 5);
+        cex(0, 1); cex(2, 3); cex(4, 5);
+        cex(1, 2); cex(3, 4);
+    }
+    // sorted list: fold every run of equal nodes into its last entry (hits add up, smallest position wins)
+    __device__ __forceinline__ void merge_repeats() {
+#pragma unroll
+        for (int i = 0; i + 1 < FL_MAX; i++) {
+            if (e[i + 1] != FL_EMPTY && (uint32_t)(e[i] >> 32) == (uint32_t)(e[i + 1] >> 32)) {
+                const uint32_t x = (uint32_t)e[i], y = (uint32_t)e[i + 1];
+                const uint32_t vk = ((x & 0xFFFF) + (y & 0xFFFF)) | (min(x >> 16, y >> 16) << 16);
+                e[i + 1] = (e[i + 1] & 0xFFFFFFFF00000000ull) | vk;
+                e[i] = FL_EMPTY;
+            }
+        }
+    }
+    // copy the register entries to the thread-local arrays of the general path
+    __device__ __forceinline__ void spill_to(uint32_t* l_node, uint32_t* l_vk) const {
+#pragma unroll
+        for (int i = 0; i < FL_MAX; i++) { l_node[i] = (uint32_t)(e[i] >> 32); l_vk[i] = (uint32_t)e[i]; }
+    }
+    // two stretches of the same node (cyclic graph)?
+    __device__ __forceinline__ bool has_repeat() const {
+        bool r = false;
+#pragma unroll
+        for (int i = 0; i + 1 < FL_MAX; i++) r |= e[i + 1] != FL_EMPTY && (uint32_t)(e[i] >> 32) == (uint32_t)(e[i + 1] >> 32);
+        return r;
+    }
+};
+
+// saturation predicate over a sorted list; writes the kept node indices in ascending order
+__device__ __forceinline__ uint32_t flat_finalize(const FlatList& fl, const IndexView& ix, uint32_t rlen, uint32_t L, ReadSlot* out) {
+    uint32_t keepmask = 0;
+#pragma unroll
+    for (int i = 0; i < FL_MAX; i++) {
+        if (fl.e[i] != FL_EMPTY) {
+            const uint32_t node = (uint32_t)(fl.e[i] >> 32), vk = (uint32_t)fl.e[i];
+            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) keepmask |= 1u << i;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < FL_MAX; i++)
+        if ((keepmask >> i) & 1) out->ids[__popc(keepmask & ((1u << i) - 1))] = (uint32_t)(fl.e[i] >> 32);
+    return (uint32_t)__popc(keepmask);
+}
+
+// The general case (more than FL_MAX stretches: graphs with many short nodes per read): the list
+// lives in thread-local arrays; repeats are merged (or reported), then the same predicate and an
+// O(n^2) rank.  Returns false if the read must go to the next tier.
+__device__ __noinline__ bool list_finalize_slow(uint32_t* l_node, uint32_t* l_vk, uint32_t nn, bool merge, const IndexView& ix,
+                                                uint32_t rlen, uint32_t L, ReadSlot* out, uint32_t& n_out) {
+    for (uint32_t a = 1; a < nn; a++) {
+        for (uint32_t b = 0; b < a; b++) {
+            if (l_node[b] == l_node[a] && l_vk[b]) {
+                if (!merge) return false;
+                const uint32_t x = l_vk[b], y = l_vk[a];
+                l_vk[b] = ((x & 0xFFFF) + (y & 0xFFFF)) | (min(x >> 16, y >> 16) << 16);
+                l_vk[a] = 0;
+                break;
+            }
+        }
+    }
+    uint32_t keepmask = 0;
+    for (uint32_t a = 0; a < nn; a++) {
+        const uint32_t vk = l_vk[a];
+        if (vk && keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + l_node[a]), rlen, L)) keepmask |= 1u << a;
+    }
+    n_out = __popc(keepmask);
+    if (n_out > (uint32_t)SLOT_IDS) return false;
+    for (uint32_t a = 0; a < nn; a++) {
+        if (!((keepmask >> a) & 1)) continue;
+        uint32_t rank = 0;
+        for (uint32_t b = 0; b < nn; b++) rank += ((keepmask >> b) & 1) && l_node[b] < l_node[a];
+        out->ids[rank] = l_node[a];
+    }
+    return true;
+}
+
 // 64 bits (32 bases) of a packed read row starting at base b (row has 2 pad words)
 __device__ __forceinline__ uint64_t read64(const uint32_t* row, uint32_t b) {
     uint32_t w = b >> 4, s = (b & 15) * 2;
@@ -492,7 +599,16 @@ map_fast_block(const IndexView& ix, const uint8_t* __restrict__ buf, const uint6
         if (rlen < L) { out->hdr = ST_SHORT; return; }
     }
     uint32_t n_out = 0;
-    if (!bail) {
+    if (!bail && nn <= (uint32_t)FL_MAX) {
+        // the common case: up to FL_MAX distinct nodes (list_add merged repeats) -- sort network,
+        // saturation predicate, ranks by popcount
+        FlatList fl;
+#pragma unroll
+        for (int i = 0; i < FL_MAX; i++)
+            fl.e[i] = (uint32_t)i < nn ? (((uint64_t)s_node[i][t] << 32) | s_vk[i][t]) : FL_EMPTY;
+        fl.sort();
+        n_out = flat_finalize(fl, ix, rlen, L, out);
+    } else if (!bail) {
         // saturation predicate per node, then ascending node order (as enumerate(nodes) gives) from
         // ranks instead of a data-dependent sort
         uint32_t keepmask = 0;
@@ -545,81 +661,16 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-read node list of the walk kernels, in REGISTERS: up to FL_MAX entries (node << 32 | v | kmin << 16),
-// empty = all ones.  Appends are predicated register writes; one fixed 12-exchange network sorts
-// the list by node index at the end, so duplicates become neighbours and the output rank of a kept
-// node is a popcount -- no data-dependent loops, every thread of the warp runs the same code.
-// ---------------------------------------------------------------------------------------------
-static constexpr int FL_MAX = 6;
-static constexpr uint64_t FL_EMPTY = ~0ull;
-
-struct FlatList {
-    uint64_t e[FL_MAX];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int i = 0; i < FL_MAX; i++) e[i] = FL_EMPTY;
-    }
-    __device__ __forceinline__ void set(uint32_t at, uint32_t node, uint32_t vk) {
-        const uint64_t x = ((uint64_t)node << 32) | vk;
-#pragma unroll
-        for (int i = 0; i < FL_MAX; i++) if (at == (uint32_t)i) e[i] = x;
-    }
-    __device__ __forceinline__ void cex(int i, int j) {
-        const uint64_t a = e[i], b = e[j];
-        e[i] = a < b ? a : b;
-        e[j] = a < b ? b : a;
-    }
-    __device__ __forceinline__ void sort() {
-        cex(0, 5); cex(1, 3); cex(2, 4);
-        cex(1, 2); cex(3, 4);
-        cex(0, 3); cex(2, 5);
-        cex(0, 1); cex(2, 3); cex(4, 5);
-        cex(1, 2); cex(3, 4);
-    }
-    // sorted list: fold every run of equal nodes into its last entry (hits add up, smallest position wins)
-    __device__ __forceinline__ void merge_repeats() {
-#pragma unroll
-        for (int i = 0; i + 1 < FL_MAX; i++) {
-            if (e[i + 1] != FL_EMPTY && (uint32_t)(e[i] >> 32) == (uint32_t)(e[i + 1] >> 32)) {
-                const uint32_t x = (uint32_t)e[i], y = (uint32_t)e[i + 1];
-                const uint32_t vk = ((x & 0xFFFF) + (y & 0xFFFF)) | (min(x >> 16, y >> 16) << 16);
-                e[i + 1] = (e[i + 1] & 0xFFFFFFFF00000000ull) | vk;
-                e[i] = FL_EMPTY;
-            }
-        }
-    }
-    // two stretches of the same node (cyclic graph)?
-    __device__ __forceinline__ bool has_repeat() const {
-        bool r = false;
-#pragma unroll
-        for (int i = 0; i + 1 < FL_MAX; i++) r |= e[i + 1] != FL_EMPTY && (uint32_t)(e[i] >> 32) == (uint32_t)(e[i + 1] >> 32);
-        return r;
-    }
-};
-
-// saturation predicate over a sorted list; writes the kept node indices in ascending order
-__device__ __forceinline__ uint32_t flat_finalize(const FlatList& fl, const IndexView& ix, uint32_t rlen, uint32_t L, ReadSlot* out) {
-    uint32_t keepmask = 0;
-#pragma unroll
-    for (int i = 0; i < FL_MAX; i++) {
-        if (fl.e[i] != FL_EMPTY) {
-            const uint32_t node = (uint32_t)(fl.e[i] >> 32), vk = (uint32_t)fl.e[i];
-            if (keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + node), rlen, L)) keepmask |= 1u << i;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < FL_MAX; i++)
-        if ((keepmask >> i) & 1) out->ids[__popc(keepmask & ((1u << i) - 1))] = (uint32_t)(fl.e[i] >> 32);
-    return (uint32_t)__popc(keepmask);
-}
-
-// ---------------------------------------------------------------------------------------------
 // k_map_first: the common case only.  Packs nothing (rows come from k_scan_pack), runs ONE clean
 // forward pass -- seed window 0, extend, walk successors -- and finishes the read if that pass
 // proves every window.  Anything else (a miss, a mismatch, a repeat, too many nodes) defers the
 // read, untouched, to k_map_fast via a worklist, so the two populations never share a warp.
 // ---------------------------------------------------------------------------------------------
-template <int STRIDE, int LPR, bool FLAT>
+// GENERAL: reads with more than FL_MAX stretches keep the extra entries in thread-local arrays and
+// finish in the O(n^2) path; otherwise they are deferred.  The host picks the variant from the share
+// of such reads in the previous launch (CNT_BIG, sampled in the first blocks): graphs with long nodes
+// run the lean variant, graphs with many short nodes per read the general one.
+template <int STRIDE, int LPR, bool FLAT, bool GENERAL>
 __global__ void __launch_bounds__(MF_THREADS)
 k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
             uint64_t n_reads, ReadSlot* __restrict__ slots, uint32_t* __restrict__ defer_list,
@@ -653,7 +704,10 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
     }
     const uint32_t* row = s_fwd + t * STRIDE;
     uint32_t nn = 0;
-    FlatList fl;                                           // per-read node list in registers
+    FlatList fl;                                           // per-read node list: first FL_MAX entries in registers,
+    uint32_t l_node[GENERAL ? MAXN : 1], l_vk[GENERAL ? MAXN : 1];   // the rest (GENERAL) thread-local
+    constexpr uint32_t LIST_CAP = GENERAL ? (uint32_t)MAXN : (uint32_t)FL_MAX;
+    bool big = false;                                      // more than FL_MAX stretches
     fl.clear();
     if (!defer) {
         uint32_t tp = NONE32, node = 0;
@@ -693,9 +747,12 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
                 if (p < lim && !chunk()) { defer = true; running = false; }
                 if (running && p >= lim) {
                     // append the stretch; a node met twice (cyclic graph) is detected at the end and deferred
-                    if (nn == (uint32_t)FL_MAX) { defer = true; running = false; }
+                    big |= nn == (uint32_t)FL_MAX;
+                    if (nn == LIST_CAP) { defer = true; running = false; }
                     else {
-                        fl.set(nn, node, (lim - L + 1 - i0) | (i0 << 16));
+                        const uint32_t vk = (lim - L + 1 - i0) | (i0 << 16);
+                        if (nn < (uint32_t)FL_MAX) fl.set(nn, node, vk);
+                        else if (GENERAL) { l_node[nn] = node; l_vk[nn] = vk; }
                         nn++;
                         if (lim >= rlen) running = false;
                         else {
@@ -721,8 +778,10 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
                     if (!chunk()) { defer = true; break; }
                 }
                 if (defer) break;
-                if (nn == (uint32_t)FL_MAX) { defer = true; break; }
-                fl.set(nn, node, (lim - L + 1 - i0) | (i0 << 16));
+                big |= nn == (uint32_t)FL_MAX;
+                if (nn == LIST_CAP) { defer = true; break; }
+                if (nn < (uint32_t)FL_MAX) fl.set(nn, node, (lim - L + 1 - i0) | (i0 << 16));
+                else if (GENERAL) { l_node[nn] = node; l_vk[nn] = (lim - L + 1 - i0) | (i0 << 16); }
                 nn++;
                 if (lim >= rlen) break;
                 const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
@@ -736,11 +795,15 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
         }
     }
     uint32_t n_out = 0;
-    if (!defer) {
+    if (!defer && nn <= (uint32_t)FL_MAX) {
         fl.sort();
         if (fl.has_repeat()) defer = true;                 // needs merging: full kernel
         else n_out = flat_finalize(fl, ix, rlen, L, out);
+    } else if (!defer && GENERAL) {
+        fl.spill_to(l_node, l_vk);
+        if (!list_finalize_slow(l_node, l_vk, nn, false, ix, rlen, L, out, n_out)) defer = true;
     }
+    if (big && blockIdx.x < BIG_SAMPLE_BLOCKS) atomicAdd(&counters[CNT_BIG], 1ull);
     if (defer) {
         const unsigned long long idx = atomicAdd(&counters[CNT_DEFER], 1ull);
         defer_list[idx] = (uint32_t)r;
@@ -758,7 +821,7 @@ k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __r
 // from the other end.  A second mismatch, a set bit, a repeat or a missing successor sends the read
 // on to k_map_fast.
 // ---------------------------------------------------------------------------------------------
-template <int STRIDE>
+template <int STRIDE, bool GENERAL>
 __device__ __forceinline__ void
 map_second_read(const IndexView& ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
                 const uint32_t r, uint32_t* row, ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list,
@@ -768,7 +831,9 @@ map_second_read(const IndexView& ix, const uint32_t* __restrict__ rows, const ui
     bool defer = (h & (PH_LONG | PH_BAD)) != 0 || ix.subst == nullptr;
     const uint32_t rlen = h & 0xFFFFFF;
     uint32_t nn = 0;
-    FlatList fl;                                           // per-read node list in registers
+    FlatList fl;                                           // per-read node list: first FL_MAX entries in registers,
+    uint32_t l_node[GENERAL ? MAXN : 1], l_vk[GENERAL ? MAXN : 1];   // the rest (GENERAL) thread-local
+    constexpr uint32_t LIST_CAP = GENERAL ? (uint32_t)MAXN : (uint32_t)FL_MAX;
     if (!defer) {
         load_row<STRIDE, false>(rows, r, row_words, rlen, row, nullptr);
         const int npos = (int)(rlen - L + 1);
@@ -864,8 +929,10 @@ map_second_read(const IndexView& ix, const uint32_t* __restrict__ rows, const ui
                     last_hit = c2 > 0 ? bw : min(bw, e - (int)L);
                 }
                 if (c1 + c2 > 0) {
-                    if (nn == (uint32_t)FL_MAX) { running = false; break; }
-                    fl.set(nn, node, (uint32_t)(c1 + c2) | ((uint32_t)(mirror ? npos - 1 - last_hit : first_hit) << 16));
+                    if (nn == LIST_CAP) { running = false; break; }
+                    const uint32_t vk = (uint32_t)(c1 + c2) | ((uint32_t)(mirror ? npos - 1 - last_hit : first_hit) << 16);
+                    if (nn < (uint32_t)FL_MAX) fl.set(nn, node, vk);
+                    else if (GENERAL) { l_node[nn] = node; l_vk[nn] = vk; }
                     nn++;
                 }
                 if (lim >= rlen) { resolved = true; running = false; break; }
@@ -884,12 +951,15 @@ map_second_read(const IndexView& ix, const uint32_t* __restrict__ rows, const ui
     }
     ReadSlot* out = slots + r;
     uint32_t n_out = 0;
-    if (!defer) {
+    if (!defer && nn <= (uint32_t)FL_MAX) {
         // a node met in two stretches (cyclic graph): after the sort they are neighbours; the last
         // of a run takes the sum of the hits and the smallest position
         fl.sort();
         fl.merge_repeats();
         n_out = flat_finalize(fl, ix, rlen, L, out);
+    } else if (!defer && GENERAL) {
+        fl.spill_to(l_node, l_vk);
+        if (!list_finalize_slow(l_node, l_vk, nn, true, ix, rlen, L, out, n_out)) defer = true;
     }
     if (defer) {
         out_list[atomicAdd(out_count, 1ull)] = r;
@@ -900,7 +970,7 @@ map_second_read(const IndexView& ix, const uint32_t* __restrict__ rows, const ui
 
 // A fixed grid walks the device-side worklist (its length is only known on the device).  The
 // deferred reads are few and each is a long serial chain: only every `spread`-th thread takes one.
-template <int STRIDE>
+template <int STRIDE, bool GENERAL>
 __global__ void __launch_bounds__(MF_THREADS)
 k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
              const uint32_t* __restrict__ in_list, const unsigned long long* __restrict__ in_count, uint32_t spread,
@@ -912,7 +982,7 @@ k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __
     for (uint64_t base = (uint64_t)blockIdx.x * per_block; base < n_items; base += (uint64_t)gridDim.x * per_block) {
         const uint64_t item = base + threadIdx.x / spread;
         if (item < n_items)
-            map_second_read<STRIDE>(ix, rows, hdr, row_words, in_list[item], s_fwd + threadIdx.x * STRIDE, slots, out_list, out_count);
+            map_second_read<STRIDE, GENERAL>(ix, rows, hdr, row_words, in_list[item], s_fwd + threadIdx.x * STRIDE, slots, out_list, out_count);
     }
 }
 
@@ -1047,15 +1117,19 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER2, 0, 8, c->stream));
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK2, 0, 8, c->stream));
     }
+    // lean or general walk kernels (forced by the map_general option, else from the last launch's CNT_BIG)
+    const bool general = c->opt_map_general >= 0 ? c->opt_map_general != 0 : c->map_general;
     if (d_rows && !c->opt_single_map) {
         // stage 1: the clean-pass kernel; what it defers goes through the full kernel
-#define VSPE_M1(S, LP, FL) k_map_first<S, LP, FL><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, n_reads, d_slots, \
-                                                                                c->defer_list.p, c->counters.p)
-        if (c->opt_flat_walk) {
-            if (cap <= 160) VSPE_M1(13, 16, true); else if (cap <= 256) VSPE_M1(19, 16, true); else VSPE_M1(23, 32, true);
-        } else {
-            if (cap <= 160) VSPE_M1(13, 16, false); else if (cap <= 256) VSPE_M1(19, 16, false); else VSPE_M1(23, 32, false);
-        }
+#define VSPE_M1(S, LP, FL, GN) k_map_first<S, LP, FL, GN><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, n_reads, d_slots, \
+                                                                                        c->defer_list.p, c->counters.p)
+#define VSPE_M1S(FL, GN) do { if (cap <= 160) VSPE_M1(13, 16, FL, GN); else if (cap <= 256) VSPE_M1(19, 16, FL, GN); else VSPE_M1(23, 32, FL, GN); } while (0)
+        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_BIG, 0, 8, c->stream));
+        if (c->opt_flat_walk) { if (general) VSPE_M1S(true, true); else VSPE_M1S(true, false); }
+        else { if (general) VSPE_M1S(false, true); else VSPE_M1S(false, false); }
+        c->big_sampled = std::min<uint64_t>(n_reads, (uint64_t)BIG_SAMPLE_BLOCKS * MF_THREADS);
+        c->big_pending = true;
+#undef VSPE_M1S
 #undef VSPE_M1
         VSPE_LAUNCH_CHECK(c);
         in_list = c->defer_list.p;
@@ -1065,9 +1139,10 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
             uint32_t* list1b = c->defer_list.p + 2 * n_reads;
             const uint32_t spread2 = pow2_spread(c->opt_second_spread);
             const uint32_t grid_s = (uint32_t)std::min<uint64_t>((n_reads * spread2 + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 16);
-#define VSPE_M2(S) k_map_second<S><<<grid_s, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->defer_list.p, \
-                                                                   c->counters.p + CNT_DEFER, spread2, d_slots, list1b, c->counters.p + CNT_DEFER2)
-            if (cap <= 160) VSPE_M2(13); else if (cap <= 256) VSPE_M2(19); else VSPE_M2(23);
+#define VSPE_M2(S, GN) k_map_second<S, GN><<<grid_s, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->defer_list.p, \
+                                                                           c->counters.p + CNT_DEFER, spread2, d_slots, list1b, c->counters.p + CNT_DEFER2)
+            if (general) { if (cap <= 160) VSPE_M2(13, true); else if (cap <= 256) VSPE_M2(19, true); else VSPE_M2(23, true); }
+            else { if (cap <= 160) VSPE_M2(13, false); else if (cap <= 256) VSPE_M2(19, false); else VSPE_M2(23, false); }
 #undef VSPE_M2
             VSPE_LAUNCH_CHECK(c);
             in_list = list1b;
@@ -1116,6 +1191,18 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     }
     // last stage: the exhaustive ASCII tier consumes what is left; list lengths stay on the device
     VSPE_TRY(map_reads_generic_dev(c, d_buf, d_seq_start, d_seq_end, to_generic, to_generic_n, d_slots));
+    return VSPE_OK;
+}
+
+// After a stream synchronisation: look at how many of the sampled reads of the last k_map_first
+// launch had more than FL_MAX stretches and pick the walk-kernel variant for the next launch.
+// Both variants are exact; this only moves reads between tiers.
+int adapt_map_variant(Ctx* c) {
+    if (!c->big_pending) return VSPE_OK;
+    unsigned long long big = 0;
+    VSPE_CUDA(cudaMemcpy(&big, c->counters.p + CNT_BIG, 8, cudaMemcpyDeviceToHost));
+    c->big_pending = false;
+    if (c->big_sampled) c->map_general = big * 50 > c->big_sampled;      // more than 2 %
     return VSPE_OK;
 }
 

@@ -566,6 +566,7 @@ int scan_pack_prepare_collect(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, u
     *n_terms = h[0];
     *err_flags = h[2] ? ERRF_TILE_FULL : 0;
     scan_pack_account(c);                                      // everything queued before is done by now
+    VSPE_TRY(adapt_map_variant(c));
     return VSPE_OK;
 }
 

@@ -261,6 +261,9 @@ int device_scan_u64(Ctx* c, const unsigned long long* in, unsigned long long* ou
 int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                       uint64_t n_reads, ReadSlot* d_slots);
 
+// after a stream sync: choose the lean / general walk kernels for the next map launch
+int adapt_map_variant(Ctx* c);
+
 // K5+K6: pairs [0, total) of two slot arrays -> += into dense matrices
 int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total);
 
