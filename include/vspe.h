@@ -139,11 +139,36 @@ int vspe_sparse_merge(vspe_ctx* ctx, const uint64_t* keys, const uint64_t* count
 int vspe_write_info_sparse(const char* path, const char* const* ids, uint32_t n, const uint64_t* keys,
                            const uint64_t* counts, uint64_t n_entries, int mat);
 
+/* Input files of vspe_run: the bytes of a plain file, or of a gzip file (RFC 1952, concatenated
+ * members included) inflated in memory -- detected by the magic bytes.  The reference reads plain
+ * text only (PE_Inference.py:105,147-152) and raises on a gzip file, so this only extends the set
+ * of accepted inputs.  *data is malloc'ed; release it with
+ * vspe_free_input. */
+int vspe_read_input(const char* path, uint8_t** data, uint64_t* n_bytes);
+void vspe_free_input(uint8_t* data);
+
 /* Pinned host memory for callers that want zero-copy streaming in vspe_count_host. */
 void* vspe_alloc_pinned(size_t bytes);
 void vspe_free_pinned(void* p);
 
-/* Tunables (tests / experiments): name in {"force_generic", "chunk_mb"}. */
+/* Tunables.  None of them changes a result (every kernel path is exact; the parity tests run the
+ * fixtures through each of them); they select kernel paths for tests, experiments and profiling.
+ *   "chunk_mb"       host-input streaming: bytes per staged chunk in MiB (default 256)
+ *   "sparse"         1: count into sorted (key, count) runs instead of N*N matrices
+ *   "scan_mode"      0 (default): TMA count pass + pack pass; 3: fused TMA scan+pack with decoupled
+ *                    look-back; 1: look-back record scan + raw-byte map kernels; 2: two-pass record scan
+ *   "scan_two_pass"  1: same as scan_mode 2
+ *   "force_generic"  1: every read through the exhaustive ASCII tier (the reference's loop as is)
+ *   "subst"          0: do not build / use the substitution-hit bitmap
+ *   "single_map"     1: skip k_map_first / k_map_second (every read through k_map_fast)
+ *   "full_second"    1: skip k_map_second
+ *   "flat_walk"      0: nested stretch / chunk loops in k_map_first instead of the flat walk loop
+ *   "map_general"    -1 (default): lean or general walk kernels chosen per launch from the share of
+ *                    reads with more than 6 stretches in the previous launch; 0 / 1: force
+ *   "fast_tier"      0: reads the walk kernels defer go straight to k_map_windows
+ *   "list_spread", "second_spread"   threads per deferred read in k_map_fast / k_map_second (1..32)
+ *   "count_low_bits" dense counting: log2 of the matrix cells per radix bucket (7..15)
+ *   "dbg_times", "dbg_dump", "dbg_counters"   profiling aids (tools/dbg_scan.py, tools/dbg_map.py) */
 int vspe_set_option(vspe_ctx* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus

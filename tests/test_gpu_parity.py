@@ -78,6 +78,24 @@ def test_cli_drop_in_writes_identical_files(golden, tmp_path):
     assert b"Paired-End Information Alignment" in p.stdout
 
 
+def test_cli_reads_gzip_inputs(tmp_path):
+    """.fastq.gz (and a gzipped GFA) give the files the plain inputs give."""
+    import gzip
+    from conftest import golden_cases
+    g = [c for c in golden_cases() if c.name == "lowcx_00"][0]
+    (tmp_path / "g.gfa.gz").write_bytes(gzip.compress(g.gfa))
+    cut = len(g.fwd) // 2
+    (tmp_path / "f.fq.gz").write_bytes(gzip.compress(g.fwd[:cut]) + gzip.compress(g.fwd[cut:]))   # two members
+    (tmp_path / "r.fq.gz").write_bytes(gzip.compress(g.rve))
+    out = tmp_path / "aln"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "utils", "VStrains_PE_Inference.py"),
+                        "-g", str(tmp_path / "g.gfa.gz"), "-o", str(out), "-f", str(tmp_path / "f.fq.gz"),
+                        "-r", str(tmp_path / "r.fq.gz"), "-k", str(g.k)], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    assert (out / "pe_info").read_bytes() == g.pe_info
+    assert (out / "st_info").read_bytes() == g.st_info
+
+
 @pytest.mark.parametrize("two_pass", [0, 1])
 def test_record_split_matches_universal_newlines(golden, two_pass):
     with pe_inference.PEIndex([b"ACGTACGTAC"], 3) as ix:

@@ -109,3 +109,51 @@ def test_sparse_writer_emits_only_nonzero_lines(tmp_path):
     pe_inference.write_info_sparse(p1, ids, keys, counts, 1)
     assert open(p0).read() == "a:-7:3\nx9:x9:12\n"
     assert open(p1).read() == "a:a:7\n-7:x9:%d\n" % 2**40
+
+
+def test_read_input_plain_and_gzip(tmp_path):
+    """vspe_read_input (what vspe_run feeds the GPU path): plain bytes as is, gzip -- one member,
+    concatenated members, empty payload -- inflated; truncated / corrupt streams are loud errors."""
+    import gzip
+    import zlib
+    from vstrains_b200 import pe_inference
+    from vstrains_b200._lib import VspeError
+    rng = np.random.default_rng(5)
+    reads = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(list(b"ACGT"), 150).astype(np.uint8)), b"I" * 150)
+                     for i in range(3000))
+    plain = tmp_path / "r.fq"
+    plain.write_bytes(reads)
+    assert pe_inference.read_input(str(plain)) == reads
+    one = tmp_path / "r.fq.gz"
+    one.write_bytes(gzip.compress(reads))
+    assert pe_inference.read_input(str(one)) == reads
+    cut = len(reads) // 3
+    multi = tmp_path / "m.fq.gz"
+    multi.write_bytes(gzip.compress(reads[:cut]) + gzip.compress(reads[cut:2 * cut], 1) + gzip.compress(reads[2 * cut:], 9))
+    assert pe_inference.read_input(str(multi)) == reads
+    empty = tmp_path / "e.gz"
+    empty.write_bytes(gzip.compress(b""))
+    assert pe_inference.read_input(str(empty)) == b""
+    zero = tmp_path / "zero"
+    zero.write_bytes(b"")
+    assert pe_inference.read_input(str(zero)) == b""
+    # highly compressible payload: the output buffer has to grow well beyond 4x the input
+    big = tmp_path / "big.gz"
+    big.write_bytes(gzip.compress(b"A" * (8 << 20)))
+    assert pe_inference.read_input(str(big)) == b"A" * (8 << 20)
+    trunc = tmp_path / "t.gz"
+    trunc.write_bytes(gzip.compress(reads)[:-40])
+    with pytest.raises(VspeError):
+        pe_inference.read_input(str(trunc))
+    bad = bytearray(gzip.compress(reads))
+    bad[len(bad) // 2] ^= 0xFF
+    corrupt = tmp_path / "c.gz"
+    corrupt.write_bytes(bytes(bad))
+    with pytest.raises(VspeError):
+        pe_inference.read_input(str(corrupt))
+    with pytest.raises(VspeError):
+        pe_inference.read_input(str(tmp_path / "missing.fq"))
+    # a zlib (not gzip) stream is not inflated: the bytes pass through and the scan rejects them later
+    z = tmp_path / "z.bin"
+    z.write_bytes(zlib.compress(reads))
+    assert pe_inference.read_input(str(z)) == zlib.compress(reads)

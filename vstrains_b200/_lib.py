@@ -55,6 +55,9 @@ def lib():
     L.vspe_create.argtypes = [i32, ctypes.POINTER(P)]
     L.vspe_destroy.argtypes = [P]
     L.vspe_destroy.restype = None
+    L.vspe_read_input.argtypes = [ctypes.c_char_p, ctypes.POINTER(P), ctypes.POINTER(u64)]
+    L.vspe_free_input.argtypes = [P]
+    L.vspe_free_input.restype = None
     L.vspe_index_build.argtypes = [P, P, P, u32, u32]
     L.vspe_reset.argtypes = [P]
     L.vspe_count_device.argtypes = [P, P, u64, P, u64]

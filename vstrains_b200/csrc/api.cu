@@ -7,6 +7,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <thread>
@@ -393,6 +394,70 @@ struct MappedFile {
             if (m == MAP_FAILED) { set_error("cannot mmap %s: %s", path, strerror(errno)); p = nullptr; return VSPE_ERR_IO; }
             madvise(m, n, MADV_SEQUENTIAL);
             p = static_cast<const uint8_t*>(m);
+        }
+        return VSPE_OK;
+    }
+};
+
+// gzip (RFC 1952) -> bytes; concatenated members (bgzip, `cat a.gz b.gz`) are one stream
+static int inflate_gzip(const uint8_t* src, uint64_t n, std::vector<uint8_t>& out, const char* path) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, 15 + 16) != Z_OK) { set_error("zlib inflateInit2 failed"); return VSPE_ERR_IO; }
+    out.clear();
+    out.resize((size_t)std::max<uint64_t>(n * 4, 1u << 16));
+    uint64_t in_pos = 0, out_pos = 0;
+    int rc = VSPE_OK;
+    while (true) {
+        if (zs.avail_in == 0 && in_pos < n) {
+            const uint64_t part = std::min<uint64_t>(n - in_pos, 1u << 30);
+            zs.next_in = const_cast<Bytef*>(src + in_pos);
+            zs.avail_in = (uInt)part;
+            in_pos += part;
+        }
+        if (out_pos == out.size()) out.resize(out.size() * 2);
+        const uint64_t room = std::min<uint64_t>(out.size() - out_pos, 1u << 30);
+        zs.next_out = out.data() + out_pos;
+        zs.avail_out = (uInt)room;
+        const int z = inflate(&zs, Z_NO_FLUSH);
+        out_pos += room - zs.avail_out;
+        if (z == Z_STREAM_END) {
+            const uint64_t left = (uint64_t)zs.avail_in + (n - in_pos);
+            if (left == 0) break;
+            // another member follows (anything else after the trailer is an error, as for gzip -d)
+            if (inflateReset(&zs) != Z_OK) { set_error("zlib inflateReset failed on %s", path); rc = VSPE_ERR_IO; break; }
+            continue;
+        }
+        if (z == Z_OK) continue;
+        if (z == Z_BUF_ERROR && zs.avail_in == 0 && in_pos == n) { set_error("%s: truncated gzip stream", path); rc = VSPE_ERR_IO; break; }
+        if (z == Z_BUF_ERROR) continue;
+        set_error("%s: corrupt gzip stream (%s)", path, zs.msg ? zs.msg : "zlib error");
+        rc = VSPE_ERR_IO;
+        break;
+    }
+    inflateEnd(&zs);
+    if (rc == VSPE_OK) out.resize(out_pos);
+    return rc;
+}
+
+// An input file of the CLI: the bytes of a plain file (mapped) or of a gzip file (inflated into
+// memory).  The reference opens plain text only (PE_Inference.py:105,147-152); a file that starts
+// with the gzip magic would make it raise UnicodeDecodeError, so accepting it is a pure extension
+//  and never changes the result for an input the reference accepts.
+struct InputFile {
+    MappedFile map;
+    std::vector<uint8_t> mem;
+    const uint8_t* p = nullptr;
+    uint64_t n = 0;
+    int open_ro(const char* path) {
+        VSPE_TRY(map.open_ro(path));
+        if (map.n >= 18 && map.p[0] == 0x1f && map.p[1] == 0x8b && map.p[2] == 8) {
+            VSPE_TRY(inflate_gzip(map.p, map.n, mem, path));
+            p = mem.data();
+            n = mem.size();
+        } else {
+            p = map.p;
+            n = map.n;
         }
         return VSPE_OK;
     }
@@ -843,12 +908,19 @@ int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, i
         std::string cmd = "mkdir -p -- '" + dir + "'";
         if (system(cmd.c_str()) != 0) { set_error("cannot create output directory %s", dir.c_str()); return VSPE_ERR_IO; }
     }
-    MappedFile g, f, r;
+    InputFile g, f, r;
     VSPE_TRY(g.open_ro(gfa_path));
     GfaNodes nodes;
     VSPE_TRY(parse_gfa_bytes(g.p, g.n, nodes));
-    VSPE_TRY(f.open_ro(fwd_path));
-    VSPE_TRY(r.open_ro(rve_path));
+    {   // the two read files are opened (and, if gzipped, inflated) side by side
+        int rc_r = VSPE_OK;
+        std::string err_r;
+        std::thread tr([&] { rc_r = r.open_ro(rve_path); if (rc_r != VSPE_OK) err_r = get_error(); });
+        const int rc_f = f.open_ro(fwd_path);
+        tr.join();
+        if (rc_f != VSPE_OK) return rc_f;
+        if (rc_r != VSPE_OK) { set_error("%s", err_r.c_str()); return rc_r; }
+    }
     uint32_t N = (uint32_t)nodes.ids.size();
     std::vector<uint64_t> nm, sm, sk, sc;
     bool sparse_out = !dense_possible(N) || (getenv("VSPE_SPARSE") && atoi(getenv("VSPE_SPARSE")) != 0);
@@ -892,6 +964,21 @@ int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, i
     VSPE_TRY(vspe_write_info((dir + "/st_info").c_str(), idp.data(), N, sm.data()));
     return VSPE_OK;
 }
+
+int vspe_read_input(const char* path, uint8_t** data, uint64_t* n_bytes) {
+    if (!path || !data || !n_bytes) { set_error("bad arguments"); return VSPE_ERR_ARG; }
+    *data = nullptr;
+    *n_bytes = 0;
+    InputFile in;
+    VSPE_TRY(in.open_ro(path));
+    uint8_t* out = static_cast<uint8_t*>(malloc(in.n ? in.n : 1));
+    if (!out) { set_error("out of memory reading %s", path); return VSPE_ERR_IO; }
+    if (in.n) memcpy(out, in.p, in.n);
+    *data = out;
+    *n_bytes = in.n;
+    return VSPE_OK;
+}
+void vspe_free_input(uint8_t* data) { free(data); }
 
 void* vspe_alloc_pinned(size_t bytes) {
     void* p = nullptr;

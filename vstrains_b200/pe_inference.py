@@ -181,6 +181,18 @@ class PEIndex:
         return nl.value, st, ln
 
 
+def read_input(path: str) -> bytes:
+    """The bytes the CLI would process for ``path``: a plain file as is, a gzip file (detected by
+    its magic bytes; concatenated members included) inflated.  Host-only, needs no GPU."""
+    L = _lib.lib()
+    data, n = ctypes.c_void_p(), ctypes.c_uint64()
+    check(L.vspe_read_input(os.fsencode(path), ctypes.byref(data), ctypes.byref(n)))
+    try:
+        return ctypes.string_at(data, n.value)
+    finally:
+        L.vspe_free_input(data)
+
+
 def pe_inference(gfa: bytes, fwd, rve, kmer_size: int, device: int = 0, options: Optional[dict] = None):
     """In-memory equivalent of the reference script: -> (ids, node_mat, short_mat, stats)."""
     ids, seqs = parse_gfa_nodes(gfa)
