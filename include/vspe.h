@@ -168,6 +168,7 @@ void vspe_free_pinned(void* p);
  *   "fast_tier"      0: reads the walk kernels defer go straight to k_map_windows
  *   "list_spread", "second_spread"   threads per deferred read in k_map_fast / k_map_second (1..32)
  *   "count_low_bits" dense counting: log2 of the matrix cells per radix bucket (7..15)
+ *   "count_flat"     1: warp-flat key enumeration (k_pair_flat) instead of the nested per-pair loops
  *   "dbg_times", "dbg_dump", "dbg_counters"   profiling aids (tools/dbg_scan.py, tools/dbg_map.py) */
 int vspe_set_option(vspe_ctx* ctx, const char* name, int64_t value);
 

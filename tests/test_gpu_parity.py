@@ -27,6 +27,7 @@ VARIANTS = [
     {"scan_mode": 0, "flat_walk": 0},                   # nested walk loops in k_map_first
     {"scan_mode": 0, "map_general": 0},                 # lean walk kernels (reads with > 6 stretches deferred)
     {"scan_mode": 0, "map_general": 1},                 # general walk kernels (up to 16 stretches in place)
+    {"scan_mode": 0, "count_flat": 1},                  # warp-flat key enumeration in the count stage
     {"scan_mode": 0, "fast_tier": 0},                   # deferred reads straight to the all-windows kernel
     {"scan_mode": 0, "fast_tier": 0, "subst": 0},
 ]

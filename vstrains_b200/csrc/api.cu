@@ -1014,6 +1014,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "fast_tier")) c->opt_fast_tier = value;
     else if (!strcmp(name, "map_general")) c->opt_map_general = value;
     else if (!strcmp(name, "count_low_bits")) c->opt_count_low_bits = value;
+    else if (!strcmp(name, "count_flat")) c->opt_count_flat = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value;
     else if (!strcmp(name, "dbg_dump")) {

@@ -224,6 +224,121 @@ k_pair_emit(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uint
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-flat key enumeration (option count_flat, default off -- candidate for the next round, see
+// DESIGN.md section 10): the nested loops of for_each_key run as many turns as the pair with the most
+// keys in the warp.  Here the warp first learns how many keys each of its 32 staged pairs has
+// (a closed form of the two list lengths), scans those counts, and then walks the M keys of the
+// round 32 at a time: key t belongs to the pair whose prefix interval holds t (binary search over
+// the 32 prefixes in shared memory) and its local index decodes to (a, b).  Same keys, same
+// per-block bucket counts, balanced lanes.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tri(uint32_t n) { return n * (n + 1) / 2; }
+
+template <bool EMIT>
+__global__ void __launch_bounds__(PAIR_THREADS)
+k_pair_flat(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uint64_t n_pairs, uint32_t ppb, uint32_t N,
+            const uint32_t* __restrict__ spill, uint32_t low_bits, uint32_t n_buckets,
+            unsigned long long* __restrict__ g_hist_or_cursor, unsigned long long* __restrict__ counters,
+            uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ keys) {
+    extern __shared__ unsigned long long s_mem[];
+    unsigned long long* s_base = s_mem;                                   // [n_buckets] (EMIT)
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_mem + n_buckets);    // [n_buckets]
+    uint32_t* s_stage = s_hist + n_buckets;                               // [PAIR_WARPS][64][STAGE_STRIDE]
+    __shared__ uint32_t s_woff[PAIR_WARPS][32], s_wn[PAIR_WARPS][32];
+    __shared__ unsigned long long s_cnt[4];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (uint32_t b = threadIdx.x; b < n_buckets; b += PAIR_THREADS) {
+        if (EMIT) {
+            const uint32_t c = __ldg(blk_hist + (uint64_t)blockIdx.x * n_buckets + b);
+            if (c) s_base[b] = atomicAdd(&g_hist_or_cursor[b], (unsigned long long)c);
+        }
+        s_hist[b] = 0;
+    }
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t lo = (uint64_t)blockIdx.x * ppb;
+    const uint64_t hi = lo + ppb < n_pairs ? lo + ppb : n_pairs;
+    uint32_t* st = s_stage + wib * 64 * STAGE_STRIDE;
+    const uint32_t NN = N * N;
+    uint32_t c_used = 0, c_n = 0, c_short = 0;
+    unsigned long long c_keys = 0;
+    for (uint64_t p0 = lo + wib * 32; p0 < hi; p0 += PAIR_THREADS) {
+        __syncwarp();                                                 // the previous round's reads are done
+        stage_slots(f, r, p0, hi, st, lane);
+        uint32_t ln = 0, rn = 0;
+        if (p0 + lane < hi) {
+            const uint32_t hf = st[lane * STAGE_STRIDE], hr = st[(32 + lane) * STAGE_STRIDE];
+            const uint32_t cls = pair_class(hf, hr);
+            if (cls == 0) { ln = hf >> 8; rn = hr >> 8; c_used++; }
+            else if (cls == 1) c_n++;
+            else c_short++;
+        }
+        const uint32_t m = tri(ln) + tri(rn) + ln * rn;
+        c_keys += m;
+        uint32_t inc = m;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        const uint32_t M = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        s_woff[wib][lane] = inc - m;
+        s_wn[wib][lane] = ln | (rn << 16);
+        __syncwarp();
+        for (uint32_t t = lane; t < M; t += 32) {
+            uint32_t own = 0;                                         // largest pair with prefix <= t
+#pragma unroll
+            for (uint32_t step = 16; step; step >>= 1)
+                if (s_woff[wib][own + step] <= t) own += step;
+            uint32_t u = t - s_woff[wib][own];
+            const uint32_t nn = s_wn[wib][own];
+            const uint32_t oln = nn & 0xFFFF, orn = nn >> 16;
+            const uint32_t* pf = st + own * STAGE_STRIDE;
+            const uint32_t* pr = st + (32 + own) * STAGE_STRIDE;
+            const uint32_t* Ll = oln <= (uint32_t)SLOT_IDS ? pf + 1 : spill + pf[1];
+            const uint32_t* Rl = orn <= (uint32_t)SLOT_IDS ? pr + 1 : spill + pr[1];
+            const uint32_t m1 = tri(oln), m2 = tri(orn);
+            uint32_t key;
+            if (u < m1 + m2) {                                        // short_mat: a <= b inside one mate's list
+                const bool second = u >= m1;
+                const uint32_t* A = second ? Rl : Ll;
+                const uint32_t n = second ? orn : oln;
+                uint32_t v = second ? u - m1 : u, a = 0;
+                while (v >= n - a) { v -= n - a; a++; }
+                key = NN + A[a] * N + A[a + v];
+            } else {                                                  // node_mat: every left node x every right node
+                const uint32_t v = u - m1 - m2, a = v / orn;
+                key = Ll[a] * N + Rl[v - a * orn];
+            }
+            const uint32_t b = key >> low_bits;
+            if (EMIT) {
+                const uint32_t o = atomicAdd(&s_hist[b], 1u);
+                keys[s_base[b] + o] = key;
+            } else {
+                atomicAdd(&s_hist[b], 1u);
+            }
+        }
+    }
+    if (EMIT) return;
+    if (c_used) atomicAdd(&s_cnt[0], (unsigned long long)c_used);
+    if (c_n) atomicAdd(&s_cnt[1], (unsigned long long)c_n);
+    if (c_short) atomicAdd(&s_cnt[2], (unsigned long long)c_short);
+    if (c_keys) atomicAdd(&s_cnt[3], c_keys);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < n_buckets; b += PAIR_THREADS) {
+        const uint32_t c = s_hist[b];
+        if (c) atomicAdd(&g_hist_or_cursor[b], (unsigned long long)c);
+        blk_hist[(uint64_t)blockIdx.x * n_buckets + b] = c;           // the emit pass reuses it
+    }
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(&counters[CNT_USED], s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&counters[CNT_N], s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(&counters[CNT_SHORT], s_cnt[2]);
+        if (s_cnt[3]) atomicAdd(&counters[CNT_KEYS], s_cnt[3]);
+    }
+}
+
 // One work item = up to HIST_SLICE keys of one bucket (item_start from k_bucket_scan): counting
 // sort of the low digit in shared memory; the per-value counts ARE the run lengths.  A bucket that
 // is a single item owns its matrix cells (plain stores); the items of a hot bucket add their partial
@@ -301,6 +416,8 @@ int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total
         VSPE_CUDA(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 15) * 4));
         VSPE_CUDA(cudaFuncSetAttribute(k_pair_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 4 + STAGE_WORDS * 4));
         VSPE_CUDA(cudaFuncSetAttribute(k_pair_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12 + STAGE_WORDS * 4));
+        VSPE_CUDA(cudaFuncSetAttribute(k_pair_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12 + STAGE_WORDS * 4));
+        VSPE_CUDA(cudaFuncSetAttribute(k_pair_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12 + STAGE_WORDS * 4));
         c->count_attr_set = true;
     }
     // blocks that are all resident at once (the emit kernel needs more shared memory: it decides)
@@ -319,8 +436,13 @@ int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total
         // the per-block histograms are kept for the emit kernel
         VSPE_TRY(c->blk_hist.reserve((uint64_t)grid * n_buckets));
         uint32_t* blk_hist = c->blk_hist.p;
-        k_pair_count<<<grid, PAIR_THREADS, smem_count, st>>>(d_f + off, d_r + off, n, ppb, N, c->spill.p, low_bits, n_buckets,
-                                                             g_hist, c->counters.p, blk_hist);
+        const bool flat = c->opt_count_flat != 0;
+        if (flat)
+            k_pair_flat<false><<<grid, PAIR_THREADS, smem_emit, st>>>(d_f + off, d_r + off, n, ppb, (uint32_t)N, c->spill.p, low_bits, n_buckets,
+                                                                      g_hist, c->counters.p, blk_hist, nullptr);
+        else
+            k_pair_count<<<grid, PAIR_THREADS, smem_count, st>>>(d_f + off, d_r + off, n, ppb, N, c->spill.p, low_bits, n_buckets,
+                                                                 g_hist, c->counters.p, blk_hist);
         VSPE_LAUNCH_CHECK(c);
         // one D2H + sync per batch: the cumulative key counter and the kernels' error flags
         VSPE_CUDA(cudaMemcpyAsync(&h_keys, c->counters.p + CNT_KEYS, 8, cudaMemcpyDeviceToHost, st));
@@ -336,8 +458,12 @@ int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total
         VSPE_TRY(c->keys.reserve(n_keys));
         k_bucket_scan<<<1, 1024, 0, st>>>(g_hist, n_buckets, g_start, g_cursor, g_item);
         VSPE_LAUNCH_CHECK(c);
-        k_pair_emit<<<grid, PAIR_THREADS, smem_emit, st>>>(d_f + off, d_r + off, n, ppb, N, c->spill.p, low_bits, n_buckets,
-                                                           g_cursor, c->keys.p, blk_hist);
+        if (flat)
+            k_pair_flat<true><<<grid, PAIR_THREADS, smem_emit, st>>>(d_f + off, d_r + off, n, ppb, (uint32_t)N, c->spill.p, low_bits, n_buckets,
+                                                                     g_cursor, c->counters.p, blk_hist, c->keys.p);
+        else
+            k_pair_emit<<<grid, PAIR_THREADS, smem_emit, st>>>(d_f + off, d_r + off, n, ppb, N, c->spill.p, low_bits, n_buckets,
+                                                               g_cursor, c->keys.p, blk_hist);
         VSPE_LAUNCH_CHECK(c);
         // work items: every non-empty bucket rounds up to whole HIST_SLICE-key items
         const uint32_t n_items = (uint32_t)std::min<uint64_t>(n_keys / HIST_SLICE + n_buckets, 0x7FFFFFFFull);

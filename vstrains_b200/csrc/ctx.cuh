@@ -84,6 +84,7 @@ struct Ctx {
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
     int64_t opt_list_spread = 2;       // list-driven k_map_fast: one read per this many threads (1, 2, 4, 8 ...)
+    int64_t opt_count_flat = 0;        // 1: warp-flat key enumeration (k_pair_flat) instead of the nested loops -- not yet measured
     int64_t opt_count_low_bits = 7;    // dense counting: log2 of the matrix cells per radix bucket (7..15; raised for large graphs)
     int64_t opt_map_general = -1;      // walk kernels: -1 adaptive, 0 lean (defer reads with > 6 stretches), 1 general
     bool map_general = false;          // adaptive choice for the next launch
