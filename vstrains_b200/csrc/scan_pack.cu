@@ -1,20 +1,25 @@
-// scan_pack.cu -- K1 + K2 fused: one pass over the raw FASTQ bytes.
+// scan_pack.cu -- K1 + K2: the raw FASTQ bytes -> record table -> 2-bit rows.
 //
 // Replaces `readlines()` + `[s[:-1] ...]` (reference utils/VStrains_PE_Inference.py:149-159) and
 // the per-character work of `fseq.count("N")` / k-mer slicing (:160, :25).
 //
-// Per 64 KiB tile (one CTA, 3 CTAs per SM):
+// Per 48 KiB tile (one CTA of 10 warps, 3 CTAs per SM):
 //   1. one elected thread issues TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of the
 //      tile + a 16-byte front margin + a 512-byte back margin into shared memory;
-//   2. every lane builds terminator bitmasks of its 16-byte vectors from shared memory
-//      (universal newlines: '\n', "\r\n" once, lone '\r');
-//   3. warp reductions + one block exchange give the tile's terminator count, published for
-//      the decoupled look-back that yields the global line number of the tile's first line;
-//   4. terminators with line%4==0 start a sequence line, line%4==1 end it -> per-tile read
+//   2. every lane tests its 16-byte vectors for bytes < 0x10; candidate vectors go to a per-warp
+//      queue (warp ballots) and only they get exact terminator masks (universal newlines: '\n',
+//      "\r\n" once, lone '\r'); a warp scan ranks the terminators;
+//   3. warp totals + one block exchange give the tile's terminator count;
+//   4. the line number of the tile's first line: scanned tile counts (two-kernel mode) or a
+//      decoupled look-back (fused mode);
+//   5. terminators with line%4==0 start a sequence line, line%4==1 end it -> per-tile read
 //      table in shared memory (+ seq_start/seq_end in HBM for the exhaustive tier);
-//   5. half-warps pack each read the tile owns (its sequence line STARTS here) to 2 bits/base
+//   6. half-warps pack each read the tile owns (its sequence line STARTS here) to 2 bits/base
 //      straight from the tile: 64-byte rows in HBM + one header word (length | flags).
-// The map kernel then never touches the raw bytes again.
+// Default (scan_mode 0): steps 1-3 as a count pass that also saves the queues (no tile waits on
+// another), a device scan of the tile counts, then steps 1, 4-6 as a pack pass with exactly
+// sized outputs.  scan_mode 3 runs 1-6 in one kernel with the look-back.  Both are limited by
+// instruction issue, not by HBM.  The map kernels never touch the raw bytes.
 #include "ctx.cuh"
 
 namespace vspe {
