@@ -157,3 +157,43 @@ def test_read_input_plain_and_gzip(tmp_path):
     z = tmp_path / "z.bin"
     z.write_bytes(zlib.compress(reads))
     assert pe_inference.read_input(str(z)) == zlib.compress(reads)
+
+
+def _consumer_parse(node_ids, pe_bytes, st_bytes):
+    """Test-side restatement of the pipeline's consumer of pe_info / st_info (reference
+    utils/VStrains_IO.py:598-627): zero-initialise every unordered id pair, then add the third
+    field of every line (up to a blank line) to the pair's entry if it exists."""
+    table = {}
+    for u in node_ids:
+        for v in node_ids:
+            table[(min(u, v), max(u, v))] = 0
+    for blob in (pe_bytes, st_bytes):
+        for line in blob.decode().splitlines(keepends=True):
+            if line == "\n":
+                break
+            u, v, mark = line[:-1].split(":")[:3]
+            key = (min(u, v), max(u, v))
+            if key in table:
+                table[key] += int(mark)
+    return table
+
+
+def test_consumer_sees_the_same_dict_from_files_and_from_matrices(golden, tmp_path):
+    """What VStrains does next with the two files (process_pe_info) gives the same dict as
+    pe_info_dict() on the matrices, and as the sparse (non-zero lines only) files."""
+    if golden.status != 0:
+        return
+    ids, _ = pe_inference.parse_gfa_nodes(golden.gfa)
+    if len(set(ids)) != len(ids) or any(":" in i for i in ids):
+        return                                   # the reference's own text format is ambiguous for such ids
+    node = parse_info(golden.pe_info, ids)
+    short = parse_info(golden.st_info, ids)
+    want = _consumer_parse(ids, golden.pe_info, golden.st_info)
+    assert pe_inference.pe_info_dict(ids, node, short) == want
+    # sparse files: only the non-zero lines
+    flat = np.concatenate([node.reshape(-1), short.reshape(-1)]).astype(np.uint64)
+    keys = np.nonzero(flat)[0].astype(np.uint64)
+    counts = flat[keys.astype(np.int64)]
+    pe_inference.write_info_sparse(str(tmp_path / "pe"), ids, keys, counts, 0)
+    pe_inference.write_info_sparse(str(tmp_path / "st"), ids, keys, counts, 1)
+    assert _consumer_parse(ids, (tmp_path / "pe").read_bytes(), (tmp_path / "st").read_bytes()) == want

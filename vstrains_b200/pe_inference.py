@@ -224,6 +224,25 @@ def write_info_sparse(path: str, ids: Sequence[str], keys: np.ndarray, counts: n
                                             c.ctypes.data if c.size else None, k.size, mat))
 
 
+def pe_info_dict(ids: Sequence[str], node_mat: np.ndarray, short_mat: np.ndarray) -> dict:
+    """The dict the pipeline's consumer builds from the two files (reference
+    utils/VStrains_IO.py:598-627 ``process_pe_info``), straight from the matrices: key
+    ``(min(u, v), max(u, v))`` over the id STRINGS (as the reference compares them), value = sum of
+    both matrices over both orientations.  Lets a caller skip the N*N-line text round trip
+    (SURVEY section 8f, row 3).  Like the reference's parser, a repeated id folds onto one key."""
+    n = len(ids)
+    tot = np.asarray(node_mat, dtype=np.uint64).reshape(n, n) + np.asarray(short_mat, dtype=np.uint64).reshape(n, n)
+    out = {}
+    for a in range(n):
+        u = ids[a]
+        row = tot[a]
+        for b in range(n):
+            v = ids[b]
+            key = (u, v) if u <= v else (v, u)
+            out[key] = out.get(key, 0) + int(row[b])
+    return out
+
+
 def single_end_read_mapping(seq: str, kmer_htable, index2seqlen: list, split_len: int, len_index2id: int):
     """API-fidelity shim for reference :16-48.  ``kmer_htable`` must be a :class:`PEIndex`
     (the device index); the Python dict of the reference is not accepted because this package
