@@ -1012,6 +1012,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "second_spread")) c->opt_second_spread = value;
     else if (!strcmp(name, "flat_walk")) c->opt_flat_walk = value;
     else if (!strcmp(name, "fast_tier")) c->opt_fast_tier = value;
+    else if (!strcmp(name, "two_err")) c->opt_two_err = value;
     else if (!strcmp(name, "map_general")) c->opt_map_general = value;
     else if (!strcmp(name, "count_low_bits")) c->opt_count_low_bits = value;
     else if (!strcmp(name, "count_flat")) c->opt_count_flat = value;

@@ -16,6 +16,7 @@ enum Counter {
     CNT_WORK2,               // reads k_map_windows left for the ASCII tier
     CNT_DEFER2,              // reads k_map_second left for k_map_fast
     CNT_BIG,                 // sampled reads of the last k_map_first launch with more than FL_MAX stretches
+    CNT_PROBE,               // reads k_map_second2 parked for k_map_probe (two_err candidate path)
     CNT_COUNT_
 };
 static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16;
@@ -90,6 +91,8 @@ struct Ctx {
     bool map_general = false;          // adaptive choice for the next launch
     bool big_pending = false;          // CNT_BIG of the last k_map_first launch has not been looked at yet
     uint64_t big_sampled = 0;          // reads that launch sampled
+    int64_t opt_two_err = 0;           // 1: k_map_second2 + k_map_probe instead of k_map_second (candidate, not yet run on a GPU)
+    DevBuf<uint8_t> probe_recs;        // 64-byte records of the reads parked for k_map_probe
     int64_t opt_fast_tier = 1;         // 0: reads the walk kernels defer go straight to k_map_windows (no k_map_fast)
     int64_t opt_flat_walk = 1;         // k_map_first: flat walk loop (0: nested stretch / chunk loops)
     int64_t opt_second_spread = 1;     // k_map_second: one read per this many threads (power of two <= 32)
