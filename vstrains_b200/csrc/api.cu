@@ -720,6 +720,7 @@ int vspe_get_stats(vspe_ctx* c, vspe_stats* out) {
     if (!c || !out) { set_error("null argument"); return VSPE_ERR_ARG; }
     VSPE_CUDA(cudaSetDevice(c->device));
     unsigned long long h[CNT_COUNT_];
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));           // (vspe_reset zeroes the counters stream-ordered)
     VSPE_CUDA(cudaMemcpy(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
     if (!c->stats_overridden) {
         c->stats.n_pairs = h[CNT_N];
