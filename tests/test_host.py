@@ -197,3 +197,19 @@ def test_consumer_sees_the_same_dict_from_files_and_from_matrices(golden, tmp_pa
     pe_inference.write_info_sparse(str(tmp_path / "pe"), ids, keys, counts, 0)
     pe_inference.write_info_sparse(str(tmp_path / "st"), ids, keys, counts, 1)
     assert _consumer_parse(ids, (tmp_path / "pe").read_bytes(), (tmp_path / "st").read_bytes()) == want
+
+
+def test_every_library_option_is_documented_in_the_header():
+    """vspe_set_option's names (api.cu) and the list in include/vspe.h must not drift apart."""
+    import re
+    with open(os.path.join(ROOT, "vstrains_b200", "csrc", "api.cu")) as f:
+        src = f.read()
+    body = src[src.index("int vspe_set_option("):]
+    names = set(re.findall(r'!strcmp\(name, "([a-z_0-9]+)"\)', body))
+    assert len(names) >= 15
+    with open(os.path.join(ROOT, "include", "vspe.h")) as f:
+        hdr = f.read()
+    doc = hdr[hdr.index("/* Tunables."):hdr.index("int vspe_set_option(")]
+    documented = set(re.findall(r'"([a-z_0-9]+)"', doc))
+    assert names <= documented, sorted(names - documented)
+    assert documented <= names, sorted(documented - names)
