@@ -166,11 +166,7 @@ void vspe_free_pinned(void* p);
  *   "map_general"    -1 (default): lean or general walk kernels chosen per launch from the share of
  *                    reads with more than 6 stretches in the previous launch; 0 / 1: force
  *   "fast_tier"      0: reads the walk kernels defer go straight to k_map_windows
- *   "two_err"        1: two-error walk + probe kernels instead of k_map_second (candidate path,
- *                    compiled but not yet validated on a GPU: keep 0)
  *   "list_spread", "second_spread"   threads per deferred read in k_map_fast / k_map_second (1..32)
- *   "count_low_bits" dense counting: log2 of the matrix cells per radix bucket (7..15)
- *   "count_flat"     1: warp-flat key enumeration (k_pair_flat) instead of the nested per-pair loops
  *   "dbg_times", "dbg_dump", "dbg_counters"   profiling aids (tools/dbg_scan.py, tools/dbg_map.py) */
 int vspe_set_option(vspe_ctx* ctx, const char* name, int64_t value);
 

@@ -12,7 +12,7 @@
 #include <algorithm>
 #include <thread>
 
-#include "ctx.cuh"
+#include "link.cuh"
 
 namespace vspe {
 
@@ -64,6 +64,17 @@ static int scan_mode_of(Ctx* c) {
     if (c->opt_scan_two_pass) mode = 2;
     if ((c->opt_force_generic || c->index.split_len > 320) && (mode == 0 || mode == 3)) mode = 1;
     return mode;
+}
+
+// A map / intern launch ran out of private list records or spill words: put the cursors back to
+// where the chunk started, clear the flags, grow the pools.  The caller repeats the launch.
+static int retry_after_pool_overflow(Ctx* c, unsigned long long flags, const unsigned long long* cur0) {
+    const unsigned long long cleared = flags & ~(unsigned long long)(ERRF_LISTS_FULL | ERRF_SPILL_FULL);
+    VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_ERR, &cleared, 8, cudaMemcpyHostToDevice, c->stream));
+    VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_SPILL_CURSOR, &cur0[0], 8, cudaMemcpyHostToDevice, c->stream));
+    VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_OVF, &cur0[1], 8, cudaMemcpyHostToDevice, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    return link_grow_overflow(c);
 }
 
 // prepared: the count pass of this chunk was already queued (scan_pack_prepare_launch)
@@ -150,6 +161,9 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     }
     VSPE_TRY(mb.slots.reserve(rec_first + n_seq + 1, true, c->stream));
     VSPE_CUDA(cudaEventRecord(e1, c->stream));
+    unsigned long long cur0[2] = {0, 0};                  // spill / private-record cursors before this chunk's map stage
+    VSPE_CUDA(cudaMemcpyAsync(&cur0[0], c->counters.p + CNT_SPILL_CURSOR, 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaMemcpyAsync(&cur0[1], c->counters.p + CNT_OVF, 8, cudaMemcpyDeviceToHost, c->stream));
     if (n_seq) {
         if (packed)
             VSPE_TRY(map_reads_packed(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p, row_words, cap, n_seq,
@@ -158,6 +172,27 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
             VSPE_TRY(map_reads_generic_list(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, nullptr, n_seq, mb.slots.p + rec_first));
         else
             VSPE_TRY(map_reads_fast(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, n_seq, mb.slots.p + rec_first));
+    }
+    // slots -> list handles (link.cuh); a launch that ran out of private list records or spill words
+    // is repeated after growing the pools (interning is idempotent)
+    VSPE_TRY(mb.handles.reserve(rec_first + n_seq + 1, true, c->stream));
+    for (int attempt = 0; n_seq; attempt++) {
+        VSPE_TRY(intern_slots(c, mb.slots.p + rec_first, n_seq, nullptr, nullptr, mb.handles.p + rec_first));
+        unsigned long long h_err = 0;
+        VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+        if (!(h_err & (ERRF_LISTS_FULL | ERRF_SPILL_FULL))) break;
+        if (attempt == 8) break;                          // reported by the caller's error check
+        VSPE_TRY(retry_after_pool_overflow(c, h_err, cur0));
+        if (h_err & ERRF_SPILL_FULL) {                    // the map tiers themselves ran out of spill words: map again
+            if (packed)
+                VSPE_TRY(map_reads_packed(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p, row_words, cap, n_seq,
+                                          mb.slots.p + rec_first));
+            else if (c->opt_force_generic)
+                VSPE_TRY(map_reads_generic_list(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, nullptr, n_seq, mb.slots.p + rec_first));
+            else
+                VSPE_TRY(map_reads_fast(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, n_seq, mb.slots.p + rec_first));
+        }
     }
     VSPE_CUDA(cudaEventRecord(e2, c->stream));
     if (sync_after) {
@@ -181,7 +216,8 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
 
 static int report_error_flags(unsigned long long e) {
     if (e & ERRF_NON_ASCII) { set_error("input contains a byte >= 0x80 (non-ASCII FASTQ is outside the reference's contract)"); return VSPE_ERR_NON_ASCII; }
-    if (e & ERRF_SPILL_FULL) { set_error("node-list spill pool exhausted"); return VSPE_ERR_LIMIT; }
+    if (e & (ERRF_SPILL_FULL | ERRF_LISTS_FULL)) { set_error("node-list pools exhausted after repeated growth"); return VSPE_ERR_LIMIT; }
+    if (e & ERRF_INTERNAL) { set_error("internal: a read reached the count stage without a node list"); return VSPE_ERR_LIMIT; }
     if (e & ERRF_KEYS_FULL) { set_error("key buffer exhausted"); return VSPE_ERR_LIMIT; }
     if (e & ERRF_TILE_FULL) { set_error("internal: a scan tile overflowed after its count pass accepted it"); return VSPE_ERR_LIMIT; }
     return VSPE_OK;
@@ -192,8 +228,7 @@ static int finish_pairs(Ctx* c, const MateStream& f, const MateStream& r) {
     cudaEvent_t e0 = c->ev[5], e1 = c->ev[6];
     VSPE_CUDA(cudaEventRecord(e0, c->stream));
     c->err_flags_fresh = false;
-    if (c->sparse.enabled) VSPE_TRY(count_pairs_sparse(c, c->mate[0].slots.p, c->mate[1].slots.p, total));
-    else VSPE_TRY(count_pairs(c, c->mate[0].slots.p, c->mate[1].slots.p, total));
+    VSPE_TRY(count_links(c, c->mate[0].handles.p, c->mate[1].handles.p, total));
     VSPE_CUDA(cudaEventRecord(e1, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0;
@@ -531,6 +566,7 @@ int vspe_index_build(vspe_ctx* c, const uint8_t* seqs, const uint64_t* seq_off, 
     VSPE_CUDA(cudaSetDevice(c->device));
     c->scratch_valid = false;
     VSPE_TRY(index_build_device(c, seqs, seq_off, n_nodes, split_len));
+    VSPE_TRY(link_setup(c));
     return vspe_reset(c);
 }
 
@@ -539,6 +575,7 @@ int vspe_reset(vspe_ctx* c) {
     uint64_t nn = 2ull * c->index.n_nodes * c->index.n_nodes;
     if (nn && !c->sparse.enabled) VSPE_CUDA(cudaMemsetAsync(c->mats.p, 0, nn * 8, c->stream));
     c->sparse.n_runs = 0;
+    VSPE_TRY(link_reset(c));
     VSPE_CUDA(cudaMemsetAsync(c->counters.p, 0, CNT_COUNT_ * 8, c->stream));   // stream-ordered: no host sync needed
     vspe_stats keep = c->stats;
     c->stats = {};
@@ -548,13 +585,13 @@ int vspe_reset(vspe_ctx* c) {
     c->stats.n_kmers = keep.n_kmers;
     c->stats.table_slots = keep.table_slots;
     c->launches = 0;
-    c->keys_seen = 0;
     return VSPE_OK;
 }
 
 static void begin_call(vspe_ctx* c) {
     // the spill pool is per call: slots of earlier calls are no longer referenced
     cudaMemsetAsync(c->counters.p + CNT_SPILL_CURSOR, 0, 8, c->stream);
+    cudaMemsetAsync(c->counters.p + CNT_OVF, 0, 8, c->stream);      // ... and so are the private list records
 }
 
 int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const uint8_t* d_rve, uint64_t n_rve) {
@@ -812,7 +849,12 @@ int vspe_map_reads(vspe_ctx* c, const uint8_t* fq, uint64_t n_bytes, uint64_t* n
     VSPE_TRY(check_kernel_errors(c));
     uint64_t recs = ms.lines / 4;
     std::vector<ReadSlot> slots(recs);
-    if (recs) VSPE_CUDA(cudaMemcpy(slots.data(), c->mate[0].slots.p, recs * sizeof(ReadSlot), cudaMemcpyDeviceToHost));
+    if (recs) {
+        VSPE_TRY(c->mate[0].slots.reserve(recs + 1));
+        VSPE_TRY(export_slots(c, c->mate[0].handles.p, recs, c->mate[0].slots.p));
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+        VSPE_CUDA(cudaMemcpy(slots.data(), c->mate[0].slots.p, recs * sizeof(ReadSlot), cudaMemcpyDeviceToHost));
+    }
     unsigned long long spill_n = 0;
     VSPE_CUDA(cudaMemcpy(&spill_n, c->counters.p + CNT_SPILL_CURSOR, 8, cudaMemcpyDeviceToHost));
     std::vector<uint32_t> spill(spill_n);
@@ -1013,10 +1055,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "second_spread")) c->opt_second_spread = value;
     else if (!strcmp(name, "flat_walk")) c->opt_flat_walk = value;
     else if (!strcmp(name, "fast_tier")) c->opt_fast_tier = value;
-    else if (!strcmp(name, "two_err")) c->opt_two_err = value;
     else if (!strcmp(name, "map_general")) c->opt_map_general = value;
-    else if (!strcmp(name, "count_low_bits")) c->opt_count_low_bits = value;
-    else if (!strcmp(name, "count_flat")) c->opt_count_flat = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value;
     else if (!strcmp(name, "dbg_dump")) {

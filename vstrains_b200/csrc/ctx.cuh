@@ -16,10 +16,16 @@ enum Counter {
     CNT_WORK2,               // reads k_map_windows left for the ASCII tier
     CNT_DEFER2,              // reads k_map_second left for k_map_fast
     CNT_BIG,                 // sampled reads of the last k_map_first launch with more than FL_MAX stretches
-    CNT_PROBE,               // reads k_map_second2 parked for k_map_probe (two_err candidate path)
+    CNT_LISTS,               // distinct node lists interned in the list table
+    CNT_OVF,                 // private list records of this call (lists the table cannot hold)
+    CNT_PAIR_OCC,            // distinct (left list, right list) combinations of the current batch
+    CNT_EXP,                 // weighted keys the current batch expands to
+    CNT_EXP_CURSOR,          // ... and the emit cursor over them
     CNT_COUNT_
 };
-static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16;
+static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16, ERRF_LISTS_FULL = 32, ERRF_INTERNAL = 64;
+// flags that end the run (the *_FULL scan flags are transient: the host repeats or ignores the launch)
+static constexpr uint64_t ERRF_FATAL = ERRF_NON_ASCII | ERRF_SPILL_FULL | ERRF_KEYS_FULL | ERRF_LISTS_FULL | ERRF_INTERNAL;
 
 // sparse (COO) counting state: sorted runs (key, count) at the front of k[0] / v[0]
 struct Sparse {
@@ -33,6 +39,7 @@ struct Sparse {
 struct MateBuf {
     Records rec;
     DevBuf<ReadSlot> slots;
+    DevBuf<uint32_t> handles;  // [n_recs] list handle (or H_N / H_SHORT) per read
     uint64_t n_recs = 0;      // complete records = lines / 4
 };
 
@@ -62,13 +69,15 @@ struct Ctx {
     DevBuf<uint32_t> spill;
     DevBuf<uint32_t> worklist;
     DevBuf<uint32_t> defer_list;
-    // K5/K6 scratch
-    DevBuf<uint32_t> keys;
-    DevBuf<unsigned long long> bucket;   // [3][n_buckets + 1]: histogram, start, cursor
-    DevBuf<unsigned long long> block_sums;
-    DevBuf<uint32_t> blk_hist;           // [blocks][n_buckets] per-block key histograms (count -> emit)
-    bool count_attr_set = false;
-    uint64_t keys_seen = 0;            // host copy of CNT_KEYS after the last count batch
+    // K5/K6: list table + pair table (link.cuh)
+    DevBuf<ListRec> list_recs;         // [list_T] table part + [list_ov_cap] private records
+    DevBuf<uint32_t> list_occ;         // [list_T]
+    uint32_t list_T = 0, list_ov_cap = 0;
+    DevBuf<PairEnt> pair_tab;          // [pair_cap] (power of two), all zero between batches
+    DevBuf<uint32_t> pair_occ;
+    uint64_t pair_cap = 0;
+    DevBuf<uint32_t> wk_hist, wk_keys;   // dense accumulation scratch: bucket histogram / segments, partitioned (digit, weight)
+    bool link_attr_set = false;
     unsigned long long last_err_flags = 0;
     bool err_flags_fresh = false;
     cudaEvent_t ev_m[2][3] = {};       // per mate: scan start, scan end / map start, map end
@@ -85,14 +94,10 @@ struct Ctx {
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
     int64_t opt_list_spread = 2;       // list-driven k_map_fast: one read per this many threads (1, 2, 4, 8 ...)
-    int64_t opt_count_flat = 0;        // 1: warp-flat key enumeration (k_pair_flat) instead of the nested loops -- not yet measured
-    int64_t opt_count_low_bits = 7;    // dense counting: log2 of the matrix cells per radix bucket (7..15; raised for large graphs)
     int64_t opt_map_general = -1;      // walk kernels: -1 adaptive, 0 lean (defer reads with > 6 stretches), 1 general
     bool map_general = false;          // adaptive choice for the next launch
     bool big_pending = false;          // CNT_BIG of the last k_map_first launch has not been looked at yet
     uint64_t big_sampled = 0;          // reads that launch sampled
-    int64_t opt_two_err = 0;           // 1: k_map_second2 + k_map_probe instead of k_map_second (candidate, not yet run on a GPU)
-    DevBuf<uint8_t> probe_recs;        // 64-byte records of the reads parked for k_map_probe
     int64_t opt_fast_tier = 1;         // 0: reads the walk kernels defer go straight to k_map_windows (no k_map_fast)
     int64_t opt_flat_walk = 1;         // k_map_first: flat walk loop (0: nested stretch / chunk loops)
     int64_t opt_second_spread = 1;     // k_map_second: one read per this many threads (power of two <= 32)

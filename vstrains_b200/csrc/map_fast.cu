@@ -32,19 +32,12 @@
 // Phase 4:      one thread per read: sort by node index, saturation predicate, write the slot.
 #include <algorithm>
 
-#include "ctx.cuh"
+#include "map_common.cuh"
 
 namespace vspe {
 
 static constexpr int MF_THREADS = 128;
 static constexpr int MAXN = 16;
-
-__device__ __forceinline__ bool keep_node_f(uint32_t v, uint32_t kmin, uint32_t len, uint32_t rlen, uint32_t L) {
-    int m = min((int)len, (int)rlen - (int)kmin);
-    int sat = m - (int)L + 1;
-    long long ab = (long long)(min(rlen, len) - L + 1) * (long long)(rlen - L);
-    return (int)v >= sat || (long long)v * rlen >= ab;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Per-read node list of the walk kernels, in REGISTERS: up to FL_MAX entries (node << 32 | v | kmin << 16),
@@ -153,39 +146,6 @@ __device__ __noinline__ bool list_finalize_slow(uint32_t* l_node, uint32_t* l_vk
     return true;
 }
 
-// 64 bits (32 bases) of a packed read row starting at base b (row has 2 pad words)
-__device__ __forceinline__ uint64_t read64(const uint32_t* row, uint32_t b) {
-    uint32_t w = b >> 4, s = (b & 15) * 2;
-    uint32_t x0 = row[w], x1 = row[w + 1], x2 = row[w + 2];
-    uint32_t lo = __funnelshift_r(x0, x1, s), hi = __funnelshift_r(x1, x2, s);
-    return ((uint64_t)hi << 32) | lo;
-}
-
-__device__ __forceinline__ uint64_t hash_read(const uint32_t* row, uint32_t b, uint32_t L) {
-    const uint32_t w0 = b >> 4, sh = (b & 15) * 2, n = (L + 15) >> 4;
-    KmerHash hs;
-    uint32_t x0 = row[w0];
-    for (uint32_t m = 0; m < n; m++) {
-        const uint32_t x1 = row[w0 + m + 1];
-        uint32_t v = __funnelshift_r(x0, x1, sh);
-        if (m == n - 1 && (L & 15)) v &= (1u << (2 * (L & 15))) - 1;
-        hs.add(v);
-        x0 = x1;
-    }
-    return hs.finish();
-}
-
-__device__ __forceinline__ bool read_equals_text(const uint32_t* row, uint32_t b, const uint64_t* __restrict__ text,
-                                                 uint32_t tp, uint32_t L) {
-    for (uint32_t m = 0; m < L; m += 32) {
-        uint64_t x = read64(row, b + m) ^ extract64(text, (uint64_t)tp + m);
-        uint32_t rem = L - m;
-        if (rem < 32) x &= (1ull << (2 * rem)) - 1;
-        if (x) return false;
-    }
-    return true;
-}
-
 // number of equal bases of read[rb..] and text[tb..], at most max_ext
 __device__ __forceinline__ uint32_t match_len(const uint32_t* row, uint32_t rb, const uint64_t* __restrict__ text,
                                               uint32_t tb, uint32_t max_ext) {
@@ -214,25 +174,6 @@ __device__ __forceinline__ uint32_t uniq_run(const uint32_t* __restrict__ uniq, 
         if (run < avail) break;
     }
     return min(done, n);
-}
-
-enum { PROBE_MISS = 0, PROBE_UNIQUE = 1, PROBE_MULTI = 2 };
-
-// probe window b of a packed row: MISS, the UNIQUE posting, or MULTI (several postings)
-__device__ __forceinline__ int probe_window(const IndexView& ix, const uint32_t* row, uint32_t b, uint32_t& tp, uint32_t& node) {
-    const uint32_t L = ix.split_len;
-    const uint64_t h = hash_read(row, b, L);
-    uint32_t j = slot_of(h, ix.slot_mask);
-    while (true) {
-        const uint2 ent = __ldg(ix.slots + j);
-        if (ent.x == EMPTY_TP) return PROBE_MISS;
-        if (fp_match(ent.y, h, ix.node_mask) && read_equals_text(row, b, ix.text, ent.x, L)) {
-            tp = ent.x;
-            node = ent.y & ix.node_mask;
-            return ((__ldg(ix.uniq + (ent.x >> 5)) >> (ent.x & 31)) & 1) ? PROBE_UNIQUE : PROBE_MULTI;
-        }
-        j = (j + 1) & ix.slot_mask;
-    }
 }
 
 // add `hits` windows of `node` (smallest read position kminc) to the node list of read t
@@ -1088,253 +1029,6 @@ k_map_windows(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* _
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// CANDIDATE FOR THE NEXT ROUND (option two_err, default off; compiled, NOT yet run on a GPU -- see
-// DESIGN.md section 10, lead 1).  Most reads k_map_second gives up on have exactly two sequencing
-// errors, and k_map_fast spends ~4 000 warp instructions on each of them, mostly in thread-per-read
-// phases with 2-6 active lanes.  What is actually unknown about such a read is small:
-//   * a window covering NO error equals a text window on the walked diagonal (compared base by base)
-//     whose uniq bit is set                                            -> one hit, as before;
-//   * a window covering exactly ONE error equals a text window except for that base, and the clear
-//     substitution-hit bit (checked in every strand that holds such windows) proves it misses;
-//   * only the windows covering BOTH errors (there are L - (e2 - e1) of them, none if the errors are
-//     at least L apart) differ from the text in two bases: nothing is known about them.
-// k_map_second2 is k_map_second's flat walk with up to two tolerated errors; a read with a non-empty
-// "covers both" range is parked as a 64-byte record (its sorted-list entries + the range, in
-// forward-read window coordinates), and k_map_probe -- one warp per record, one lane per window --
-// looks those windows up.  All of them missing (what the reference's look-ups would find, and the
-// overwhelmingly common case) finishes the read from the record; anything else sends it on to
-// k_map_fast, untouched.
-// ---------------------------------------------------------------------------------------------
-struct __align__(16) ProbeRec {
-    uint32_t r;                      // read index
-    uint32_t range;                  // first unknown window | count << 16  (forward-read coordinates)
-    uint32_t nn, pad;
-    uint64_t e[FL_MAX];              // FlatList entries (unsorted)
-};
-static_assert(sizeof(ProbeRec) == 64, "ProbeRec is one 64-byte record");
-
-template <int STRIDE>
-__device__ __forceinline__ void
-map_second2_read(const IndexView& ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
-                 const uint32_t r, uint32_t* row, ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list,
-                 unsigned long long* __restrict__ out_count, ProbeRec* __restrict__ recs,
-                 unsigned long long* __restrict__ rec_count, uint32_t rec_cap) {
-    const uint32_t L = ix.split_len;
-    const uint32_t h = __ldg(hdr + r);
-    bool defer = (h & (PH_LONG | PH_BAD)) != 0 || ix.subst == nullptr;
-    const uint32_t rlen = h & 0xFFFFFF;
-    uint32_t nn = 0;
-    FlatList fl;
-    fl.clear();
-    bool resolved = false, mirror = false;
-    int ne = 0, e0 = 0, e1 = 0;                            // tolerated errors (walked-row positions, e0 < e1)
-    uint32_t rb0 = 0, rb1 = 0;                             // the read's bases there
-    const int npos = (int)(rlen - L + 1);
-    if (!defer) {
-        load_row<STRIDE, false>(rows, r, row_words, rlen, row, nullptr);
-        uint32_t tp = NONE32, node = 0;
-        int pr = probe_window(ix, row, 0, tp, node);
-        if (pr == PROBE_MISS) {
-            // reverse-complement the packed row in place
-            constexpr int NW = STRIDE - 3;
-            const uint32_t nwords = (rlen + 15) >> 4, pad = 16 * nwords - rlen;
-            uint32_t y[NW];
-            uint32_t prev = 0;
-#pragma unroll
-            for (int k = 0; k < NW; k++) {
-                y[k] = 0;
-                const int kk = NW - 1 - k;
-                if ((uint32_t)kk >= nwords) continue;
-                uint32_t rv = __brev(row[kk]);
-                rv = (((rv & 0x55555555u) << 1) | ((rv >> 1) & 0x55555555u)) ^ 0xAAAAAAAAu;
-                const int j = (int)nwords - 1 - kk;
-                if (j > 0) y[j - 1] = __funnelshift_r(prev, rv, 2 * pad);
-                prev = rv;
-            }
-            if (nwords) y[nwords - 1] = __funnelshift_r(prev, 0u, 2 * pad);
-#pragma unroll
-            for (int k = 0; k < NW; k++) row[k] = y[k];
-            mirror = true;
-            pr = probe_window(ix, row, 0, tp, node);
-        }
-        bool running = pr == PROBE_UNIQUE;
-        uint32_t i0 = 0, p = L, q = 0, lim = 0;
-        int delta = 0;
-        // does some window of the current strand that covers text base (e + delta), with read base rb there, have a posting?
-        auto subst_hit = [&](int e, uint32_t rb) -> bool {
-            const uint32_t te = (uint32_t)(e + delta);
-            return ((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u) != 0;
-        };
-        auto enter = [&]() -> bool {
-            const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
-            const bool rcs = tp >= s1;
-            q = 2 * node + (rcs ? 1u : 0u);
-            const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
-            delta = (int)tp - (int)i0;
-            lim = min(rlen, (uint32_t)((int)send - delta));
-            // a strand entered after an error still holds windows covering it if it starts at or before it
-            if (ne >= 1 && (int)i0 <= e0 && subst_hit(e0, rb0)) return false;
-            if (ne >= 2 && (int)i0 <= e1 && subst_hit(e1, rb1)) return false;
-            return true;
-        };
-        if (running && !enter()) running = false;
-        while (running) {
-            if (p < lim) {
-                const uint32_t n = min(32u, lim - p);
-                uint64_t x = read64(row, p) ^ extract64(ix.text, (uint64_t)((int)p + delta));
-                if (n < 32) x &= (1ull << (2 * n)) - 1;
-                bool ok = true;
-                while (x && ok) {                                  // every mismatching base of this chunk, left to right
-                    const uint32_t off = (uint32_t)(__ffsll((long long)x) - 1) >> 1;
-                    x &= ~(3ull << (2 * off));
-                    const int e = (int)(p + off);
-                    const uint32_t rb = (row[(uint32_t)e >> 4] >> (((uint32_t)e & 15) * 2)) & 3u;
-                    if (ne == 2) ok = false;                       // third error
-                    else {
-                        if (ne == 0) { e0 = e; rb0 = rb; } else { e1 = e; rb1 = rb; }
-                        ne++;
-                        if (subst_hit(e, rb)) ok = false;
-                    }
-                }
-                const uint32_t u = (uint32_t)((int)p + delta) - L + 1;
-                const uint32_t ub = __funnelshift_r(__ldg(ix.uniq + (u >> 5)), __ldg(ix.uniq + (u >> 5) + 1), u & 31);
-                const uint32_t m32 = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
-                if ((ub & m32) != m32) ok = false;
-                if (!ok) { running = false; break; }
-                p += n;
-            }
-            if (p >= lim) {
-                // windows [a, bw] of this node minus the windows covering an error: up to three runs
-                const int a = (int)i0, bw = (int)lim - (int)L;
-                int cnt = 0, first_hit = 0, last_hit = 0, lo = a;
-                const int es[2] = {e0, e1};
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const int hi = k < ne ? min(bw, es[k < 2 ? k : 1] - (int)L) : bw;
-                    if (k <= ne && hi >= lo) {
-                        if (cnt == 0) first_hit = lo;
-                        last_hit = hi;
-                        cnt += hi - lo + 1;
-                    }
-                    if (k < ne) lo = max(lo, es[k < 2 ? k : 1] + 1);
-                }
-                if (cnt > 0) {
-                    if (nn == (uint32_t)FL_MAX) { running = false; break; }
-                    fl.set(nn, node, (uint32_t)cnt | ((uint32_t)(mirror ? npos - 1 - last_hit : first_hit) << 16));
-                    nn++;
-                }
-                if (lim >= rlen) { resolved = true; running = false; break; }
-                const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
-                const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
-                if (sc.x == NONE32) { running = false; break; }
-                i0 = lim - L + 1;
-                tp = sc.x;
-                node = sc.y;
-                p = lim + 1;
-                if (!enter()) { running = false; break; }
-            }
-        }
-        if (!resolved) defer = true;
-    }
-    // windows covering both errors: walked-row coordinates [e1 - L + 1, e0] clipped to [0, npos)
-    if (!defer && ne == 2 && e1 - e0 < (int)L) {
-        const int ulo = max(e1 - (int)L + 1, 0), uhi = min(e0, npos - 1);
-        if (uhi >= ulo) {
-            const uint32_t cnt = (uint32_t)(uhi - ulo + 1);
-            const uint32_t lo_f = (uint32_t)(mirror ? npos - 1 - uhi : ulo);
-            const unsigned long long idx = atomicAdd(rec_count, 1ull);
-            if (idx < rec_cap) {
-                ProbeRec* rec = recs + idx;
-                rec->r = r;
-                rec->range = lo_f | (cnt << 16);
-                rec->nn = nn;
-                rec->pad = 0;
-#pragma unroll
-                for (int i = 0; i < FL_MAX; i++) rec->e[i] = fl.e[i];
-                return;                                            // k_map_probe finishes (or defers) this read
-            }
-            defer = true;                                          // record pool full: the full kernel decides
-        }
-    }
-    ReadSlot* out = slots + r;
-    uint32_t n_out = 0;
-    if (!defer) {
-        fl.sort();
-        fl.merge_repeats();
-        n_out = flat_finalize(fl, ix, rlen, L, out);
-    }
-    if (defer) {
-        out_list[atomicAdd(out_count, 1ull)] = r;
-        return;
-    }
-    out->hdr = ST_OK | (n_out << 8);
-}
-
-template <int STRIDE>
-__global__ void __launch_bounds__(MF_THREADS)
-k_map_second2(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
-              const uint32_t* __restrict__ in_list, const unsigned long long* __restrict__ in_count, uint32_t spread,
-              ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list, unsigned long long* __restrict__ out_count,
-              ProbeRec* __restrict__ recs, unsigned long long* __restrict__ rec_count, uint32_t rec_cap) {
-    __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
-    const uint64_t n_items = *in_count;
-    const uint32_t per_block = MF_THREADS / spread;
-    if (threadIdx.x % spread != 0) return;
-    for (uint64_t base = (uint64_t)blockIdx.x * per_block; base < n_items; base += (uint64_t)gridDim.x * per_block) {
-        const uint64_t item = base + threadIdx.x / spread;
-        if (item < n_items)
-            map_second2_read<STRIDE>(ix, rows, hdr, row_words, in_list[item], s_fwd + threadIdx.x * STRIDE, slots, out_list, out_count,
-                                     recs, rec_count, rec_cap);
-    }
-}
-
-// One warp per parked read: look up the windows that cover both errors (forward-read coordinates;
-// both strands of every node are indexed, so the forward window finds every posting).
-template <int STRIDE>
-__global__ void __launch_bounds__(128)
-k_map_probe(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
-            const ProbeRec* __restrict__ recs, const unsigned long long* __restrict__ rec_count, uint32_t rec_cap,
-            ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list, unsigned long long* __restrict__ out_count) {
-    __shared__ uint32_t s_row[4][STRIDE];
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned long long n_all = *rec_count;
-    const uint64_t n_items = n_all < rec_cap ? n_all : rec_cap;
-    const uint64_t gw = (uint64_t)blockIdx.x * 4 + wib, nw = (uint64_t)gridDim.x * 4;
-    const uint32_t L = ix.split_len;
-    uint32_t* row = s_row[wib];
-    for (uint64_t item = gw; item < n_items; item += nw) {
-        const ProbeRec* rec = recs + item;
-        const uint32_t r = rec->r, range = rec->range;
-        const uint32_t rlen = __ldg(hdr + r) & 0xFFFFFF, nwords = (rlen + 15) >> 4;
-        __syncwarp();
-        for (uint32_t w = lane; w < (uint32_t)STRIDE; w += 32) row[w] = w < nwords ? __ldg(rows + (uint64_t)r * row_words + w) : 0u;
-        __syncwarp();
-        const uint32_t lo = range & 0xFFFF, cnt = range >> 16;
-        bool clean = true;
-        for (uint32_t w0 = 0; w0 < cnt && clean; w0 += 32) {
-            const uint32_t w = w0 + lane;
-            uint32_t tp = 0, node = 0;
-            int res = PROBE_MISS;
-            if (w < cnt) res = probe_window(ix, row, lo + w, tp, node);
-            if (__any_sync(0xFFFFFFFFu, res != PROBE_MISS)) clean = false;
-        }
-        if (lane != 0) continue;
-        if (!clean) {                                              // a posting after all: the full kernel decides
-            out_list[atomicAdd(out_count, 1ull)] = r;
-            continue;
-        }
-        FlatList fl;
-#pragma unroll
-        for (int i = 0; i < FL_MAX; i++) fl.e[i] = rec->e[i];
-        fl.sort();
-        fl.merge_repeats();
-        ReadSlot* out = slots + r;
-        const uint32_t n_out = flat_finalize(fl, ix, rlen, L, out);
-        out->hdr = ST_OK | (n_out << 8);
-    }
-}
-
 int map_reads_generic_dev(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                           const uint32_t* d_worklist, const unsigned long long* d_n_items, ReadSlot* d_slots);
 
@@ -1388,24 +1082,7 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
             const uint32_t grid_s = (uint32_t)std::min<uint64_t>((n_reads * spread2 + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 16);
 #define VSPE_M2(S, GN) k_map_second<S, GN><<<grid_s, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->defer_list.p, \
                                                                            c->counters.p + CNT_DEFER, spread2, d_slots, list1b, c->counters.p + CNT_DEFER2)
-            if (c->opt_two_err) {
-                // candidate path (see k_map_second2): two tolerated errors, unknown windows parked for k_map_probe
-                const uint32_t rec_cap = (uint32_t)std::min<uint64_t>(n_reads / 2 + 1024, 0x7FFFFFFFull);
-                VSPE_TRY(c->probe_recs.reserve((size_t)rec_cap * sizeof(ProbeRec)));
-                VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_PROBE, 0, 8, c->stream));
-                ProbeRec* recs = reinterpret_cast<ProbeRec*>(c->probe_recs.p);
-#define VSPE_M22(S) k_map_second2<S><<<grid_s, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->defer_list.p, c->counters.p + CNT_DEFER, \
-                                                                     spread2, d_slots, list1b, c->counters.p + CNT_DEFER2, recs,                \
-                                                                     c->counters.p + CNT_PROBE, rec_cap)
-                if (cap <= 160) VSPE_M22(13); else if (cap <= 256) VSPE_M22(19); else VSPE_M22(23);
-#undef VSPE_M22
-                VSPE_LAUNCH_CHECK(c);
-                const uint32_t pgrid = (uint32_t)std::min<uint64_t>((rec_cap + 3) / 4, (uint64_t)c->sm_count * 16);
-#define VSPE_MP(S) k_map_probe<S><<<pgrid, 128, 0, c->stream>>>(v, d_rows, d_hdr, row_words, recs, c->counters.p + CNT_PROBE, rec_cap, d_slots, \
-                                                          list1b, c->counters.p + CNT_DEFER2)
-                if (cap <= 160) VSPE_MP(13); else if (cap <= 256) VSPE_MP(19); else VSPE_MP(23);
-#undef VSPE_MP
-            } else if (general) { if (cap <= 160) VSPE_M2(13, true); else if (cap <= 256) VSPE_M2(19, true); else VSPE_M2(23, true); }
+            if (general) { if (cap <= 160) VSPE_M2(13, true); else if (cap <= 256) VSPE_M2(19, true); else VSPE_M2(23, true); }
             else { if (cap <= 160) VSPE_M2(13, false); else if (cap <= 256) VSPE_M2(19, false); else VSPE_M2(23, false); }
 #undef VSPE_M2
             VSPE_LAUNCH_CHECK(c);

@@ -1,13 +1,15 @@
-// sparse.cu -- K5 + K6 for graphs whose dense N x N matrices cannot exist (e.g. the 200 000-node
-// stress config: 2 * N^2 * 8 B = 640 GB).
+// sparse.cu -- K6: radix sort + run-length reduce of weighted (matrix, i, j) keys.
 //
-// Replaces the accumulation loops of reference utils/VStrains_PE_Inference.py:174-188 with a
-// sorted run list (COO): key = mat*N*N + i*N + j (64 bit), count.  Exactly the north-star recipe:
-//   keys of a batch of pairs  ->  stable LSD radix sort (8-bit digits, only the digits the key
-//   range needs)  ->  run-length reduce (head flags + prefix sums)  ->  merged into the context's
-//   sorted run list by one more sort + reduce.  No atomics on the counts; integer sums only, so
-//   the result does not depend on batch or rank boundaries.
-#include "ctx.cuh"
+// The last step of the accumulation of reference utils/VStrains_PE_Inference.py:174-188 for every
+// graph size: key = mat*N*N + i*N + j (64 bit) with a weight (link.cu expands each distinct
+// combination of node lists once, weighted by its multiplicity).  The north-star recipe:
+//   stable LSD radix sort (8-bit digits, only the digits the key range needs)  ->  run-length
+//   reduce (head flags + prefix sums of the weights)  ->  runs (key, count), keys ascending.
+// Dense mode adds the runs to the N x N matrices; sparse mode (graphs whose matrices cannot exist,
+// e.g. the 200 000-node stress config: 2 * N^2 * 8 B = 640 GB) keeps them as the context's sorted
+// run list and merges new batches / other ranks' runs by one more sort + reduce.  No atomics on
+// the counts; integer sums only, so the result does not depend on batch or rank boundaries.
+#include "link.cuh"
 
 namespace vspe {
 
@@ -122,75 +124,6 @@ int device_scan_u64(Ctx* c, const unsigned long long* in, unsigned long long* ou
 }
 
 // ---------------------------------------------------------------------------------------------
-// keys of a batch of pairs
-// ---------------------------------------------------------------------------------------------
-struct ListRef64 {
-    const uint32_t* ids;
-    uint32_t n;
-};
-__device__ __forceinline__ ListRef64 list_of64(const ReadSlot* s, const uint32_t* __restrict__ spill) {
-    ListRef64 r;
-    r.n = s->hdr >> 8;
-    r.ids = r.n <= (uint32_t)SLOT_IDS ? s->ids : spill + s->ids[0];
-    return r;
-}
-__device__ __forceinline__ uint32_t pair_class64(uint32_t hf, uint32_t hr) {
-    const uint32_t sf = hf & 0xFF, sr = hr & 0xFF;
-    if (sf == ST_N || sr == ST_N) return 1;
-    if (sf == ST_SHORT || sr == ST_SHORT) return 2;
-    return 0;
-}
-
-// m[p] = number of keys of pair p (0 for skipped pairs) + the pair counters
-__global__ void __launch_bounds__(256)
-k_sparse_m(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uint64_t n_pairs, unsigned long long* __restrict__ m_out,
-           unsigned long long* __restrict__ counters) {
-    __shared__ unsigned long long s_cnt[4];
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n_pairs) {
-        const uint32_t hf = f[p].hdr, hr = r[p].hdr, cls = pair_class64(hf, hr);
-        unsigned long long m = 0;
-        if (cls == 0) {
-            const unsigned long long L = hf >> 8, R = hr >> 8;
-            m = L * (L + 1) / 2 + R * (R + 1) / 2 + L * R;
-            atomicAdd(&s_cnt[0], 1ull);
-            atomicAdd(&s_cnt[3], m);
-        } else {
-            atomicAdd(&s_cnt[cls], 1ull);
-        }
-        m_out[p] = m;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_cnt[0]) atomicAdd(&counters[CNT_USED], s_cnt[0]);
-        if (s_cnt[1]) atomicAdd(&counters[CNT_N], s_cnt[1]);
-        if (s_cnt[2]) atomicAdd(&counters[CNT_SHORT], s_cnt[2]);
-        if (s_cnt[3]) atomicAdd(&counters[CNT_KEYS], s_cnt[3]);
-    }
-}
-
-// PE_Inference.py:174-188 as 64-bit keys, written at the pair's exclusive offset
-__global__ void __launch_bounds__(256)
-k_sparse_emit(const ReadSlot* __restrict__ f, const ReadSlot* __restrict__ r, uint64_t n_pairs, uint64_t N,
-              const uint32_t* __restrict__ spill, const unsigned long long* __restrict__ off, unsigned long long* __restrict__ keys,
-              unsigned long long* __restrict__ vals) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    if (pair_class64(f[p].hdr, r[p].hdr) != 0) return;
-    const ListRef64 l = list_of64(f + p, spill), rr = list_of64(r + p, spill);
-    unsigned long long o = off[p];
-    const unsigned long long NN = N * N;
-    for (uint32_t a = 0; a < l.n; a++)
-        for (uint32_t b = a; b < l.n; b++) { keys[o] = NN + (unsigned long long)l.ids[a] * N + l.ids[b]; vals[o++] = 1; }
-    for (uint32_t a = 0; a < rr.n; a++)
-        for (uint32_t b = a; b < rr.n; b++) { keys[o] = NN + (unsigned long long)rr.ids[a] * N + rr.ids[b]; vals[o++] = 1; }
-    for (uint32_t a = 0; a < l.n; a++)
-        for (uint32_t b = 0; b < rr.n; b++) { keys[o] = (unsigned long long)l.ids[a] * N + rr.ids[b]; vals[o++] = 1; }
-}
-
-// ---------------------------------------------------------------------------------------------
 // stable LSD radix sort of (key, value) pairs, 8-bit digits.  One warp per 4096-element tile:
 //   k_radix_hist     per-tile digit histogram -> hist[digit][tile]
 //   (exclusive scan over hist in digit-major order = global offset of every (digit, tile))
@@ -272,8 +205,15 @@ k_rle_counts(const unsigned long long* __restrict__ run_start, uint64_t n_runs, 
 
 // sort (keys, vals)[0..n) by key and reduce equal keys by summing their values.
 // In / out in sp.k[0], sp.v[0]; the other buffers are scratch.  Returns the number of runs.
-static int sort_reduce(Ctx* c, uint64_t n, uint32_t key_bits, uint64_t* n_runs_out) {
+static uint32_t bits_for(uint64_t cells) {
+    uint32_t b = 1;
+    while (b < 64 && (1ull << b) < cells) b++;
+    return b;
+}
+
+int sparse_sort_reduce(Ctx* c, uint64_t n, uint64_t* n_runs_out) {
     Sparse& sp = c->sparse;
+    const uint32_t key_bits = bits_for(2ull * c->index.n_nodes * c->index.n_nodes);
     *n_runs_out = 0;
     if (n == 0) return VSPE_OK;
     if (n > 0xFFFFFFF0ull) { set_error("sparse batch too large"); return VSPE_ERR_LIMIT; }
@@ -318,58 +258,14 @@ static int sort_reduce(Ctx* c, uint64_t n, uint32_t key_bits, uint64_t* n_runs_o
     return VSPE_OK;
 }
 
-static uint32_t bits_for(uint64_t cells) {
-    uint32_t b = 1;
-    while (b < 64 && (1ull << b) < cells) b++;
-    return b;
-}
-
 // make room for `extra` more elements after the first `keep` ones (both double buffers)
-static int sparse_reserve(Ctx* c, uint64_t total) {
+int sparse_reserve(Ctx* c, uint64_t total) {
     Sparse& sp = c->sparse;
     for (int b = 0; b < 2; b++) {
         VSPE_TRY(sp.k[b].reserve(total + 8, b == 0, c->stream));
         VSPE_TRY(sp.v[b].reserve(total + 8, b == 0, c->stream));
     }
     if (!sp.totals.p) VSPE_TRY(sp.totals.reserve(4));
-    return VSPE_OK;
-}
-
-int count_pairs_sparse(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total) {
-    Sparse& sp = c->sparse;
-    const uint64_t N = c->index.n_nodes;
-    c->stats.total_pairs += total;
-    if (total == 0) return VSPE_OK;
-    const uint32_t key_bits = bits_for(2ull * N * N);
-    const uint64_t BATCH = 2ull << 20;                        // pairs per batch
-    cudaStream_t st = c->stream;
-    for (uint64_t off = 0; off < total; off += BATCH) {
-        const uint64_t n = std::min<uint64_t>(BATCH, total - off);
-        const uint32_t grid = (uint32_t)((n + 255) / 256);
-        VSPE_TRY(sp.m.reserve(n + 4));
-        VSPE_TRY(sp.moff.reserve(n + 4));
-        VSPE_TRY(sp.sums64.reserve(n / SC_TILE + 8));
-        if (!sp.totals.p) VSPE_TRY(sp.totals.reserve(4));
-        k_sparse_m<<<grid, 256, 0, st>>>(d_f + off, d_r + off, n, sp.m.p, c->counters.p);
-        VSPE_LAUNCH_CHECK(c);
-        VSPE_TRY(device_exclusive_scan<unsigned long long>(c, sp.m.p, sp.moff.p, n, sp.sums64.p, sp.totals.p + 2));
-        unsigned long long n_keys = 0, h_err = 0;
-        VSPE_CUDA(cudaMemcpyAsync(&n_keys, sp.totals.p + 2, 8, cudaMemcpyDeviceToHost, st));
-        VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, st));
-        VSPE_CUDA(cudaStreamSynchronize(st));
-        c->last_err_flags = h_err;
-        c->err_flags_fresh = true;
-        if (n_keys == 0) continue;
-        // the accumulated runs stay at the front of k[0]/v[0]; the batch keys go right behind them
-        VSPE_TRY(sparse_reserve(c, sp.n_runs + n_keys));
-        k_sparse_emit<<<grid, 256, 0, st>>>(d_f + off, d_r + off, n, N, c->spill.p, sp.moff.p,
-                                            reinterpret_cast<unsigned long long*>(sp.k[0].p) + sp.n_runs,
-                                            reinterpret_cast<unsigned long long*>(sp.v[0].p) + sp.n_runs);
-        VSPE_LAUNCH_CHECK(c);
-        uint64_t runs = 0;
-        VSPE_TRY(sort_reduce(c, sp.n_runs + n_keys, key_bits, &runs));
-        sp.n_runs = runs;
-    }
     return VSPE_OK;
 }
 
@@ -381,7 +277,7 @@ int sparse_merge_host(Ctx* c, const uint64_t* keys, const uint64_t* counts, uint
     VSPE_CUDA(cudaMemcpyAsync(sp.k[0].p + sp.n_runs, keys, n * 8, cudaMemcpyHostToDevice, c->stream));
     VSPE_CUDA(cudaMemcpyAsync(sp.v[0].p + sp.n_runs, counts, n * 8, cudaMemcpyHostToDevice, c->stream));
     uint64_t runs = 0;
-    VSPE_TRY(sort_reduce(c, sp.n_runs + n, bits_for(2ull * c->index.n_nodes * c->index.n_nodes), &runs));
+    VSPE_TRY(sparse_sort_reduce(c, sp.n_runs + n, &runs));
     sp.n_runs = runs;
     return VSPE_OK;
 }

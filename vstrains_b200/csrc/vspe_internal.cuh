@@ -172,6 +172,23 @@ struct __align__(64) ReadSlot {
 static constexpr uint32_t ST_OK = 0, ST_N = 1, ST_SHORT = 2;
 
 // ---------------------------------------------------------------------------------------
+// Link stage records (link.cuh): one 64-byte record per distinct node list, one 16-byte
+// entry per distinct (left list, right list) combination of a batch of read pairs.
+// ---------------------------------------------------------------------------------------
+static constexpr int LR_IDS = 13;
+struct __align__(64) ListRec {
+    uint32_t tag;                 // table part: list fingerprint | 1 (0 = free slot)
+    uint32_t nplus1;              // ids + 1 (0 = not yet published)
+    uint32_t used;                // used pairs of the current batch with this list as a mate (short_mat weight)
+    uint32_t ids[LR_IDS];         // n <= LR_IDS: node index + 1; longer: ids[0] = offset into the spill pool
+};
+struct __align__(16) PairEnt {
+    unsigned long long key1;      // ((handle_left << 32) | handle_right) + 1, 0 = free
+    uint32_t count;               // pairs of the batch with this combination (node_mat weight)
+    uint32_t pad;
+};
+
+// ---------------------------------------------------------------------------------------
 // simple owning device buffer
 // ---------------------------------------------------------------------------------------
 template <class T>
@@ -264,12 +281,8 @@ int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start,
 // after a stream sync: choose the lean / general walk kernels for the next map launch
 int adapt_map_variant(Ctx* c);
 
-// K5+K6: pairs [0, total) of two slot arrays -> += into dense matrices
-int count_pairs(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total);
-
-int count_pairs_sparse(Ctx* c, const ReadSlot* d_f, const ReadSlot* d_r, uint64_t total);
 int sparse_merge_host(Ctx* c, const uint64_t* keys, const uint64_t* counts, uint64_t n);
-// dense counting needs 2*N*N <= 2^32 cells in <= 8192 buckets of <= 2^15 cells
+// dense matrices are kept for 2*N*N <= 2^28 cells (2 GiB of uint64); larger graphs count sparsely
 inline bool dense_possible(uint64_t n_nodes) { return 2ull * n_nodes * n_nodes <= (8192ull << 15); }
 
 }  // namespace vspe
