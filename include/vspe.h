@@ -138,6 +138,16 @@ int vspe_sparse_host(vspe_ctx* ctx, uint64_t* n_entries, const uint64_t** keys, 
 int vspe_sparse_merge(vspe_ctx* ctx, const uint64_t* keys, const uint64_t* counts, uint64_t n_entries);
 int vspe_write_info_sparse(const char* path, const char* const* ids, uint32_t n, const uint64_t* keys,
                            const uint64_t* counts, uint64_t n_entries, int mat);
+/* The same run list in device memory (valid until the next counting / merge call on the context), and
+ * a merge of runs that already live on this context's device -- what a multi-GPU caller needs to
+ * exchange the runs with ONE all-gather over NVLink instead of a host round trip. */
+int vspe_sparse_device(vspe_ctx* ctx, uint64_t* n_entries, uint64_t** d_keys, uint64_t** d_counts);
+int vspe_sparse_merge_device(vspe_ctx* ctx, const uint64_t* d_keys, const uint64_t* d_counts, uint64_t n_entries);
+
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on.  Work a caller
+ * enqueues on it (e.g. the NCCL allreduce of vspe_matrices_device) is ordered after the counting calls
+ * without a host synchronisation. */
+void* vspe_stream(vspe_ctx* ctx);
 
 /* Input files of vspe_run: the bytes of a plain file, or of a gzip file (RFC 1952, concatenated
  * members included) inflated in memory -- detected by the magic bytes.  The reference reads plain

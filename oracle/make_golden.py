@@ -20,7 +20,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from vstrains_b200 import synth  # noqa: E402
+import synthgen as synth  # noqa: E402
 
 REF = "/root/reference/utils/VStrains_PE_Inference.py"
 OUT = os.path.join(ROOT, "tests", "golden")

@@ -1,6 +1,7 @@
 """Deterministic synthetic quasispecies graphs + paired-end reads.
 
-Test / bench tooling only: this module produces the *inputs* the hot path consumes,
+Test / bench tooling only (not part of the product package): this module produces the *inputs* the
+hot path consumes,
 in the formats the reference reads:
 
 * a ``s_graph_L1.gfa``-dialect assembly graph (``S\\t<id>\\t<SEQ>\\tDP:f:<cov>`` then
@@ -355,3 +356,58 @@ def write_dataset(cfg: Config, out_dir: str, pairs: Optional[int] = None) -> Dic
     with open(paths["paths"], "wb") as fh:
         fh.write(g.to_paths())
     return paths
+
+
+# ----------------------------------------------------------------------------------------
+# fast generator (C, OpenMP): bench-size inputs in seconds
+# ----------------------------------------------------------------------------------------
+_FQ = None
+
+
+def _fq_lib():
+    """libfastqgen.so (synthgen/fastq_gen.c), built on first use."""
+    global _FQ
+    if _FQ is None:
+        import ctypes
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        path = os.path.join(here, "libfastqgen.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-s", "-C", here])
+        _FQ = ctypes.CDLL(path)
+    return _FQ
+
+
+def make_reads_fast(genomes: List[np.ndarray], ab: np.ndarray, read_len: int, pairs: int, k: int, seed: int,
+                    first_idx: int = 0, sub_rate: float = 0.001, n_rate: float = 0.005, short_rate: float = 0.005,
+                    out: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """Same read model as :func:`make_reads` from a counter-based random stream keyed by
+    (seed, pair index): pairs [first_idx, first_idx + pairs) are the same bytes whatever range they
+    are generated in.  ``out``: optional (fwd, rve) uint8 buffers of at least
+    ``pairs * (2 * read_len + 18)`` bytes (e.g. pinned host memory); views of the filled parts are
+    returned."""
+    import ctypes
+
+    class P(ctypes.Structure):
+        _fields_ = [("genomes", ctypes.c_void_p), ("n_genomes", ctypes.c_uint64), ("strains", ctypes.c_uint64),
+                    ("G", ctypes.c_uint64), ("ab_cdf", ctypes.c_void_p), ("read_len", ctypes.c_uint32), ("k", ctypes.c_uint32),
+                    ("sub_rate", ctypes.c_double), ("n_rate", ctypes.c_double), ("short_rate", ctypes.c_double),
+                    ("seed", ctypes.c_uint64)]
+    stack = np.ascontiguousarray(np.stack(genomes).astype(np.uint8))            # [n_genomes, S, G]
+    cdf = np.ascontiguousarray(np.cumsum(np.asarray(ab, dtype=np.float64)))
+    cdf[-1] = 1.0
+    cap = pairs * (2 * read_len + 18)
+    if out is None:
+        out = (np.empty(cap, dtype=np.uint8), np.empty(cap, dtype=np.uint8))
+    f, r = out
+    assert f.size >= cap and r.size >= cap and f.dtype == np.uint8 and r.dtype == np.uint8
+    prm = P(stack.ctypes.data, stack.shape[0], stack.shape[1], stack.shape[2], cdf.ctypes.data, read_len, k,
+            sub_rate, n_rate, short_rate, seed)
+    nf, nr = ctypes.c_uint64(), ctypes.c_uint64()
+    lib = _fq_lib()
+    lib.fq_generate.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_void_p]
+    rc = lib.fq_generate(ctypes.byref(prm), first_idx, pairs, f.ctypes.data, r.ctypes.data, ctypes.byref(nf), ctypes.byref(nr))
+    if rc != 0:
+        raise ValueError("fq_generate: bad parameters")
+    return f[: nf.value], r[: nr.value]

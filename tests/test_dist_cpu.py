@@ -12,7 +12,8 @@ import torch.multiprocessing as mp
 
 from oracle import c_oracle, pe_oracle
 from vstrains_b200 import dist as vdist
-from vstrains_b200 import shard, synth
+import synthgen as synth
+from vstrains_b200 import shard
 
 
 def _free_port():

@@ -9,7 +9,8 @@ import pytest
 
 from conftest import ROOT
 from oracle import c_oracle, pe_oracle
-from vstrains_b200 import pe_inference, synth
+import synthgen as synth
+from vstrains_b200 import pe_inference
 from vstrains_b200._lib import VspeError
 
 pytestmark = pytest.mark.gpu
@@ -25,11 +26,13 @@ VARIANTS = [
     {"scan_mode": 3},                                   # fused scan+pack with look-back
     {"scan_mode": 0, "map_general": 0},                 # lean walk kernels (reads with > 6 stretches deferred)
     {"scan_mode": 0, "map_general": 1},                 # general walk kernels (up to 16 stretches in place)
+    {"scan_mode": 4},                                   # fused scan + pack + walk (one pass over the bytes)
+    {"scan_mode": 4, "subst": 0},                       # ... without the substitution-hit bitmap
 ]
 
 
 def _variant_id(o):
-    return ",".join("%s=%s" % kv for kv in o.items())
+    return ",".join("%s%s" % kv for kv in o.items())
 
 
 def _info(ids, mat, tmp_path, name):
@@ -124,7 +127,7 @@ def test_record_split_edge_cases(two_pass):
                 assert fq[int(start[r]):int(start[r]) + int(length[r])].decode() == lines[4 * r + 1][:-1]
 
 
-@pytest.mark.parametrize("force_generic,scan_mode", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("force_generic,scan_mode", [(0, 0), (0, 1), (1, 1), (0, 4)])
 def test_per_read_mapping_matches_oracle(golden, force_generic, scan_mode):
     if golden.status != 0:
         return
@@ -160,7 +163,7 @@ def test_chunked_streaming_equals_single_chunk():
     g, f, r = synth.generate(cfg, pairs=9000)
     ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())
     res = []
-    for chunk_mb, two_pass, scan_mode in ((256, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 0, 3)):
+    for chunk_mb, two_pass, scan_mode in ((256, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 0, 3), (1, 0, 4), (256, 0, 4)):
         with pe_inference.PEIndex(seqs, cfg.k) as ix:
             ix.set_option("chunk_mb", chunk_mb)
             ix.set_option("scan_two_pass", two_pass)
@@ -254,6 +257,44 @@ def test_cli_multi_gpu_is_byte_identical(tmp_path):
     assert outs[0] == outs[1]
 
 
+def test_cli_multi_gpu_sparse_merge_is_identical(tmp_path):
+    """vspe_run with n_gpus = 2 in sparse mode: the runs are exchanged with NCCL all-gathers and
+    merged on device 0; the files must equal the single-GPU sparse files line for line."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cfg = synth.CONFIGS["C3"]
+    g, f, r = synth.generate(cfg, pairs=5000)
+    (tmp_path / "g.gfa").write_bytes(g.to_gfa())
+    f.tofile(tmp_path / "f.fq")
+    r.tofile(tmp_path / "r.fq")
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / ("aln%d" % gpus)
+        env = dict(os.environ, VSPE_GPUS=str(gpus), VSPE_SPARSE="1")
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "utils", "VStrains_PE_Inference.py"), "-g", str(tmp_path / "g.gfa"),
+                            "-o", str(out), "-f", str(tmp_path / "f.fq"), "-r", str(tmp_path / "r.fq"), "-k", str(cfg.k)],
+                           capture_output=True, env=env)
+        assert p.returncode == 0, p.stderr.decode()
+        outs.append(((out / "pe_info").read_bytes(), (out / "st_info").read_bytes()))
+    assert outs[0] == outs[1]
+    assert len(outs[0][0]) > 0
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_torchrun_nccl_ranks_match_oracle(world):
+    """One process per GPU (torchrun, NCCL): dist.run_rank on record-aligned shards + one allreduce
+    must reproduce the C oracle's matrices of the whole input on every rank."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs >= %d GPUs" % world)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", str(29513 + world),
+                        os.path.join(ROOT, "tests", "nccl_rank_check.py"), "C3", "20000"], capture_output=True, timeout=600)
+    assert p.returncode == 0, (p.stdout.decode()[-2000:], p.stderr.decode()[-2000:])
+    assert p.stdout.decode().count("bit-exact") == world
+
+
 def _mk_fastq(seqs, nl=b"\n"):
     return b"".join(b"@r" + nl + s + nl + b"+" + nl + b"I" * len(s) + nl for s in seqs)
 
@@ -268,7 +309,7 @@ def _decoy_fastq(seqs, seq_prefix):
     return b"".join(out)
 
 
-@pytest.mark.parametrize("scan_mode", [0, 1, 3])
+@pytest.mark.parametrize("scan_mode", [0, 1, 3, 4])
 def test_whole_path_edge_shapes(scan_mode):
     """Shapes that stress the tiled scan: thousands of tiny records per tile (fallback path),
     reads longer than the packed rows / the scan margin, CRLF and lone-CR files, reads that
@@ -306,9 +347,9 @@ def test_whole_path_edge_shapes(scan_mode):
             assert stats[k] == v, (name, k)
 
 
-@pytest.mark.parametrize("subst,full_second,fast_tier", [(1, 0, 1), (0, 1, 1), (1, 1, 1)])
+@pytest.mark.parametrize("subst,full_second,fast_tier,scan_mode", [(1, 0, 1, 0), (0, 1, 1, 0), (1, 1, 1, 0), (1, 0, 1, 4), (0, 0, 1, 4)])
 @pytest.mark.parametrize("sub_rate", [0.002, 0.01, 0.04])
-def test_noisy_reads_match_c_oracle(subst, full_second, fast_tier, sub_rate):
+def test_noisy_reads_match_c_oracle(subst, full_second, fast_tier, scan_mode, sub_rate):
     """1 % and 4 % substitution rates: several errors per read, errors next to node ends and to
     each other, reads that follow another strain's bubble arm after an error."""
     for name, pairs in (("C2", 4000), ("C3", 3000)):
@@ -317,7 +358,7 @@ def test_noisy_reads_match_c_oracle(subst, full_second, fast_tier, sub_rate):
         g, genomes, ab = synth.make_graph(cfg, rng, 10.0)
         f, r = synth.make_reads(genomes, ab, cfg.read_len, pairs, cfg.k, rng, sub_rate=sub_rate)
         gfa = g.to_gfa()
-        ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"subst": subst, "full_second": full_second, "fast_tier": fast_tier})
+        ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"subst": subst, "full_second": full_second, "fast_tier": fast_tier, "scan_mode": scan_mode})
         onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
         assert np.array_equal(node.astype(np.int64), onode), name
         assert np.array_equal(short.astype(np.int64), oshort), name
@@ -443,3 +484,69 @@ def test_full_size_c2_matches_c_oracle_and_invariants():
     assert np.array_equal(short.astype(np.int64), oshort)
     for k, v in ostats.items():
         assert st[k] == v
+
+
+@pytest.mark.parametrize("name,block,replay", [("C3", 10_000_000, 1), ("C4", 10_000_000, 2)])
+def test_full_size_blocks_invariants_and_oracle_subsample(name, block, replay):
+    """BASELINE.json configs[2] (10 M pairs 2x150) and the 10 M-pair unique block of configs[3] (replayed:
+    the counts must scale exactly by the replay factor) at full size on one GPU: the counters
+    partition the pairs, every link key is in the matrices, short_mat is upper triangular, two runs
+    are identical; the first 100 000 pairs of the same stream are bit-exact against the C oracle."""
+    import bench
+    cfg, g, genomes, ab = bench.make_graph(name, block * replay)
+    f, r = bench.make_reads(cfg, genomes, ab, block, 0)
+    gfa = g.to_gfa()
+    ids, seqs = pe_inference.parse_gfa_nodes(gfa)
+    with pe_inference.PEIndex(seqs, cfg.k) as ix:
+        ix.count_host(f, r)
+        node1, short1 = ix.matrices()
+        st1 = ix.stats()
+        for _ in range(replay - 1):
+            ix.count_host(f, r)
+        node, short = ix.matrices()
+        st = ix.stats()
+        ix.reset()
+        for _ in range(replay):
+            ix.count_host(f, r)
+        node2, short2 = ix.matrices()
+        assert np.array_equal(node, node2) and np.array_equal(short, short2)          # determinism
+        assert np.array_equal(node, node1 * np.uint64(replay)) and np.array_equal(short, short1 * np.uint64(replay))
+        assert st1["total_pairs"] == block == st1["n_pairs"] + st1["short_pairs"] + st1["used_pairs"]
+        assert st["total_pairs"] == block * replay
+        assert int(node.sum()) + int(short.sum()) == st["n_keys"] == replay * st1["n_keys"]
+        assert int(np.tril(short, -1).sum()) == 0
+        # oracle on a sub-sample of the same stream
+        sub = 100_000
+        fs, rs = bench.prefix_pairs(f, r, 0, sub, cfg.read_len)
+        ix.reset()
+        ix.count_host(fs, rs)
+        sn, ss = ix.matrices()
+        sst = ix.stats()
+    onode, oshort, ostats = c_oracle.run(gfa, fs, rs, cfg.k)
+    assert np.array_equal(sn.astype(np.int64), onode)
+    assert np.array_equal(ss.astype(np.int64), oshort)
+    for k, v in ostats.items():
+        assert sst[k] == v
+
+
+def test_many_long_node_lists_grow_the_pools():
+    """reads that map to more nodes than a list record / slot holds (a graph of many nodes with a
+    one-base overhang) need private list records and spill words by the million; the pools grow and the
+    launch is repeated instead of failing with VSPE_ERR_LIMIT."""
+    rng = np.random.default_rng(77)
+    k = 31
+    genome = rng.integers(0, 4, size=4000, dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    # nodes = every (k+2)-window of the genome: consecutive nodes overlap by k+1, each holds two (k+1)-mers
+    seqs = [acgt[genome[i:i + k + 2]].tobytes() for i in range(0, genome.size - k - 2)]
+    gfa = b"".join(b"S\t%d\t%s\n" % (i, s) for i, s in enumerate(seqs))
+    n_reads, rl = 40000, 100
+    starts = rng.integers(0, genome.size - rl, size=n_reads)
+    reads = [acgt[genome[s:s + rl]].tobytes() for s in starts]
+    fq = _mk_fastq(reads)
+    ids, node, short, stats = pe_inference.pe_inference(gfa, fq, fq, k)
+    onode, oshort, ostats = c_oracle.run(gfa, fq, fq, k)
+    assert np.array_equal(node.astype(np.int64), onode)
+    assert np.array_equal(short.astype(np.int64), oshort)
+    for kk, v in ostats.items():
+        assert stats[kk] == v

@@ -2,7 +2,8 @@
 import sys
 import numpy as np
 sys.path.insert(0, '.')
-from vstrains_b200 import pe_inference, synth
+import synthgen as synth
+from vstrains_b200 import pe_inference
 cfg = synth.CONFIGS["C1"]
 g, f, r = synth.generate(cfg, pairs=9000)
 ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())

@@ -2,7 +2,8 @@
 import glob, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from vstrains_b200 import pe_inference, synth
+import synthgen as synth
+from vstrains_b200 import pe_inference
 for p in sorted(glob.glob("tests/golden/*.npz"))[:8] + ["tests/golden/synth_2x250_k127.npz", "tests/golden/synth_2x150_k77.npz"]:
     z = np.load(p)
     if int(z["status"]) != 0:

@@ -32,6 +32,10 @@ int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, co
 int map_reads_packed(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                      const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
                      uint64_t n_reads, ReadSlot* d_slots);
+int map_prepare_lists(Ctx* c, uint64_t n_reads);
+int map_reads_deferred(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                       const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
+                       uint64_t n_reads_cap, ReadSlot* d_slots);
 uint32_t map_fast_cap(uint32_t hint);
 int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len,
                   const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve, int n_gpus,
@@ -62,7 +66,7 @@ static int check_kernel_errors(Ctx* c) {
 static int scan_mode_of(Ctx* c) {
     int mode = (int)c->opt_scan_mode;
     if (c->opt_scan_two_pass) mode = 2;
-    if ((c->opt_force_generic || c->index.split_len > 320) && (mode == 0 || mode == 3)) mode = 1;
+    if ((c->opt_force_generic || c->index.split_len > 320) && (mode == 0 || mode == 3 || mode == 4)) mode = 1;
     return mode;
 }
 
@@ -75,6 +79,63 @@ static int retry_after_pool_overflow(Ctx* c, unsigned long long flags, const uns
     VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_OVF, &cur0[1], 8, cudaMemcpyHostToDevice, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     return link_grow_overflow(c);
+}
+
+// One chunk through the fused kernel (scan_mode 4): k_scan_map -> list-driven tiers on what it left
+// unresolved -> their slots interned -> one host sync (terminator count + error flags).  A launch whose
+// guessed table size was too small, or that ran out of list records / spill words, is repeated
+// (every step is idempotent).  *fell_back: a tile owned more reads than the kernel's table holds
+// (records of a few bytes): the caller takes the plain path for this chunk.
+static int feed_chunk_fused(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint64_t n, bool* fell_back, uint64_t* n_terms_out,
+                            uint64_t* n_seq_out) {
+    MateBuf& mb = c->mate[m];
+    *fell_back = false;
+    const uint64_t lb = ms.line_base, rec_first = seq_lines_before(lb);
+    const uint32_t cap = map_fast_cap(c->read_len_hint);
+    const uint32_t row_words = cap <= 160 ? 12 : cap <= 256 ? 16 : 20;
+    uint64_t guess = n / (2ull * std::max<uint32_t>(c->read_len_hint, 20) + 8) * 21 / 20 + 4096;
+    cudaEvent_t e0 = c->ev_m[m][0], e1 = c->ev_m[m][1], e2 = c->ev_m[m][2];
+    VSPE_CUDA(cudaEventRecord(e0, c->stream));
+    for (int attempt = 0;; attempt++) {
+        VSPE_TRY(mb.handles.reserve(rec_first + guess + 2, true, c->stream));
+        VSPE_TRY(mb.rec.seq_start.reserve(guess + 2));
+        VSPE_TRY(mb.rec.seq_end.reserve(guess + 2));
+        VSPE_TRY(mb.rec.hdr.reserve(guess + 2));
+        VSPE_TRY(mb.rec.rows.reserve((guess + 2) * row_words));
+        VSPE_TRY(mb.slots.reserve(guess + 2));                  // slots of the unresolved reads (chunk-local index)
+        VSPE_TRY(map_prepare_lists(c, guess + 2));
+        unsigned long long cur0[2] = {0, 0}, h_total = 0, h_err = 0;
+        VSPE_CUDA(cudaMemcpyAsync(&cur0[0], c->counters.p + CNT_SPILL_CURSOR, 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_CUDA(cudaMemcpyAsync(&cur0[1], c->counters.p + CNT_OVF, 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_TRY(scan_map(c, d_buf, n, lb, rec_first, guess, mb.handles.p + rec_first, mb.rec.seq_start.p, mb.rec.seq_end.p,
+                          mb.rec.rows.p, mb.rec.hdr.p, c->defer_list.p, row_words, cap));
+        if (attempt == 0) VSPE_CUDA(cudaEventRecord(e1, c->stream));
+        VSPE_TRY(map_reads_deferred(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p, row_words, cap,
+                                    guess, mb.slots.p));
+        VSPE_TRY(intern_slots(c, mb.slots.p, guess, c->defer_list.p, c->counters.p + CNT_DEFER, mb.handles.p + rec_first));
+        VSPE_CUDA(cudaMemcpyAsync(&h_total, scan_map_total_ptr(c, n, d_buf), 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_CUDA(cudaStreamSynchronize(c->stream));
+        scan_map_account(c);
+        const uint64_t n_seq = seq_lines_before(lb + h_total) - rec_first;
+        const unsigned long long transient = ERRF_SLOTS_FULL | ERRF_TILE_FULL;
+        if (h_err & transient) {
+            const unsigned long long cleared = h_err & ~transient;
+            VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_ERR, &cleared, 8, cudaMemcpyHostToDevice, c->stream));
+            VSPE_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        *n_terms_out = h_total;
+        *n_seq_out = n_seq;
+        if (h_err & ERRF_TILE_FULL) { *fell_back = true; return VSPE_OK; }
+        if (attempt < 8 && (h_err & (ERRF_LISTS_FULL | ERRF_SPILL_FULL))) {
+            VSPE_TRY(retry_after_pool_overflow(c, h_err, cur0));
+            continue;
+        }
+        if (attempt < 8 && n_seq > guess) { guess = n_seq; continue; }          // the guessed table was too small
+        break;
+    }
+    VSPE_CUDA(cudaEventRecord(e2, c->stream));
+    return VSPE_OK;
 }
 
 // prepared: the count pass of this chunk was already queued (scan_pack_prepare_launch)
@@ -97,6 +158,29 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     const uint32_t row_words = cap <= 160 ? 12 : cap <= 256 ? 16 : 20;
     int mode = scan_mode_of(c);
     bool packed = false;
+    if (mode == 4) {
+        bool fell_back = false;
+        VSPE_TRY(feed_chunk_fused(c, m, ms, d_buf, n, &fell_back, &n_terms, &n_seq));
+        if (!fell_back) {
+            if (sync_after) {                             // (streaming callers: account the stage times now)
+                VSPE_CUDA(cudaStreamSynchronize(c->stream));
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, e0, e1);
+                cudaEventElapsedTime(&b, e1, e2);
+                c->stats.ms_scan += a;
+                c->stats.ms_map += b;
+            }
+            ms.n_slots = rec_first + n_seq;
+            ms.line_base = lb + n_terms;
+            if (is_last) {
+                bool term = last_byte == '\n' || last_byte == '\r';
+                ms.lines = ms.line_base + (term ? 0 : 1);
+            }
+            return VSPE_OK;
+        }
+        mode = 1;
+        VSPE_CUDA(cudaEventRecord(e0, c->stream));
+    }
     if (mode == 0) {
         // count pass (terminator masks, no inter-tile dependency) + device scan, then the pack
         // pass with exactly sized outputs
@@ -280,8 +364,8 @@ static uint32_t seq_len_hint(const uint8_t* p, uint64_t n) {
     return (uint32_t)std::min<uint64_t>(best, 1u << 20);
 }
 
-static void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t n) {
-    unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+static void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t n, unsigned max_threads) {
+    unsigned nt = std::min(std::max(1u, max_threads), std::max(1u, std::thread::hardware_concurrency()));
     if (n < (8u << 20) || nt == 1) { memcpy(dst, src, n); return; }
     std::vector<std::thread> th;
     size_t per = (n + nt - 1) / nt;
@@ -344,7 +428,7 @@ static int stream_mates_host(Ctx* c, MateStream* ms, const uint8_t* const* srcs,
         int b = (int)(i & 1);
         const Piece& p = pieces[i];
         const uint8_t* from = srcs[p.m] + p.lo;
-        if (!pinned_src[p.m]) { parallel_memcpy(c->pinned[b], from, p.hi - p.lo); from = c->pinned[b]; }
+        if (!pinned_src[p.m]) { parallel_memcpy(c->pinned[b], from, p.hi - p.lo, (unsigned)c->opt_stage_threads); from = c->pinned[b]; }
         VSPE_CUDA(cudaMemcpyAsync(c->dev_in[b].p, from, p.hi - p.lo, cudaMemcpyHostToDevice, c->copy_stream[b]));
         VSPE_CUDA(cudaEventRecord(copied[b], c->copy_stream[b]));
         return VSPE_OK;
@@ -634,7 +718,7 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     float ms_total = 0;
     cudaEventElapsedTime(&ms_total, t0, t1);
-    c->stats.ms_total = ms_total;
+    c->stats.ms_total += ms_total;
     scan_pack_account(c);
     if (prelaunch && c->ev_m[0][0] && ns[0]) {
         // the count passes of both mates ran between the start of the call and mate 0's first event
@@ -674,7 +758,7 @@ int vspe_count_host(vspe_ctx* c, const uint8_t* fwd, uint64_t n_fwd, const uint8
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     float ms_total = 0;
     cudaEventElapsedTime(&ms_total, t0, t1);
-    c->stats.ms_total = ms_total;
+    c->stats.ms_total += ms_total;
     c->stats.bytes_fwd += n_fwd;
     c->stats.bytes_rve += n_rve;
     return VSPE_OK;
@@ -709,6 +793,23 @@ int vspe_sparse_merge(vspe_ctx* c, const uint64_t* keys, const uint64_t* counts,
 }
 
 int vspe_is_sparse(vspe_ctx* c) { return c && c->sparse.enabled ? 1 : 0; }
+
+int vspe_sparse_device(vspe_ctx* c, uint64_t* n_entries, uint64_t** d_keys, uint64_t** d_counts) {
+    VSPE_TRY(require_index(c));
+    if (!c->sparse.enabled) { set_error("this context counts densely: use vspe_matrices_device"); return VSPE_ERR_ARG; }
+    if (n_entries) *n_entries = c->sparse.n_runs;
+    if (d_keys) *d_keys = reinterpret_cast<uint64_t*>(c->sparse.k[0].p);
+    if (d_counts) *d_counts = reinterpret_cast<uint64_t*>(c->sparse.v[0].p);
+    return VSPE_OK;
+}
+
+int vspe_sparse_merge_device(vspe_ctx* c, const uint64_t* d_keys, const uint64_t* d_counts, uint64_t n_entries) {
+    VSPE_TRY(require_index(c));
+    if (!c->sparse.enabled) { set_error("this context counts densely"); return VSPE_ERR_ARG; }
+    return sparse_merge_device(c, d_keys, d_counts, n_entries);
+}
+
+void* vspe_stream(vspe_ctx* c) { return c ? reinterpret_cast<void*>(c->stream) : nullptr; }
 
 int vspe_write_info_sparse(const char* path, const char* const* ids, uint32_t n, const uint64_t* keys, const uint64_t* counts,
                            uint64_t n_entries, int mat) {

@@ -82,6 +82,9 @@ struct Ctx {
     bool err_flags_fresh = false;
     cudaEvent_t ev_m[2][3] = {};       // per mate: scan start, scan end / map start, map end
     bool scan_pack_attr_set = false;
+    bool scan_map_attr_set = false;     // fused scan + map kernel (scan_map.cu): attributes set, launch events pending
+    bool scan_map_pending[2] = {false, false};
+    uint32_t scan_map_events = 0;
     // staging for host-input entry points
     uint8_t* pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;
@@ -93,6 +96,7 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_stage_threads = 8;     // host threads that copy an unpinned input chunk into the pinned staging buffer
     int64_t opt_list_spread = 2;       // list-driven k_map_fast: one read per this many threads (1, 2, 4, 8 ...)
     int64_t opt_map_general = -1;      // walk kernels: -1 adaptive, 0 lean (defer reads with > 6 stretches), 1 general
     bool map_general = false;          // adaptive choice for the next launch

@@ -86,14 +86,15 @@ k_intern_slots(LinkView lv, const ReadSlot* __restrict__ slots, uint64_t n_arg, 
                const unsigned long long* __restrict__ n_dev, uint32_t* __restrict__ handles) {
     const uint64_t n = n_dev ? *n_dev : n_arg;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const ReadSlot* s = slots + i;
+        const uint64_t r = scatter ? scatter[i] : i;                  // listed reads: slot and handle share the index
+        const ReadSlot* s = slots + r;
         const uint32_t hdr = s->hdr, st = hdr & 0xFF, cnt = hdr >> 8;
         uint32_t h;
         if (st == ST_N) h = H_N;
         else if (st == ST_SHORT) h = H_SHORT;
         else if (cnt <= (uint32_t)SLOT_IDS) h = intern_list(lv, cnt, s->ids, 1);
         else h = intern_list(lv, cnt, lv.spill + s->ids[0], 1, s->ids[0]);
-        handles[scatter ? scatter[i] : i] = h;
+        handles[r] = h;
     }
 }
 

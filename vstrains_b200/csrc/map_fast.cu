@@ -1039,20 +1039,37 @@ static uint32_t pow2_spread(int64_t v) {
     return s;
 }
 
+// Work lists of the list-driven tiers for a chunk of up to n_reads reads (reserved and emptied before
+// the first kernel that appends to them).
+int map_prepare_lists(Ctx* c, uint64_t n_reads) {
+    if (n_reads > 0xFFFFFFFFull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
+    VSPE_TRY(c->worklist.reserve(n_reads + 1));
+    VSPE_TRY(c->defer_list.reserve(3 * n_reads + 3));
+    VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
+    VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER, 0, 8, c->stream));
+    VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER2, 0, 8, c->stream));
+    VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK2, 0, 8, c->stream));
+    return VSPE_OK;
+}
+
+// pre_listed: the reads to map are the counters[CNT_DEFER] entries of c->defer_list (written by k_scan_map
+// after map_prepare_lists); the walk stages 1 / 1b already ran inside that kernel.
 static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                            const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                           uint64_t n_reads, ReadSlot* d_slots) {
+                           uint64_t n_reads, ReadSlot* d_slots, bool pre_listed = false) {
     if (n_reads == 0) return VSPE_OK;
     if (n_reads > 0xFFFFFFFFull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
-    VSPE_TRY(c->worklist.reserve(n_reads));
-    VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
+    if (!pre_listed) {
+        VSPE_TRY(c->worklist.reserve(n_reads));
+        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
+    }
     const uint32_t grid = (uint32_t)((n_reads + MF_THREADS - 1) / MF_THREADS);
     IndexView v = c->index.view();
     const uint32_t* in_list = nullptr;
     const unsigned long long* in_count = nullptr;
     const uint32_t* to_generic = c->worklist.p;                 // reads the ASCII tier must map
     const unsigned long long* to_generic_n = c->counters.p + CNT_WORK;
-    if (d_rows) {
+    if (d_rows && !pre_listed) {
         VSPE_TRY(c->defer_list.reserve(3 * n_reads));
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER, 0, 8, c->stream));
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER2, 0, 8, c->stream));
@@ -1060,7 +1077,10 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     }
     // lean or general walk kernels (forced by the map_general option, else from the last launch's CNT_BIG)
     const bool general = c->opt_map_general >= 0 ? c->opt_map_general != 0 : c->map_general;
-    if (d_rows && !c->opt_single_map) {
+    if (pre_listed) {
+        in_list = c->defer_list.p;
+        in_count = c->counters.p + CNT_DEFER;
+    } else if (d_rows && !c->opt_single_map) {
         // stage 1: the clean-pass kernel; what it defers goes through the full kernel
 #define VSPE_M1(S, LP, FL, GN) k_map_first<S, LP, FL, GN><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, n_reads, d_slots, \
                                                                                         c->defer_list.p, c->counters.p)
@@ -1160,6 +1180,14 @@ int map_reads_packed(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, 
                      const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
                      uint64_t n_reads, ReadSlot* d_slots) {
     return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, row_words, cap, n_reads, d_slots);
+}
+
+// the reads k_scan_map left unresolved (listed in c->defer_list): full seed-and-extend kernel, then the
+// all-windows kernel, then the ASCII tier; results go to d_slots[r] for the listed r
+int map_reads_deferred(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
+                       const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
+                       uint64_t n_reads_cap, ReadSlot* d_slots) {
+    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, row_words, cap, n_reads_cap, d_slots, true);
 }
 
 }  // namespace vspe

@@ -24,6 +24,7 @@ struct NcclApi {
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -36,6 +37,7 @@ struct NcclApi {
         VSPE_SYM(CommInitAll, "ncclCommInitAll")
         VSPE_SYM(CommDestroy, "ncclCommDestroy")
         VSPE_SYM(AllReduce, "ncclAllReduce")
+        VSPE_SYM(AllGather, "ncclAllGather")
         VSPE_SYM(GroupStart, "ncclGroupStart")
         VSPE_SYM(GroupEnd, "ncclGroupEnd")
         VSPE_SYM(GetErrorString, "ncclGetErrorString")
@@ -44,50 +46,60 @@ struct NcclApi {
     }
 };
 
-// byte offsets one past the terminator that ends line `4*rec - 1` for rec in cuts (host scan)
-static void record_cuts(const uint8_t* p, uint64_t n, const std::vector<uint64_t>& recs, std::vector<uint64_t>& out) {
-    out.assign(recs.size(), n);
-    uint64_t line = 0;
-    size_t k = 0;
-    while (k < recs.size() && recs[k] == 0) out[k++] = 0;
-    for (uint64_t i = 0; i < n && k < recs.size(); i++) {
-        uint8_t c = p[i];
-        bool term = c == '\n' || (c == '\r' && !(i + 1 < n && p[i + 1] == '\n'));
-        if (!term) continue;
-        line++;
-        while (k < recs.size() && line == 4 * recs[k]) out[k++] = i + 1;
-    }
+// Universal-newline terminator test at byte i of p[0..n)  ("\r\n" counts once, at the '\n').
+static inline bool is_term(const uint8_t* p, uint64_t n, uint64_t i) {
+    const uint8_t c = p[i];
+    return c == '\n' || (c == '\r' && !(i + 1 < n && p[i + 1] == '\n'));
 }
 
-static uint64_t count_lines_host(const uint8_t* p, uint64_t n) {
-    // parallel terminator count; a "\r\n" split across two slices is counted once because the
-    // '\r' looks at its successor byte wherever that lives
-    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    std::vector<uint64_t> part(nt, 0);
-    std::vector<std::thread> th;
-    uint64_t per = (n + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; t++) {
-        uint64_t a = t * per, b = std::min(n, a + per);
-        if (a >= b) break;
-        th.emplace_back([=, &part] {
-            uint64_t c = 0;
-            for (uint64_t i = a; i < b; i++) {
-                uint8_t ch = p[i];
-                c += ch == '\n' || (ch == '\r' && !(i + 1 < n && p[i + 1] == '\n'));
-            }
-            part[t] = c;
-        });
-    }
-    for (auto& t : th) t.join();
+// Lines of a buffer and the byte offsets one past the terminator that ends line 4*rec - 1 for every rec
+// in `recs` (ascending).  The buffer is cut into slices whose terminators are counted in parallel; a cut
+// then only rescans the one slice that holds it.
+struct LineIndex {
+    const uint8_t* p = nullptr;
+    uint64_t n = 0, per = 0;
+    std::vector<uint64_t> before;                  // terminators before slice t
     uint64_t lines = 0;
-    for (auto v : part) lines += v;
-    if (n && !(p[n - 1] == '\n' || p[n - 1] == '\r')) lines++;
-    return lines;
-}
+    void build(const uint8_t* buf, uint64_t len) {
+        p = buf;
+        n = len;
+        unsigned nt = std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+        if (n < (1u << 20)) nt = 1;
+        per = (n + nt - 1) / nt;
+        std::vector<uint64_t> part(nt, 0);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) {
+            const uint64_t a = t * per, b = std::min(n, a + per);
+            if (a >= b) break;
+            th.emplace_back([=, &part] {
+                uint64_t c = 0;
+                for (uint64_t i = a; i < b; i++) c += is_term(p, n, i);
+                part[t] = c;
+            });
+        }
+        for (auto& t : th) t.join();
+        before.assign(nt + 1, 0);
+        for (unsigned t = 0; t < nt; t++) before[t + 1] = before[t] + part[t];
+        lines = before[nt];
+        if (n && !(p[n - 1] == '\n' || p[n - 1] == '\r')) lines++;
+    }
+    // byte offset one past the terminator number `line` (1-based); n if there are fewer
+    uint64_t end_of_line(uint64_t line) const {
+        if (line == 0) return 0;
+        if (line > before.back()) return n;
+        size_t t = 0;
+        while (before[t + 1] < line) t++;           // slice holding terminator number `line`
+        uint64_t seen = before[t];
+        for (uint64_t i = t * per; i < n; i++) {
+            if (!is_term(p, n, i)) continue;
+            if (++seen == line) return i + 1;
+        }
+        return n;
+    }
+};
 
 extern "C" int vspe_count_host(vspe_ctx* c, const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve);
 extern "C" int vspe_sparse_host(vspe_ctx* c, uint64_t* n_entries, const uint64_t** keys, const uint64_t** counts);
-extern "C" int vspe_sparse_merge(vspe_ctx* c, const uint64_t* keys, const uint64_t* counts, uint64_t n_entries);
 
 int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len,
                   const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve, int n_gpus,
@@ -101,12 +113,31 @@ int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes
     }
     static NcclApi nccl;
     VSPE_TRY(nccl.load());
-    // record-aligned shards (pairing is by record index: PE_Inference.py:154-159)
-    const uint64_t total = std::min(count_lines_host(fwd, n_fwd) / 4, count_lines_host(rve, n_rve) / 4);
-    std::vector<uint64_t> recs(n_gpus + 1), cf, cr;
-    for (int g = 0; g <= n_gpus; g++) recs[g] = total * g / n_gpus;
-    record_cuts(fwd, n_fwd, recs, cf);
-    record_cuts(rve, n_rve, recs, cr);
+    // record-aligned shards (pairing is by record index: PE_Inference.py:154-159); both files are
+    // indexed side by side, every cut then rescans one slice only
+    LineIndex li_f, li_r;
+    {
+        std::thread tr([&] { li_r.build(rve, n_rve); });
+        li_f.build(fwd, n_fwd);
+        tr.join();
+    }
+    const uint64_t total = std::min(li_f.lines / 4, li_r.lines / 4);
+    std::vector<uint64_t> cf(n_gpus + 1), cr(n_gpus + 1);
+    for (int g = 0; g <= n_gpus; g++) {
+        const uint64_t rec = total * g / n_gpus;
+        cf[g] = g == n_gpus ? n_fwd : li_f.end_of_line(4 * rec);
+        cr[g] = g == n_gpus ? n_rve : li_r.end_of_line(4 * rec);
+    }
+    // the communicator is created while the devices count (it takes longer than a small run)
+    const uint64_t nn = (uint64_t)n_nodes * n_nodes;
+    std::vector<ncclComm_t> comms(n_gpus, nullptr);
+    ncclResult_t comm_rc = 0;
+    std::thread comm_thread([&] {
+        std::vector<int> devs(n_gpus);
+        for (int g = 0; g < n_gpus; g++) devs[g] = g;
+        comm_rc = nccl.CommInitAll(comms.data(), n_gpus, devs.data());
+    });
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
 
     std::vector<vspe_ctx*> ctx(n_gpus, nullptr);
     std::vector<int> rc(n_gpus, VSPE_OK);
@@ -116,6 +147,7 @@ int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes
         th.emplace_back([&, g] {
             int r = vspe_create(g, &ctx[g]);
             if (r == VSPE_OK && sparse) ctx[g]->opt_sparse = 1;
+            if (r == VSPE_OK) ctx[g]->opt_stage_threads = std::max(1u, std::min(8u, hw / (unsigned)n_gpus));
             if (r == VSPE_OK) r = vspe_index_build(ctx[g], seqs, seq_off, n_nodes, split_len);
             if (r == VSPE_OK) r = vspe_count_host(ctx[g], fwd + cf[g], cf[g + 1] - cf[g], rve + cr[g], cr[g + 1] - cr[g]);
             rc[g] = r;
@@ -127,15 +159,62 @@ int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes
     for (int g = 0; g < n_gpus; g++)
         if (rc[g] != VSPE_OK) { set_error("GPU %d: %s", g, err[g].c_str()); result = rc[g]; break; }
 
-    const uint64_t nn = (uint64_t)n_nodes * n_nodes;
+    comm_thread.join();
+    if (result == VSPE_OK && comm_rc != 0) { set_error("ncclCommInitAll: %s", nccl.GetErrorString(comm_rc)); result = VSPE_ERR_NCCL; }
     if (result == VSPE_OK && sparse) {
-        // sparse runs: host-mediated merge into device 0 (append + radix sort + run-length reduce)
-        for (int g = 1; g < n_gpus && result == VSPE_OK; g++) {
-            uint64_t ne = 0;
-            const uint64_t *pk = nullptr, *pc = nullptr;
+        // sparse runs: ONE exchange step over NVLink -- all-gather of the run counts, all-gather of the
+        // (padded) runs -- then device 0 merges the other devices' runs locally (sort + run-length reduce)
+        std::vector<DevBuf<unsigned long long>> cnt(n_gpus), gath_n(n_gpus), send(n_gpus), gath(n_gpus);
+        for (int g = 0; g < n_gpus && result == VSPE_OK; g++) {
             cudaSetDevice(g);
-            result = vspe_sparse_host(ctx[g], &ne, &pk, &pc);
-            if (result == VSPE_OK) { cudaSetDevice(0); result = vspe_sparse_merge(ctx[0], pk, pc, ne); }
+            if (cnt[g].reserve(1) != VSPE_OK || gath_n[g].reserve(n_gpus) != VSPE_OK) { result = VSPE_ERR_CUDA; break; }
+            const unsigned long long nr = ctx[g]->sparse.n_runs;
+            cudaMemcpyAsync(cnt[g].p, &nr, 8, cudaMemcpyHostToDevice, ctx[g]->stream);
+            cudaStreamSynchronize(ctx[g]->stream);
+        }
+        ncclResult_t nr = 0;
+        if (result == VSPE_OK) {
+            nccl.GroupStart();
+            for (int g = 0; g < n_gpus; g++) {
+                cudaSetDevice(g);
+                nr = nccl.AllGather(cnt[g].p, gath_n[g].p, 1, kNcclUint64, comms[g], ctx[g]->stream);
+                if (nr != 0) break;
+            }
+            const ncclResult_t ge = nccl.GroupEnd();
+            if (nr != 0 || ge != 0) { set_error("ncclAllGather: %s", nccl.GetErrorString(nr ? nr : ge)); result = VSPE_ERR_NCCL; }
+        }
+        std::vector<unsigned long long> sizes(n_gpus, 0);
+        if (result == VSPE_OK) {
+            cudaSetDevice(0);
+            cudaMemcpyAsync(sizes.data(), gath_n[0].p, 8ull * n_gpus, cudaMemcpyDeviceToHost, ctx[0]->stream);
+            cudaStreamSynchronize(ctx[0]->stream);
+            unsigned long long cap = 1;
+            for (auto v : sizes) cap = std::max(cap, v);
+            for (int g = 0; g < n_gpus && result == VSPE_OK; g++) {
+                cudaSetDevice(g);
+                if (send[g].reserve(2 * cap) != VSPE_OK || gath[g].reserve(2 * cap * n_gpus) != VSPE_OK) { result = VSPE_ERR_CUDA; break; }
+                cudaMemsetAsync(send[g].p, 0, 16 * cap, ctx[g]->stream);
+                if (ctx[g]->sparse.n_runs) {
+                    cudaMemcpyAsync(send[g].p, ctx[g]->sparse.k[0].p, 8 * ctx[g]->sparse.n_runs, cudaMemcpyDeviceToDevice, ctx[g]->stream);
+                    cudaMemcpyAsync(send[g].p + cap, ctx[g]->sparse.v[0].p, 8 * ctx[g]->sparse.n_runs, cudaMemcpyDeviceToDevice, ctx[g]->stream);
+                }
+            }
+            if (result == VSPE_OK) {
+                nccl.GroupStart();
+                for (int g = 0; g < n_gpus; g++) {
+                    cudaSetDevice(g);
+                    nr = nccl.AllGather(send[g].p, gath[g].p, 2 * cap, kNcclUint64, comms[g], ctx[g]->stream);
+                    if (nr != 0) break;
+                }
+                const ncclResult_t ge = nccl.GroupEnd();
+                if (nr != 0 || ge != 0) { set_error("ncclAllGather: %s", nccl.GetErrorString(nr ? nr : ge)); result = VSPE_ERR_NCCL; }
+                for (int g = 0; g < n_gpus; g++) { cudaSetDevice(g); cudaStreamSynchronize(ctx[g]->stream); }
+            }
+            cudaSetDevice(0);
+            for (int g = 1; g < n_gpus && result == VSPE_OK; g++) {
+                const uint64_t* base = reinterpret_cast<const uint64_t*>(gath[0].p) + 2 * cap * g;
+                result = sparse_merge_device(ctx[0], base, base + cap, sizes[g]);
+            }
         }
         if (result == VSPE_OK) {
             uint64_t ne = 0;
@@ -144,26 +223,24 @@ int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes
             result = vspe_sparse_host(ctx[0], &ne, &pk, &pc);
             if (result == VSPE_OK) { sparse_keys->assign(pk, pk + ne); sparse_counts->assign(pc, pc + ne); }
         }
-    }
-    if (result == VSPE_OK && nn && !sparse) {
-        std::vector<ncclComm_t> comms(n_gpus);
-        std::vector<int> devs(n_gpus);
-        for (int g = 0; g < n_gpus; g++) devs[g] = g;
-        ncclResult_t nr = nccl.CommInitAll(comms.data(), n_gpus, devs.data());
-        if (nr != 0) { set_error("ncclCommInitAll: %s", nccl.GetErrorString(nr)); result = VSPE_ERR_NCCL; }
-        if (result == VSPE_OK) {
-            nccl.GroupStart();
-            for (int g = 0; g < n_gpus; g++) {
-                cudaSetDevice(g);
-                nr = nccl.AllReduce(ctx[g]->mats.p, ctx[g]->mats.p, 2 * nn, kNcclUint64, kNcclSum, comms[g], ctx[g]->stream);
-                if (nr != 0) break;
-            }
-            ncclResult_t ge = nccl.GroupEnd();
-            if (nr != 0 || ge != 0) { set_error("ncclAllReduce: %s", nccl.GetErrorString(nr ? nr : ge)); result = VSPE_ERR_NCCL; }
-            for (int g = 0; g < n_gpus; g++) { cudaSetDevice(g); cudaStreamSynchronize(ctx[g]->stream); }
-            for (int g = 0; g < n_gpus; g++) nccl.CommDestroy(comms[g]);
+        for (int g = 0; g < n_gpus; g++) {          // the scratch buffers belong to their devices
+            cudaSetDevice(g);
+            cnt[g].release(); gath_n[g].release(); send[g].release(); gath[g].release();
         }
     }
+    if (result == VSPE_OK && nn && !sparse) {
+        ncclResult_t nr = 0;
+        nccl.GroupStart();
+        for (int g = 0; g < n_gpus; g++) {
+            cudaSetDevice(g);
+            nr = nccl.AllReduce(ctx[g]->mats.p, ctx[g]->mats.p, 2 * nn, kNcclUint64, kNcclSum, comms[g], ctx[g]->stream);
+            if (nr != 0) break;
+        }
+        const ncclResult_t ge = nccl.GroupEnd();
+        if (nr != 0 || ge != 0) { set_error("ncclAllReduce: %s", nccl.GetErrorString(nr ? nr : ge)); result = VSPE_ERR_NCCL; }
+        for (int g = 0; g < n_gpus; g++) { cudaSetDevice(g); cudaStreamSynchronize(ctx[g]->stream); }
+    }
+    if (comm_rc == 0) for (int g = 0; g < n_gpus; g++) if (comms[g]) nccl.CommDestroy(comms[g]);
     if (result == VSPE_OK && !sparse) {
         node_mat.assign(nn, 0);
         short_mat.assign(nn, 0);

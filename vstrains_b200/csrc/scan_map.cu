@@ -302,14 +302,13 @@ k_scan_map(const ScanMapArgs a, const IndexView ix, const LinkView lv) {
     for (int it = 0; it < SM_ITERS; it++) {
         const uint32_t vid = (wib * SM_ITERS + it) * 32 + lane;       // vector index inside the tile
         const uint4 v = *reinterpret_cast<const uint4*>(tb + vid * 16);
-        bool cand;
-        if (interior) {
-            const uint32_t t = ((v.x - 0x10101010u) | v.x) | ((v.y - 0x10101010u) | v.y) | ((v.z - 0x10101010u) | v.z) |
-                               ((v.w - 0x10101010u) | v.w);
-            cand = (t & 0x80808080u) != 0;
-        } else {                                                       // first / last tile of the chunk
+        const uint32_t t = ((v.x - 0x10101010u) | v.x) | ((v.y - 0x10101010u) | v.y) | ((v.z - 0x10101010u) | v.z) |
+                           ((v.w - 0x10101010u) | v.w);
+        bool cand = (t & 0x80808080u) != 0;
+        if (!interior) {                                               // first / last tile of the chunk
             const int64_t p = pos0 + (int64_t)vid * 16;
-            cand = p < nn && p + 16 > 0;                               // every vector that overlaps the buffer
+            const bool full = p >= 0 && p + 16 <= nn;
+            if (!full) cand = p < nn && p + 16 > 0;                    // partial vector: M2 masks the outside bytes
         }
         const uint32_t bm = __ballot_sync(0xFFFFFFFFu, cand);
         if (cand) {

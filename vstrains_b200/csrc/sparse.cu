@@ -282,4 +282,17 @@ int sparse_merge_host(Ctx* c, const uint64_t* keys, const uint64_t* counts, uint
     return VSPE_OK;
 }
 
+// add runs that already live on this device (e.g. gathered from the other ranks over NVLink)
+int sparse_merge_device(Ctx* c, const uint64_t* d_keys, const uint64_t* d_counts, uint64_t n) {
+    Sparse& sp = c->sparse;
+    if (n == 0) return VSPE_OK;
+    VSPE_TRY(sparse_reserve(c, sp.n_runs + n));
+    VSPE_CUDA(cudaMemcpyAsync(sp.k[0].p + sp.n_runs, d_keys, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    VSPE_CUDA(cudaMemcpyAsync(sp.v[0].p + sp.n_runs, d_counts, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    uint64_t runs = 0;
+    VSPE_TRY(sparse_sort_reduce(c, sp.n_runs + n, &runs));
+    sp.n_runs = runs;
+    return VSPE_OK;
+}
+
 }  // namespace vspe

@@ -274,6 +274,13 @@ void scan_pack_account(Ctx* c);
 int device_scan_u64(Ctx* c, const unsigned long long* in, unsigned long long* out, uint64_t n, unsigned long long* sums,
                     unsigned long long* total);
 
+// K1+K2+K4 fused (scan_map.cu): one pass over a device-resident chunk -> handles + the unresolved reads, packed and listed
+int scan_map(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots, uint32_t* d_handles,
+             uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t* d_defer_list, uint32_t row_words,
+             uint32_t cap);
+const unsigned long long* scan_map_total_ptr(Ctx* c, uint64_t n, const uint8_t* d_buf);
+void scan_map_account(Ctx* c);
+
 // K2+K4: map reads [0, n_reads) of a chunk into slots[rec_off + r]
 int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                       uint64_t n_reads, ReadSlot* d_slots);
@@ -282,6 +289,7 @@ int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start,
 int adapt_map_variant(Ctx* c);
 
 int sparse_merge_host(Ctx* c, const uint64_t* keys, const uint64_t* counts, uint64_t n);
+int sparse_merge_device(Ctx* c, const uint64_t* d_keys, const uint64_t* d_counts, uint64_t n);
 // dense matrices are kept for 2*N*N <= 2^28 cells (2 GiB of uint64); larger graphs count sparsely
 inline bool dense_possible(uint64_t n_nodes) { return 2ull * n_nodes * n_nodes <= (8192ull << 15); }
 

@@ -123,6 +123,20 @@ class PEIndex:
         counts = np.ctypeslib.as_array(ctypes.cast(pc, ctypes.POINTER(ctypes.c_uint64)), (n.value,)).copy()
         return keys, counts
 
+    def stream(self) -> int:
+        """The cudaStream_t (as an integer) this context launches on, e.g. for ``torch.cuda.ExternalStream``."""
+        return self._L.vspe_stream(self._ctx) or 0
+
+    def sparse_device(self) -> Tuple[int, int, int]:
+        """Sparse mode: (n_runs, device pointer of the keys, device pointer of the counts)."""
+        n, pk, pc = ctypes.c_uint64(), ctypes.c_void_p(), ctypes.c_void_p()
+        check(self._L.vspe_sparse_device(self._ctx, ctypes.byref(n), ctypes.byref(pk), ctypes.byref(pc)))
+        return n.value, pk.value or 0, pc.value or 0
+
+    def sparse_merge_device(self, kptr: int, cptr: int, n: int):
+        """Add runs that live in this context's device memory (exact integer sums)."""
+        check(self._L.vspe_sparse_merge_device(self._ctx, kptr, cptr, n))
+
     def sparse_merge(self, keys: np.ndarray, counts: np.ndarray):
         """Add the runs of another context / rank (exact integer sums)."""
         k = np.ascontiguousarray(keys, dtype=np.uint64)
