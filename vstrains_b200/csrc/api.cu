@@ -29,9 +29,6 @@ int map_reads_generic_list(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
                            const uint32_t* d_worklist, uint64_t n_items, ReadSlot* d_slots);
 int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                    uint64_t n_reads, ReadSlot* d_slots);
-int map_reads_packed(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
-                     const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                     uint64_t n_reads, ReadSlot* d_slots);
 int map_prepare_lists(Ctx* c, uint64_t n_reads);
 int map_reads_deferred(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                        const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
@@ -64,9 +61,12 @@ static int check_kernel_errors(Ctx* c) {
 // One chunk of one mate's byte stream, resident on the device.  The chunk must start at a line
 // start and (unless it is the last chunk) end right after a terminator.
 static int scan_mode_of(Ctx* c) {
+    // 0 (default): k_scan_rows + k_walk + list-driven tiers; 1: look-back record scan + raw-byte map kernels
+    // (also the fallback of mode 0); 2: two-pass record scan + raw-byte map kernels (cross-check)
     int mode = (int)c->opt_scan_mode;
     if (c->opt_scan_two_pass) mode = 2;
-    if ((c->opt_force_generic || c->index.split_len > 320) && (mode == 0 || mode == 3 || mode == 4)) mode = 1;
+    if (mode < 0 || mode > 2) mode = 0;
+    if ((c->opt_force_generic || c->index.split_len > 320) && mode == 0) mode = 1;
     return mode;
 }
 
@@ -81,7 +81,7 @@ static int retry_after_pool_overflow(Ctx* c, unsigned long long flags, const uns
     return link_grow_overflow(c);
 }
 
-// One chunk through the fused kernel (scan_mode 4): k_scan_map -> list-driven tiers on what it left
+// One chunk through the default path (scan_mode 0): k_scan_rows -> k_walk -> list-driven tiers on what the walk left
 // unresolved -> their slots interned -> one host sync (terminator count + error flags).  A launch whose
 // guessed table size was too small, or that ran out of list records / spill words, is repeated
 // (every step is idempotent).  *fell_back: a tile owned more reads than the kernel's table holds
@@ -138,9 +138,10 @@ static int feed_chunk_fused(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf,
     return VSPE_OK;
 }
 
-// prepared: the count pass of this chunk was already queued (scan_pack_prepare_launch)
+// One chunk of one mate's byte stream, resident on the device.  The chunk must start at a line
+// start and (unless it is the last chunk) end right after a terminator.
 static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint64_t n, bool is_last, int last_byte,
-                      bool sync_after = true, bool prepared = false) {
+                      bool sync_after = true) {
     if (n == 0) {
         if (is_last) ms.lines = ms.line_base;
         return VSPE_OK;
@@ -149,16 +150,20 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
     uint64_t n_terms = 0;
     for (auto& e : c->ev_m[m]) if (!e) VSPE_CUDA(cudaEventCreate(&e));
     cudaEvent_t e0 = c->ev_m[m][0], e1 = c->ev_m[m][1], e2 = c->ev_m[m][2];
-    VSPE_CUDA(cudaEventRecord(e0, c->stream));
     const uint64_t lb = ms.line_base;
     const uint64_t rec_first = seq_lines_before(lb);
     uint64_t n_seq = 0;
     c->cur_buf_n = n;
-    const uint32_t cap = map_fast_cap(c->read_len_hint);
-    const uint32_t row_words = cap <= 160 ? 12 : cap <= 256 ? 16 : 20;
     int mode = scan_mode_of(c);
-    bool packed = false;
-    if (mode == 4) {
+    auto finish = [&]() {
+        ms.n_slots = rec_first + n_seq;
+        ms.line_base = lb + n_terms;
+        if (is_last) {
+            bool term = last_byte == '\n' || last_byte == '\r';
+            ms.lines = ms.line_base + (term ? 0 : 1);
+        }
+    };
+    if (mode == 0) {
         bool fell_back = false;
         VSPE_TRY(feed_chunk_fused(c, m, ms, d_buf, n, &fell_back, &n_terms, &n_seq));
         if (!fell_back) {
@@ -170,64 +175,19 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
                 c->stats.ms_scan += a;
                 c->stats.ms_map += b;
             }
-            ms.n_slots = rec_first + n_seq;
-            ms.line_base = lb + n_terms;
-            if (is_last) {
-                bool term = last_byte == '\n' || last_byte == '\r';
-                ms.lines = ms.line_base + (term ? 0 : 1);
-            }
+            finish();
             return VSPE_OK;
         }
-        mode = 1;
-        VSPE_CUDA(cudaEventRecord(e0, c->stream));
+        mode = 1;                                         // a tile owned more reads than its table holds: plain path
     }
-    if (mode == 0) {
-        // count pass (terminator masks, no inter-tile dependency) + device scan, then the pack
-        // pass with exactly sized outputs
-        unsigned long long flags = 0;
-        if (!prepared) VSPE_TRY(scan_pack_prepare_launch(c, m, d_buf, n));
-        VSPE_TRY(scan_pack_prepare_collect(c, m, d_buf, n, &n_terms, &flags));
-        if (flags & ERRF_TILE_FULL) {
-            mode = 1;                                   // a warp row with too many candidates: plain path
-        } else {
-            n_seq = seq_lines_before(lb + n_terms) - rec_first;
-            VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
-            VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
-            VSPE_TRY(mb.rec.hdr.reserve(n_seq + 2));
-            VSPE_TRY(mb.rec.rows.reserve((n_seq + 2) * row_words));
-            VSPE_TRY(scan_pack_finish(c, m, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p,
-                                      mb.rec.hdr.p, row_words, cap));
-            packed = true;
-        }
-    } else if (mode == 3) {
-        // fused single pass with look-back and a guessed table size (from the read length of the
-        // first records); if a tile owns too many records or the guess was too small, fall through
-        uint64_t guess = n / (2ull * std::max<uint32_t>(c->read_len_hint, 20) + 8) * 21 / 20 + 4096;
-        unsigned long long flags = 0;
-        VSPE_TRY(mb.rec.seq_start.reserve(guess + 2));
-        VSPE_TRY(mb.rec.seq_end.reserve(guess + 2));
-        VSPE_TRY(mb.rec.hdr.reserve(guess + 2));
-        VSPE_TRY(mb.rec.rows.reserve((guess + 2) * row_words));
-        VSPE_TRY(scan_pack(c, d_buf, n, lb, rec_first, guess, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p,
-                           row_words, cap, &n_terms, &flags));
-        n_seq = seq_lines_before(lb + n_terms) - rec_first;
-        if ((flags & ERRF_SLOTS_FULL) && !(flags & ERRF_TILE_FULL)) {
-            VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
-            VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
-            VSPE_TRY(mb.rec.hdr.reserve(n_seq + 2));
-            VSPE_TRY(mb.rec.rows.reserve((n_seq + 2) * row_words));
-            VSPE_TRY(scan_pack(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p,
-                               row_words, cap, &n_terms, &flags));
-        }
-        if (flags & (ERRF_TILE_FULL | ERRF_SLOTS_FULL)) mode = 1; else packed = true;
-    }
+    VSPE_CUDA(cudaEventRecord(e0, c->stream));
     if (mode == 2) {
         VSPE_TRY(scan_count_lines(c, d_buf, n, &n_terms));
         n_seq = seq_lines_before(lb + n_terms) - rec_first;
         VSPE_TRY(mb.rec.seq_start.reserve(n_seq + 2));
         VSPE_TRY(mb.rec.seq_end.reserve(n_seq + 2));
         VSPE_TRY(scan_index_records(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p));
-    } else if (mode == 1) {
+    } else {
         // one pass with a guessed table size (a FASTQ record is rarely under 48 bytes); if the
         // guess was too small the pass is repeated once with the exact size
         uint64_t guess = n / 48 + 1024;
@@ -243,58 +203,45 @@ static int feed_chunk(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint6
             VSPE_TRY(scan_records_single_pass(c, d_buf, n, lb, rec_first, n_seq, mb.rec.seq_start.p, mb.rec.seq_end.p, &n_terms, &overflow));
         }
     }
-    VSPE_TRY(mb.slots.reserve(rec_first + n_seq + 1, true, c->stream));
+    // the raw-byte map kernels write one slot per read (chunk-local index), which is then interned
+    VSPE_TRY(mb.slots.reserve(n_seq + 1));
     VSPE_CUDA(cudaEventRecord(e1, c->stream));
     unsigned long long cur0[2] = {0, 0};                  // spill / private-record cursors before this chunk's map stage
     VSPE_CUDA(cudaMemcpyAsync(&cur0[0], c->counters.p + CNT_SPILL_CURSOR, 8, cudaMemcpyDeviceToHost, c->stream));
     VSPE_CUDA(cudaMemcpyAsync(&cur0[1], c->counters.p + CNT_OVF, 8, cudaMemcpyDeviceToHost, c->stream));
-    if (n_seq) {
-        if (packed)
-            VSPE_TRY(map_reads_packed(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p, row_words, cap, n_seq,
-                                      mb.slots.p + rec_first));
-        else if (c->opt_force_generic)
-            VSPE_TRY(map_reads_generic_list(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, nullptr, n_seq, mb.slots.p + rec_first));
-        else
-            VSPE_TRY(map_reads_fast(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, n_seq, mb.slots.p + rec_first));
-    }
+    auto map_all = [&]() -> int {
+        if (c->opt_force_generic) return map_reads_generic_list(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, nullptr, n_seq, mb.slots.p);
+        return map_reads_fast(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, n_seq, mb.slots.p);
+    };
+    if (n_seq) VSPE_TRY(map_all());
     // slots -> list handles (link.cuh); a launch that ran out of private list records or spill words
     // is repeated after growing the pools (interning is idempotent)
     VSPE_TRY(mb.handles.reserve(rec_first + n_seq + 1, true, c->stream));
     for (int attempt = 0; n_seq; attempt++) {
-        VSPE_TRY(intern_slots(c, mb.slots.p + rec_first, n_seq, nullptr, nullptr, mb.handles.p + rec_first));
-        unsigned long long h_err = 0;
+        // the slots of this chunk keep their spill ranges: interning alone is repeated from the cursors as the map stage left them
+        unsigned long long cur1[2] = {0, 0}, h_err = 0;
+        VSPE_CUDA(cudaMemcpyAsync(&cur1[0], c->counters.p + CNT_SPILL_CURSOR, 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_CUDA(cudaMemcpyAsync(&cur1[1], c->counters.p + CNT_OVF, 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_TRY(intern_slots(c, mb.slots.p, n_seq, nullptr, nullptr, mb.handles.p + rec_first));
         VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
         VSPE_CUDA(cudaStreamSynchronize(c->stream));
         if (!(h_err & (ERRF_LISTS_FULL | ERRF_SPILL_FULL))) break;
         if (attempt == 8) break;                          // reported by the caller's error check
-        VSPE_TRY(retry_after_pool_overflow(c, h_err, cur0));
-        if (h_err & ERRF_SPILL_FULL) {                    // the map tiers themselves ran out of spill words: map again
-            if (packed)
-                VSPE_TRY(map_reads_packed(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p, row_words, cap, n_seq,
-                                          mb.slots.p + rec_first));
-            else if (c->opt_force_generic)
-                VSPE_TRY(map_reads_generic_list(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, nullptr, n_seq, mb.slots.p + rec_first));
-            else
-                VSPE_TRY(map_reads_fast(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, n_seq, mb.slots.p + rec_first));
-        }
+        const bool remap = (h_err & ERRF_SPILL_FULL) != 0;
+        VSPE_TRY(retry_after_pool_overflow(c, h_err, remap ? cur0 : cur1));
+        if (remap) VSPE_TRY(map_all());                   // spill words ran out (possibly inside the map tiers): map again
     }
     VSPE_CUDA(cudaEventRecord(e2, c->stream));
     if (sync_after) {
         // streaming callers reuse the chunk buffer next: wait, and account the stage times now
         VSPE_CUDA(cudaStreamSynchronize(c->stream));
-        scan_pack_account(c);
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, e0, e1);
         cudaEventElapsedTime(&b, e1, e2);
         c->stats.ms_scan += a;
         c->stats.ms_map += b;
     }
-    ms.n_slots = rec_first + n_seq;
-    ms.line_base = lb + n_terms;
-    if (is_last) {
-        bool term = last_byte == '\n' || last_byte == '\r';
-        ms.lines = ms.line_base + (term ? 0 : 1);
-    }
+    finish();
     return VSPE_OK;
 }
 
@@ -689,10 +636,6 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
     MateStream* ms[2] = {&f, &r};
     int last[2] = {-1, -1};
     uint32_t hint = 0;
-    // the count passes of both mates need nothing from the host: queue them before the first sync
-    const bool prelaunch = scan_mode_of(c) == 0;
-    if (prelaunch)
-        for (int m = 0; m < 2; m++) VSPE_TRY(scan_pack_prepare_launch(c, m, bufs[m], ns[m]));
     {   // one small D2H round for both mates: last byte (does the file end with a terminator?)
         // and a prefix to size the packed rows
         static thread_local std::vector<uint8_t> head(2 * 16384);
@@ -712,19 +655,14 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
         }
     }
     c->read_len_hint = hint;
-    for (int m = 0; m < 2; m++) VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last[m], false, prelaunch));
+    for (int m = 0; m < 2; m++) VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last[m], false));
     VSPE_TRY(finish_pairs(c, f, r));
     VSPE_CUDA(cudaEventRecord(t1, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
     float ms_total = 0;
     cudaEventElapsedTime(&ms_total, t0, t1);
     c->stats.ms_total += ms_total;
-    scan_pack_account(c);
-    if (prelaunch && c->ev_m[0][0] && ns[0]) {
-        // the count passes of both mates ran between the start of the call and mate 0's first event
-        float pre = 0;
-        if (cudaEventElapsedTime(&pre, t0, c->ev_m[0][0]) == cudaSuccess) c->stats.ms_scan += pre;
-    }
+    scan_map_account(c);
     for (int m = 0; m < 2; m++) {
         if (!ns[m]) continue;
         float a = 0, b = 0;
@@ -1150,19 +1088,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
             }
         }
     }
-    else if (!strcmp(name, "single_map")) c->opt_single_map = value;
-    else if (!strcmp(name, "full_second")) c->opt_no_second = value;
-    else if (!strcmp(name, "list_spread")) c->opt_list_spread = value;
-    else if (!strcmp(name, "second_spread")) c->opt_second_spread = value;
-    else if (!strcmp(name, "flat_walk")) c->opt_flat_walk = value;
-    else if (!strcmp(name, "fast_tier")) c->opt_fast_tier = value;
-    else if (!strcmp(name, "map_general")) c->opt_map_general = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
-    else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value;
-    else if (!strcmp(name, "dbg_dump")) {
-        // profiling aid: copy the per-tile stamps of the last scan to the host pointer `value`
-        if (c->dbg_tiles && value) cudaMemcpy(reinterpret_cast<void*>(value), c->dbg_times.p, c->dbg_tiles * 64, cudaMemcpyDeviceToHost);
-    }
     else if (!strcmp(name, "dbg_counters")) {
         // profiling aid: copy the device counters (enum Counter order, CNT_COUNT_ words) to the host pointer `value`
         if (value) cudaMemcpy(reinterpret_cast<void*>(value), c->counters.p, CNT_COUNT_ * 8, cudaMemcpyDeviceToHost);

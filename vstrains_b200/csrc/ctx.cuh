@@ -12,10 +12,10 @@ enum Counter {
     CNT_FAST, CNT_GENERIC,   // reads resolved per tier
     CNT_WORK,                // generic-tier worklist length
     CNT_BAILED,              // reads the fast tier handed to the exhaustive tier
-    CNT_DEFER,               // reads k_map_first deferred to k_map_fast
+    CNT_DEFER,               // reads k_walk left for the list-driven tiers
     CNT_WORK2,               // reads k_map_windows left for the ASCII tier
-    CNT_DEFER2,              // reads k_map_second left for k_map_fast
-    CNT_BIG,                 // sampled reads of the last k_map_first launch with more than FL_MAX stretches
+    CNT_DEFER2,              // (unused)
+    CNT_BIG,                 // (unused)
     CNT_LISTS,               // distinct node lists interned in the list table
     CNT_OVF,                 // private list records of this call (lists the table cannot hold)
     CNT_PAIR_OCC,            // distinct (left list, right list) combinations of the current batch
@@ -48,12 +48,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev[8] = {};
-    // two-kernel scan, per mate: events around the pack pass [0..1] and the count pass [2..3],
-    // candidate queues per (tile, warp), tile totals + their scan
-    cudaEvent_t ev_scan[2][4] = {};
-    bool scan_pack_pending[2] = {false, false}, scan_count_pending[2] = {false, false};
-    DevBuf<uint8_t> scan_q[2];
-    DevBuf<uint64_t> scan_tiles[2];
+    cudaEvent_t ev_scan[2][4] = {};     // events around the k_scan_rows [0] / k_walk [1] launches (two in flight each)
     Index index;
     DevBuf<uint64_t> mats;            // [2][N][N] node_mat then short_mat (dense mode)
     Sparse sparse;                    // sorted (key, count) runs (sparse mode)
@@ -81,7 +76,6 @@ struct Ctx {
     unsigned long long last_err_flags = 0;
     bool err_flags_fresh = false;
     cudaEvent_t ev_m[2][3] = {};       // per mate: scan start, scan end / map start, map end
-    bool scan_pack_attr_set = false;
     bool scan_map_attr_set = false;     // fused scan + map kernel (scan_map.cu): attributes set, launch events pending
     bool scan_map_pending[2] = {false, false};
     uint32_t scan_map_events = 0;
@@ -97,24 +91,10 @@ struct Ctx {
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
     int64_t opt_stage_threads = 8;     // host threads that copy an unpinned input chunk into the pinned staging buffer
-    int64_t opt_list_spread = 2;       // list-driven k_map_fast: one read per this many threads (1, 2, 4, 8 ...)
-    int64_t opt_map_general = -1;      // walk kernels: -1 adaptive, 0 lean (defer reads with > 6 stretches), 1 general
-    bool map_general = false;          // adaptive choice for the next launch
-    bool big_pending = false;          // CNT_BIG of the last k_map_first launch has not been looked at yet
-    uint64_t big_sampled = 0;          // reads that launch sampled
-    int64_t opt_fast_tier = 1;         // 0: reads the walk kernels defer go straight to k_map_windows (no k_map_fast)
-    int64_t opt_flat_walk = 1;         // k_map_first: flat walk loop (0: nested stretch / chunk loops)
-    int64_t opt_second_spread = 1;     // k_map_second: one read per this many threads (power of two <= 32)
-    int64_t opt_no_second = 0;         // 1: skip k_map_second
-    int64_t opt_single_map = 0;        // 1: skip k_map_first (every read through the full kernel)
     int64_t opt_subst = 1;             // build / use the substitution-hit bitmap
-    int64_t opt_dbg_times = 0;
-    DevBuf<unsigned long long> dbg_times;
-    uint64_t dbg_tiles = 0;
     int64_t opt_scan_two_pass = 0;     // K1 as count + index passes (cross-check of the look-back kernel)
     uint64_t cur_buf_n = 0;            // bytes of the chunk being mapped (exhaustive tier bound)
-    int64_t opt_scan_mode = 0;         // 0: TMA count pass + pack pass, 3: fused TMA scan+pack with look-back,
-                                       // 1: look-back scan + raw-byte map, 2: two-pass scan
+    int64_t opt_scan_mode = 0;         // 0: k_scan_rows + k_walk, 1: look-back record scan + raw-byte map, 2: two-pass record scan
     uint32_t read_len_hint = 320;      // longest sequence line among the first records of the input
     // accounting
     vspe_stats stats = {};

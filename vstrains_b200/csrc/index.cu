@@ -124,6 +124,21 @@ k_index_succ(IndexView ix, uint32_t* __restrict__ succ) {
     succ[2 * t + 1] = res_node;
 }
 
+// the successor table again, widened to everything a walk needs to enter the successor strand
+__global__ void __launch_bounds__(128)
+k_index_succ16(IndexView ix, const uint32_t* __restrict__ succ, uint4* __restrict__ succ16) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 8 * ix.n_nodes) return;
+    const uint32_t tp = succ[2 * t], node = succ[2 * t + 1];
+    uint4 out = make_uint4(NONE32, 0, 0, 0);
+    if (tp != NONE32) {
+        const uint4 nr = ix.node_rec[node];
+        const bool rcs = tp >= nr.y;
+        out = make_uint4(tp, 2 * node + (rcs ? 1u : 0u), rcs ? nr.z : nr.y, nr.w);
+    }
+    succ16[t] = out;
+}
+
 // --- substitution-hit bitmap -----------------------------------------------------------------
 // For every window w of every strand, every offset o and every other base b: does the k-mer
 // "window w with base o replaced by b" have a posting?  If yes, bit b of text base w+o is set.
@@ -225,9 +240,13 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
     VSPE_TRY(ix.text.reserve(n_words));
     VSPE_TRY(ix.strand_start.reserve(h_ss.size()));
     VSPE_TRY(ix.node_len.reserve(h_len.size()));
+    VSPE_TRY(ix.node_rec.reserve(h_len.size()));
+    std::vector<uint4> h_rec(h_len.size());
+    for (uint32_t i = 0; i < n_nodes; i++) h_rec[i] = make_uint4(h_ss[2 * i], h_ss[2 * i + 1], h_ss[2 * i + 2], h_len[i]);
     VSPE_TRY(ix.slots.reserve(slots));
     VSPE_TRY(ix.uniq.reserve(n_words));
     VSPE_TRY(ix.succ.reserve(16 * (size_t)n_nodes + 16));
+    VSPE_TRY(ix.succ16.reserve(8 * (size_t)n_nodes + 8));
     DevBuf<uint8_t> d_seqs;
     DevBuf<uint64_t> d_off;
     uint64_t seq_bytes = n_nodes ? seq_off[n_nodes] : 0;
@@ -239,6 +258,7 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
     VSPE_CUDA(cudaMemcpyAsync(d_off.p, seq_off, ((size_t)n_nodes + 1) * 8, cudaMemcpyHostToDevice, st));
     VSPE_CUDA(cudaMemcpyAsync(ix.strand_start.p, h_ss.data(), h_ss.size() * 4, cudaMemcpyHostToDevice, st));
     VSPE_CUDA(cudaMemcpyAsync(ix.node_len.p, h_len.data(), (size_t)n_nodes * 4, cudaMemcpyHostToDevice, st));
+    VSPE_CUDA(cudaMemcpyAsync(ix.node_rec.p, h_rec.data(), (size_t)n_nodes * sizeof(uint4), cudaMemcpyHostToDevice, st));
     VSPE_CUDA(cudaMemsetAsync(ix.slots.p, 0xFF, slots * sizeof(uint2), st));
     VSPE_CUDA(cudaMemsetAsync(ix.uniq.p, 0, (size_t)n_words * 4, st));
 
@@ -262,6 +282,8 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
     }
     if (n_nodes) {
         k_index_succ<<<(8 * n_nodes + 127) / 128, 128, 0, st>>>(v, ix.succ.p);
+        VSPE_LAUNCH_CHECK(c);
+        k_index_succ16<<<(8 * n_nodes + 127) / 128, 128, 0, st>>>(ix.view(), ix.succ.p, ix.succ16.p);
         VSPE_LAUNCH_CHECK(c);
     }
     // the substitution-hit bitmap costs 3*L probes per window: build it for viral-scale graphs

@@ -37,22 +37,25 @@ __device__ __forceinline__ uint64_t hash_read(const uint32_t* row, uint32_t b, u
 
 __device__ __forceinline__ bool read_equals_text(const uint32_t* row, uint32_t b, const uint64_t* __restrict__ text,
                                                  uint32_t tp, uint32_t L) {
+    uint64_t acc = 0;
     for (uint32_t m = 0; m < L; m += 32) {
         uint64_t x = read64(row, b + m) ^ extract64(text, (uint64_t)tp + m);
-        uint32_t rem = L - m;
+        const uint32_t rem = L - m;
         if (rem < 32) x &= (1ull << (2 * rem)) - 1;
-        if (x) return false;
+        acc |= x;
     }
-    return true;
+    return acc == 0;
 }
 
 enum { PROBE_MISS = 0, PROBE_UNIQUE = 1, PROBE_MULTI = 2 };
 
-// probe window b of a packed row: MISS, the UNIQUE posting, or MULTI (several postings)
-__device__ __forceinline__ int probe_window(const IndexView& ix, const uint32_t* row, uint32_t b, uint32_t& tp, uint32_t& node) {
+// probe window b of a packed row: MISS, the UNIQUE posting, or MULTI (several postings).
+// The slot walk only looks for the first fingerprint match (one load + one compare per turn); the
+// base-by-base verification is straight-line code after that loop, so the lanes of a warp -- whose
+// slot walks differ in length -- run it once and together.  A fingerprint match that fails the
+// verification (2^-20 per occupied slot passed) continues in the out-of-line loop.
+static __device__ __noinline__ int probe_window_rest(const IndexView& ix, const uint32_t* row, uint32_t b, uint64_t h, uint32_t j, uint32_t& tp, uint32_t& node) {
     const uint32_t L = ix.split_len;
-    const uint64_t h = hash_read(row, b, L);
-    uint32_t j = slot_of(h, ix.slot_mask);
     while (true) {
         const uint2 ent = __ldg(ix.slots + j);
         if (ent.x == EMPTY_TP) return PROBE_MISS;
@@ -65,6 +68,22 @@ __device__ __forceinline__ int probe_window(const IndexView& ix, const uint32_t*
     }
 }
 
+__device__ __forceinline__ int probe_window(const IndexView& ix, const uint32_t* row, uint32_t b, uint32_t& tp, uint32_t& node) {
+    const uint32_t L = ix.split_len;
+    const uint64_t h = hash_read(row, b, L);
+    uint32_t j = slot_of(h, ix.slot_mask);
+    uint2 ent;
+    while (true) {
+        ent = __ldg(ix.slots + j);
+        if (ent.x == EMPTY_TP || fp_match(ent.y, h, ix.node_mask)) break;
+        j = (j + 1) & ix.slot_mask;
+    }
+    if (ent.x == EMPTY_TP) return PROBE_MISS;
+    if (!read_equals_text(row, b, ix.text, ent.x, L)) return probe_window_rest(ix, row, b, h, (j + 1) & ix.slot_mask, tp, node);
+    tp = ent.x;
+    node = ent.y & ix.node_mask;
+    return ((__ldg(ix.uniq + (ent.x >> 5)) >> (ent.x & 31)) & 1) ? PROBE_UNIQUE : PROBE_MULTI;
+}
 
 // Reverse-complement a packed read row in place (rlen bases in 16-base words): reverse the 2-bit
 // groups of every word, complement, realign by the padding of the last word.  NW = data words.

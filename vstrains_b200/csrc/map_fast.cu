@@ -46,7 +46,6 @@ static constexpr int MAXN = 16;
 // node is a popcount -- no data-dependent loops, every thread of the warp runs the same code.
 // ---------------------------------------------------------------------------------------------
 static constexpr int FL_MAX = 6;
-static constexpr uint32_t BIG_SAMPLE_BLOCKS = 64;          // k_map_first blocks that report reads with > FL_MAX stretches
 static constexpr uint64_t FL_EMPTY = ~0ull;
 
 struct FlatList {
@@ -72,30 +71,6 @@ struct FlatList {
         cex(0, 1); cex(2, 3); cex(4, 5);
         cex(1, 2); cex(3, 4);
     }
-    // sorted list: fold every run of equal nodes into its last entry (hits add up, smallest position wins)
-    __device__ __forceinline__ void merge_repeats() {
-#pragma unroll
-        for (int i = 0; i + 1 < FL_MAX; i++) {
-            if (e[i + 1] != FL_EMPTY && (uint32_t)(e[i] >> 32) == (uint32_t)(e[i + 1] >> 32)) {
-                const uint32_t x = (uint32_t)e[i], y = (uint32_t)e[i + 1];
-                const uint32_t vk = ((x & 0xFFFF) + (y & 0xFFFF)) | (min(x >> 16, y >> 16) << 16);
-                e[i + 1] = (e[i + 1] & 0xFFFFFFFF00000000ull) | vk;
-                e[i] = FL_EMPTY;
-            }
-        }
-    }
-    // copy the register entries to the thread-local arrays of the general path
-    __device__ __forceinline__ void spill_to(uint32_t* l_node, uint32_t* l_vk) const {
-#pragma unroll
-        for (int i = 0; i < FL_MAX; i++) { l_node[i] = (uint32_t)(e[i] >> 32); l_vk[i] = (uint32_t)e[i]; }
-    }
-    // two stretches of the same node (cyclic graph)?
-    __device__ __forceinline__ bool has_repeat() const {
-        bool r = false;
-#pragma unroll
-        for (int i = 0; i + 1 < FL_MAX; i++) r |= e[i + 1] != FL_EMPTY && (uint32_t)(e[i] >> 32) == (uint32_t)(e[i + 1] >> 32);
-        return r;
-    }
 };
 
 // saturation predicate over a sorted list; writes the kept node indices in ascending order
@@ -112,38 +87,6 @@ __device__ __forceinline__ uint32_t flat_finalize(const FlatList& fl, const Inde
     for (int i = 0; i < FL_MAX; i++)
         if ((keepmask >> i) & 1) out->ids[__popc(keepmask & ((1u << i) - 1))] = (uint32_t)(fl.e[i] >> 32);
     return (uint32_t)__popc(keepmask);
-}
-
-// The general case (more than FL_MAX stretches: graphs with many short nodes per read): the list
-// lives in thread-local arrays; repeats are merged (or reported), then the same predicate and an
-// O(n^2) rank.  Returns false if the read must go to the next tier.
-__device__ __noinline__ bool list_finalize_slow(uint32_t* l_node, uint32_t* l_vk, uint32_t nn, bool merge, const IndexView& ix,
-                                                uint32_t rlen, uint32_t L, ReadSlot* out, uint32_t& n_out) {
-    for (uint32_t a = 1; a < nn; a++) {
-        for (uint32_t b = 0; b < a; b++) {
-            if (l_node[b] == l_node[a] && l_vk[b]) {
-                if (!merge) return false;
-                const uint32_t x = l_vk[b], y = l_vk[a];
-                l_vk[b] = ((x & 0xFFFF) + (y & 0xFFFF)) | (min(x >> 16, y >> 16) << 16);
-                l_vk[a] = 0;
-                break;
-            }
-        }
-    }
-    uint32_t keepmask = 0;
-    for (uint32_t a = 0; a < nn; a++) {
-        const uint32_t vk = l_vk[a];
-        if (vk && keep_node_f(vk & 0xFFFF, vk >> 16, __ldg(ix.node_len + l_node[a]), rlen, L)) keepmask |= 1u << a;
-    }
-    n_out = __popc(keepmask);
-    if (n_out > (uint32_t)SLOT_IDS) return false;
-    for (uint32_t a = 0; a < nn; a++) {
-        if (!((keepmask >> a) & 1)) continue;
-        uint32_t rank = 0;
-        for (uint32_t b = 0; b < nn; b++) rank += ((keepmask >> b) & 1) && l_node[b] < l_node[a];
-        out->ids[rank] = l_node[a];
-    }
-    return true;
 }
 
 // number of equal bases of read[rb..] and text[tb..], at most max_ext
@@ -332,7 +275,7 @@ __device__ __forceinline__ uint32_t run_pass(const IndexView& ix, const uint32_t
     return limit;
 }
 
-// PACKED: phase 1 loads the 2-bit rows written by k_scan_pack (scan_pack.cu) instead of packing
+// PACKED: phase 1 loads the 2-bit rows written by k_scan_rows (scan_map.cu) instead of packing
 // the raw bytes itself.
 template <int STRIDE, int LPR, bool PACKED>
 __device__ __forceinline__ void
@@ -602,333 +545,7 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_map_first: the common case only.  Packs nothing (rows come from k_scan_pack), runs ONE clean
-// forward pass -- seed window 0, extend, walk successors -- and finishes the read if that pass
-// proves every window.  Anything else (a miss, a mismatch, a repeat, too many nodes) defers the
-// read, untouched, to k_map_fast via a worklist, so the two populations never share a warp.
-// ---------------------------------------------------------------------------------------------
-// GENERAL: reads with more than FL_MAX stretches keep the extra entries in thread-local arrays and
-// finish in the O(n^2) path; otherwise they are deferred.  The host picks the variant from the share
-// of such reads in the previous launch (CNT_BIG, sampled in the first blocks): graphs with long nodes
-// run the lean variant, graphs with many short nodes per read the general one.
-template <int STRIDE, int LPR, bool FLAT, bool GENERAL>
-__global__ void __launch_bounds__(MF_THREADS)
-k_map_first(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
-            uint64_t n_reads, ReadSlot* __restrict__ slots, uint32_t* __restrict__ defer_list,
-            unsigned long long* __restrict__ counters) {
-    __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
-    __shared__ uint32_t s_len[MF_THREADS];
-    const uint64_t r0 = (uint64_t)blockIdx.x * MF_THREADS;
-    const uint32_t L = ix.split_len;
-    {
-        const uint32_t t = threadIdx.x;
-        const uint64_t r = r0 + t;
-        uint32_t h = 0xFFFFFFFFu;
-        if (r < n_reads) {
-            h = __ldg(hdr + r);
-            if (!(h & PH_LONG)) load_row<STRIDE, false>(rows, r, row_words, h & 0xFFFFFF, s_fwd + t * STRIDE, nullptr);
-        }
-        s_len[t] = h;
-    }
-    __syncwarp();
-    const uint32_t t = threadIdx.x;
-    const uint64_t r = r0 + t;
-    const uint32_t h = s_len[t];
-    if (h == 0xFFFFFFFFu) return;
-    if (t == 0 && blockIdx.x == 0) atomicAdd(&counters[CNT_FAST], (unsigned long long)n_reads);
-    ReadSlot* out = slots + r;
-    const uint32_t rlen = h & 0xFFFFFF;
-    bool defer = (h & (PH_LONG | PH_BAD)) != 0;
-    if (!(h & PH_LONG)) {
-        if (h & PH_N) { out->hdr = ST_N; return; }
-        if (rlen < L) { out->hdr = ST_SHORT; return; }
-    }
-    const uint32_t* row = s_fwd + t * STRIDE;
-    uint32_t nn = 0;
-    FlatList fl;                                           // per-read node list: first FL_MAX entries in registers,
-    uint32_t l_node[GENERAL ? MAXN : 1], l_vk[GENERAL ? MAXN : 1];   // the rest (GENERAL) thread-local
-    constexpr uint32_t LIST_CAP = GENERAL ? (uint32_t)MAXN : (uint32_t)FL_MAX;
-    bool big = false;                                      // more than FL_MAX stretches
-    fl.clear();
-    if (!defer) {
-        uint32_t tp = NONE32, node = 0;
-        if (probe_window(ix, row, 0, tp, node) != PROBE_UNIQUE) defer = true;
-        // Walk the read along one diagonal per node strand: read base p sits at text position
-        // p + delta.  Each step compares 32 bases and tests the uniq bits of the 32 windows that
-        // END at those bases; the first window of a stretch is unique by construction (seed:
-        // PROBE_UNIQUE, later ones: successor table).
-        // FLAT: one loop whose every turn is "compare up to 32 bases, then -- if the stretch is complete --
-        // append it and step to the successor strand", so the threads of a warp stay in step however
-        // their reads are cut into stretches (the nested form runs max-stretches x max-chunks turns).
-        uint32_t i0 = 0, p = L, q = 0, lim = 0;
-        int delta = 0;
-        auto enter = [&]() {                                   // strand of window i0 = text position tp
-            const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
-            const bool rcs = tp >= s1;
-            q = 2 * node + (rcs ? 1u : 0u);
-            const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
-            delta = (int)tp - (int)i0;
-            lim = min(rlen, (uint32_t)((int)send - delta));    // read position where the strand ends
-        };
-        auto chunk = [&]() -> bool {                           // bases [p, p + n) and the windows ending there
-            const uint32_t n = min(32u, lim - p);
-            uint64_t x = read64(row, p) ^ extract64(ix.text, (uint64_t)((int)p + delta));
-            const uint32_t u = (uint32_t)((int)p + delta) - L + 1;             // text position of the first window ending here
-            const uint32_t ub = __funnelshift_r(__ldg(ix.uniq + (u >> 5)), __ldg(ix.uniq + (u >> 5) + 1), u & 31);
-            const uint32_t m32 = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
-            if (n < 32) x &= (1ull << (2 * n)) - 1;
-            if (x != 0 || (ub & m32) != m32) return false;
-            p += n;
-            return true;
-        };
-        if (FLAT) {
-            bool running = !defer;
-            if (running) enter();
-            while (running) {
-                if (p < lim && !chunk()) { defer = true; running = false; }
-                if (running && p >= lim) {
-                    // append the stretch; a node met twice (cyclic graph) is detected at the end and deferred
-                    big |= nn == (uint32_t)FL_MAX;
-                    if (nn == LIST_CAP) { defer = true; running = false; }
-                    else {
-                        const uint32_t vk = (lim - L + 1 - i0) | (i0 << 16);
-                        if (nn < (uint32_t)FL_MAX) fl.set(nn, node, vk);
-                        else if (GENERAL) { l_node[nn] = node; l_vk[nn] = vk; }
-                        nn++;
-                        if (lim >= rlen) running = false;
-                        else {
-                            // the strand ended before the read: successor window for the read's next base
-                            const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
-                            const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
-                            if (sc.x == NONE32) { defer = true; running = false; }
-                            else {
-                                i0 = lim - L + 1;
-                                tp = sc.x;
-                                node = sc.y;
-                                p = lim + 1;
-                                enter();
-                            }
-                        }
-                    }
-                }
-            }
-        } else {
-            while (!defer) {
-                enter();
-                while (p < lim) {
-                    if (!chunk()) { defer = true; break; }
-                }
-                if (defer) break;
-                big |= nn == (uint32_t)FL_MAX;
-                if (nn == LIST_CAP) { defer = true; break; }
-                if (nn < (uint32_t)FL_MAX) fl.set(nn, node, (lim - L + 1 - i0) | (i0 << 16));
-                else if (GENERAL) { l_node[nn] = node; l_vk[nn] = (lim - L + 1 - i0) | (i0 << 16); }
-                nn++;
-                if (lim >= rlen) break;
-                const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
-                const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
-                if (sc.x == NONE32) { defer = true; break; }
-                i0 = lim - L + 1;
-                tp = sc.x;
-                node = sc.y;
-                p = lim + 1;
-            }
-        }
-    }
-    uint32_t n_out = 0;
-    if (!defer && nn <= (uint32_t)FL_MAX) {
-        fl.sort();
-        if (fl.has_repeat()) defer = true;                 // needs merging: full kernel
-        else n_out = flat_finalize(fl, ix, rlen, L, out);
-    } else if (!defer && GENERAL) {
-        fl.spill_to(l_node, l_vk);
-        if (!list_finalize_slow(l_node, l_vk, nn, false, ix, rlen, L, out, n_out)) defer = true;
-    }
-    if (big && blockIdx.x < BIG_SAMPLE_BLOCKS) atomicAdd(&counters[CNT_BIG], 1ull);
-    if (defer) {
-        const unsigned long long idx = atomicAdd(&counters[CNT_DEFER], 1ull);
-        defer_list[idx] = (uint32_t)r;
-        return;
-    }
-    out->hdr = ST_OK | (n_out << 8);
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_map_second: the reads k_map_first deferred, one thread per read, still one walk -- but ONE
-// mismatching base is tolerated.  The windows covering it equal text windows except for that base,
-// so a clear substitution-hit bit in every strand that holds such windows proves that they all miss
-// (exactly what the reference's look-ups would find); they are simply not counted.  If window 0
-// does not seed (error in the first split_len bases) the same walk runs on the reverse complement
-// from the other end.  A second mismatch, a set bit, a repeat or a missing successor sends the read
-// on to k_map_fast.
-// ---------------------------------------------------------------------------------------------
-template <int STRIDE, bool GENERAL>
-__device__ __forceinline__ void
-map_second_read(const IndexView& ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
-                const uint32_t r, uint32_t* row, ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list,
-                unsigned long long* __restrict__ out_count) {
-    const uint32_t L = ix.split_len;
-    const uint32_t h = __ldg(hdr + r);
-    bool defer = (h & (PH_LONG | PH_BAD)) != 0 || ix.subst == nullptr;
-    const uint32_t rlen = h & 0xFFFFFF;
-    uint32_t nn = 0;
-    FlatList fl;                                           // per-read node list: first FL_MAX entries in registers,
-    uint32_t l_node[GENERAL ? MAXN : 1], l_vk[GENERAL ? MAXN : 1];   // the rest (GENERAL) thread-local
-    constexpr uint32_t LIST_CAP = GENERAL ? (uint32_t)MAXN : (uint32_t)FL_MAX;
-    if (!defer) {
-        load_row<STRIDE, false>(rows, r, row_words, rlen, row, nullptr);
-        const int npos = (int)(rlen - L + 1);
-        // Which end seeds?  Window 0 of the read, else (error in the first split_len bases) window 0 of
-        // its reverse complement.  The walk itself then runs ONCE, for all threads of the warp together.
-        bool resolved = false, mirror = false;
-        uint32_t tp = NONE32, node = 0;
-        int pr = probe_window(ix, row, 0, tp, node);
-        if (pr == PROBE_MISS) {
-            // reverse-complement the packed row in place
-            constexpr int NW = STRIDE - 3;
-            const uint32_t nwords = (rlen + 15) >> 4, pad = 16 * nwords - rlen;
-            uint32_t y[NW];
-            uint32_t prev = 0;
-#pragma unroll
-            for (int k = 0; k < NW; k++) {
-                y[k] = 0;
-                const int kk = NW - 1 - k;
-                if ((uint32_t)kk >= nwords) continue;
-                uint32_t rv = __brev(row[kk]);
-                rv = (((rv & 0x55555555u) << 1) | ((rv >> 1) & 0x55555555u)) ^ 0xAAAAAAAAu;
-                const int j = (int)nwords - 1 - kk;
-                if (j > 0) y[j - 1] = __funnelshift_r(prev, rv, 2 * pad);
-                prev = rv;
-            }
-            if (nwords) y[nwords - 1] = __funnelshift_r(prev, 0u, 2 * pad);
-#pragma unroll
-            for (int k = 0; k < NW; k++) row[k] = y[k];
-            mirror = true;
-            pr = probe_window(ix, row, 0, tp, node);
-        }
-        fl.clear();
-        // (PROBE_MULTI, or both ends miss: a real complication, the full kernel decides)
-        bool running = pr == PROBE_UNIQUE;
-        bool err = false;
-        int e = 0;
-        uint32_t rb = 0;
-        uint32_t i0 = 0, p = L, q = 0, lim = 0;
-        int delta = 0;
-        // strand of window i0 = text position tp; false if the error's windows cannot be proven to miss there
-        auto enter = [&]() -> bool {
-            const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
-            const bool rcs = tp >= s1;
-            q = 2 * node + (rcs ? 1u : 0u);
-            const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
-            delta = (int)tp - (int)i0;
-            lim = min(rlen, (uint32_t)((int)send - delta));      // read position where the strand ends
-            // a strand entered after the error still holds windows covering it if it starts at or before e
-            if (err && (int)i0 <= e) {
-                const uint32_t te = (uint32_t)(e + delta);
-                if ((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u) return false;
-            }
-            return true;
-        };
-        if (running && !enter()) running = false;
-        // flat loop: every turn compares up to 32 bases and, when the stretch is complete, books it and
-        // steps to the successor strand
-        while (running) {
-            if (p < lim) {
-                const uint32_t n = min(32u, lim - p);
-                uint64_t x = read64(row, p) ^ extract64(ix.text, (uint64_t)((int)p + delta));
-                if (n < 32) x &= (1ull << (2 * n)) - 1;
-                bool ok = true;
-                if (x) {
-                    const uint32_t off = (uint32_t)(__ffsll((long long)x) - 1) >> 1;
-                    if (err || (x & ~(3ull << (2 * off)))) ok = false;          // second mismatch
-                    else {
-                        err = true;
-                        e = (int)(p + off);
-                        rb = (row[(uint32_t)e >> 4] >> (((uint32_t)e & 15) * 2)) & 3u;
-                        const uint32_t te = (uint32_t)(e + delta);
-                        if ((__ldg(ix.subst + (te >> 3)) >> (4 * (te & 7) + rb)) & 1u) ok = false;
-                    }
-                }
-                const uint32_t u = (uint32_t)((int)p + delta) - L + 1;     // text position of the first window ending here
-                const uint32_t ub = __funnelshift_r(__ldg(ix.uniq + (u >> 5)), __ldg(ix.uniq + (u >> 5) + 1), u & 31);
-                const uint32_t m32 = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
-                if ((ub & m32) != m32) ok = false;
-                if (!ok) { running = false; break; }
-                p += n;
-            }
-            if (p >= lim) {
-                // windows [a, bw] of this node are resolved; those covering e are proven misses
-                const int a = (int)i0, bw = (int)lim - (int)L;
-                int c1 = bw - a + 1, c2 = 0, last_hit = bw, first_hit = a;
-                if (err) {
-                    c1 = min(bw, e - (int)L) - a + 1;
-                    if (c1 < 0) c1 = 0;
-                    const int a2 = max(a, e + 1);
-                    c2 = bw - a2 + 1;
-                    if (c2 < 0) c2 = 0;
-                    first_hit = c1 > 0 ? a : a2;
-                    last_hit = c2 > 0 ? bw : min(bw, e - (int)L);
-                }
-                if (c1 + c2 > 0) {
-                    if (nn == LIST_CAP) { running = false; break; }
-                    const uint32_t vk = (uint32_t)(c1 + c2) | ((uint32_t)(mirror ? npos - 1 - last_hit : first_hit) << 16);
-                    if (nn < (uint32_t)FL_MAX) fl.set(nn, node, vk);
-                    else if (GENERAL) { l_node[nn] = node; l_vk[nn] = vk; }
-                    nn++;
-                }
-                if (lim >= rlen) { resolved = true; running = false; break; }
-                // the strand ended before the read: successor window for the read's next base
-                const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
-                const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
-                if (sc.x == NONE32) { running = false; break; }
-                i0 = lim - L + 1;
-                tp = sc.x;
-                node = sc.y;
-                p = lim + 1;
-                if (!enter()) { running = false; break; }
-            }
-        }
-        if (!resolved) defer = true;
-    }
-    ReadSlot* out = slots + r;
-    uint32_t n_out = 0;
-    if (!defer && nn <= (uint32_t)FL_MAX) {
-        // a node met in two stretches (cyclic graph): after the sort they are neighbours; the last
-        // of a run takes the sum of the hits and the smallest position
-        fl.sort();
-        fl.merge_repeats();
-        n_out = flat_finalize(fl, ix, rlen, L, out);
-    } else if (!defer && GENERAL) {
-        fl.spill_to(l_node, l_vk);
-        if (!list_finalize_slow(l_node, l_vk, nn, true, ix, rlen, L, out, n_out)) defer = true;
-    }
-    if (defer) {
-        out_list[atomicAdd(out_count, 1ull)] = r;
-        return;
-    }
-    out->hdr = ST_OK | (n_out << 8);
-}
-
-// A fixed grid walks the device-side worklist (its length is only known on the device).  The
-// deferred reads are few and each is a long serial chain: only every `spread`-th thread takes one.
-template <int STRIDE, bool GENERAL>
-__global__ void __launch_bounds__(MF_THREADS)
-k_map_second(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr, uint32_t row_words,
-             const uint32_t* __restrict__ in_list, const unsigned long long* __restrict__ in_count, uint32_t spread,
-             ReadSlot* __restrict__ slots, uint32_t* __restrict__ out_list, unsigned long long* __restrict__ out_count) {
-    __shared__ uint32_t s_fwd[MF_THREADS * STRIDE];
-    const uint64_t n_items = *in_count;
-    const uint32_t per_block = MF_THREADS / spread;
-    if (threadIdx.x % spread != 0) return;
-    for (uint64_t base = (uint64_t)blockIdx.x * per_block; base < n_items; base += (uint64_t)gridDim.x * per_block) {
-        const uint64_t item = base + threadIdx.x / spread;
-        if (item < n_items)
-            map_second_read<STRIDE, GENERAL>(ix, rows, hdr, row_words, in_list[item], s_fwd + threadIdx.x * STRIDE, slots, out_list, out_count);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_map_windows: the reads k_map_first deferred (sequencing errors, repeats, many nodes).
+// k_map_windows: the reads k_map_fast could not prove (repeats, palindromes, more than 16 nodes).
 // One warp per read, one lane per window, every window looked up -- the reference's algorithm
 // (PE_Inference.py:24-31) with no shortcuts, so every postings multiplicity is exact.  All lanes
 // stay busy; hit counts and first positions live in lane registers (lane k owns the k-th distinct
@@ -1032,118 +649,55 @@ k_map_windows(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* _
 int map_reads_generic_dev(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                           const uint32_t* d_worklist, const unsigned long long* d_n_items, ReadSlot* d_slots);
 
-// threads per deferred read in the list-driven kernels: a power of two in [1, 32]
-static uint32_t pow2_spread(int64_t v) {
-    uint32_t s = 1;
-    while (s < 32 && (int64_t)s * 2 <= v) s *= 2;
-    return s;
-}
-
 // Work lists of the list-driven tiers for a chunk of up to n_reads reads (reserved and emptied before
 // the first kernel that appends to them).
 int map_prepare_lists(Ctx* c, uint64_t n_reads) {
     if (n_reads > 0xFFFFFFFFull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
     VSPE_TRY(c->worklist.reserve(n_reads + 1));
-    VSPE_TRY(c->defer_list.reserve(3 * n_reads + 3));
+    VSPE_TRY(c->defer_list.reserve(2 * n_reads + 2));
     VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
     VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER, 0, 8, c->stream));
-    VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER2, 0, 8, c->stream));
     VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK2, 0, 8, c->stream));
     return VSPE_OK;
 }
 
-// pre_listed: the reads to map are the counters[CNT_DEFER] entries of c->defer_list (written by k_scan_map
-// after map_prepare_lists); the walk stages 1 / 1b already ran inside that kernel.
+static constexpr uint32_t LIST_SPREAD = 2;      // list-driven k_map_fast: every 2nd thread takes a read (long serial chains)
+
+// The tiers behind the walk.  pre_listed: the reads to map are the counters[CNT_DEFER] entries of c->defer_list
+// (written by k_walk after map_prepare_lists) and their packed rows exist; otherwise every read [0, n_reads) goes
+// through the full seed-and-extend kernel, which packs the raw bytes itself.
+//   stage 1  k_map_fast     seed-and-extend in both directions + cooperative confirmation probes
+//   stage 2  k_map_windows  what stage 1 could not prove (repeats, > 16 nodes): one warp per read, every window looked up
+//                           (packed reads only)
+//   stage 3  k_map_generic  the exhaustive ASCII tier: any read length / alphabet
 static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                            const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                           uint64_t n_reads, ReadSlot* d_slots, bool pre_listed = false) {
+                           uint64_t n_reads, ReadSlot* d_slots, bool pre_listed) {
     if (n_reads == 0) return VSPE_OK;
     if (n_reads > 0xFFFFFFFFull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
     if (!pre_listed) {
         VSPE_TRY(c->worklist.reserve(n_reads));
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
     }
-    const uint32_t grid = (uint32_t)((n_reads + MF_THREADS - 1) / MF_THREADS);
     IndexView v = c->index.view();
-    const uint32_t* in_list = nullptr;
-    const unsigned long long* in_count = nullptr;
+    const uint32_t* in_list = pre_listed ? c->defer_list.p : nullptr;
+    const unsigned long long* in_count = pre_listed ? c->counters.p + CNT_DEFER : nullptr;
     const uint32_t* to_generic = c->worklist.p;                 // reads the ASCII tier must map
     const unsigned long long* to_generic_n = c->counters.p + CNT_WORK;
-    if (d_rows && !pre_listed) {
-        VSPE_TRY(c->defer_list.reserve(3 * n_reads));
-        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER, 0, 8, c->stream));
-        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER2, 0, 8, c->stream));
-        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK2, 0, 8, c->stream));
-    }
-    // lean or general walk kernels (forced by the map_general option, else from the last launch's CNT_BIG)
-    const bool general = c->opt_map_general >= 0 ? c->opt_map_general != 0 : c->map_general;
-    if (pre_listed) {
-        in_list = c->defer_list.p;
-        in_count = c->counters.p + CNT_DEFER;
-    } else if (d_rows && !c->opt_single_map) {
-        // stage 1: the clean-pass kernel; what it defers goes through the full kernel
-#define VSPE_M1(S, LP, FL, GN) k_map_first<S, LP, FL, GN><<<grid, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, n_reads, d_slots, \
-                                                                                        c->defer_list.p, c->counters.p)
-#define VSPE_M1S(FL, GN) do { if (cap <= 160) VSPE_M1(13, 16, FL, GN); else if (cap <= 256) VSPE_M1(19, 16, FL, GN); else VSPE_M1(23, 32, FL, GN); } while (0)
-        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_BIG, 0, 8, c->stream));
-        if (c->opt_flat_walk) { if (general) VSPE_M1S(true, true); else VSPE_M1S(true, false); }
-        else { if (general) VSPE_M1S(false, true); else VSPE_M1S(false, false); }
-        c->big_sampled = std::min<uint64_t>(n_reads, (uint64_t)BIG_SAMPLE_BLOCKS * MF_THREADS);
-        c->big_pending = true;
-#undef VSPE_M1S
-#undef VSPE_M1
-        VSPE_LAUNCH_CHECK(c);
-        in_list = c->defer_list.p;
-        in_count = c->counters.p + CNT_DEFER;
-        if (c->index.has_subst && !c->opt_no_second) {
-            // stage 1b: one-error-tolerant walk on the deferred reads; its leftovers go to stage 2
-            uint32_t* list1b = c->defer_list.p + 2 * n_reads;
-            const uint32_t spread2 = pow2_spread(c->opt_second_spread);
-            const uint32_t grid_s = (uint32_t)std::min<uint64_t>((n_reads * spread2 + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 16);
-#define VSPE_M2(S, GN) k_map_second<S, GN><<<grid_s, MF_THREADS, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->defer_list.p, \
-                                                                           c->counters.p + CNT_DEFER, spread2, d_slots, list1b, c->counters.p + CNT_DEFER2)
-            if (general) { if (cap <= 160) VSPE_M2(13, true); else if (cap <= 256) VSPE_M2(19, true); else VSPE_M2(23, true); }
-            else { if (cap <= 160) VSPE_M2(13, false); else if (cap <= 256) VSPE_M2(19, false); else VSPE_M2(23, false); }
-#undef VSPE_M2
-            VSPE_LAUNCH_CHECK(c);
-            in_list = list1b;
-            in_count = c->counters.p + CNT_DEFER2;
-        }
-    }
-    // what stage 3 reads: the reads stage 2 gave up on -- or, without stage 2, everything stage 1 deferred
-    const uint32_t* win_list = c->worklist.p;
-    const unsigned long long* win_count = c->counters.p + CNT_WORK;
-    const bool skip_fast = d_rows && in_list && !c->opt_fast_tier;
-    if (skip_fast) {
-        win_list = in_list;
-        win_count = in_count;
-    }
-    // stage 2: the full seed-and-extend kernel (on the deferred reads, or on everything)
-    const uint32_t list_spread = pow2_spread(c->opt_list_spread);
-    const uint32_t grid2 = in_list ? (uint32_t)std::min<uint64_t>((n_reads * list_spread + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 8) : grid;
-#define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid2, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
-                                                                               row_words, n_reads, in_list, in_count, list_spread, d_slots, \
-                                                                               c->worklist.p, c->counters.p)
-    if (skip_fast) {
-        // (stage 2 skipped: the deferred reads go straight to the all-windows kernel)
-    } else if (d_rows) {
-        if (cap <= 160) VSPE_MF(13, 16, true); else if (cap <= 256) VSPE_MF(19, 16, true); else VSPE_MF(23, 32, true);
-        VSPE_LAUNCH_CHECK(c);
-    } else {
-        if (cap <= 160) VSPE_MF(13, 16, false); else if (cap <= 256) VSPE_MF(19, 16, false); else VSPE_MF(23, 32, false);
-        VSPE_LAUNCH_CHECK(c);
-    }
+    const uint32_t grid = pre_listed ? (uint32_t)std::min<uint64_t>((n_reads * LIST_SPREAD + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 8)
+                                     : (uint32_t)((n_reads + MF_THREADS - 1) / MF_THREADS);
+#define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
+                                                                              row_words, n_reads, in_list, in_count, LIST_SPREAD, d_slots, \
+                                                                              c->worklist.p, c->counters.p)
+    if (pre_listed) { if (cap <= 160) VSPE_MF(13, 16, true); else if (cap <= 256) VSPE_MF(19, 16, true); else VSPE_MF(23, 32, true); }
+    else { if (cap <= 160) VSPE_MF(13, 16, false); else if (cap <= 256) VSPE_MF(19, 16, false); else VSPE_MF(23, 32, false); }
 #undef VSPE_MF
-    if (d_rows) {
-        // stage 3: what stage 2 could not prove (repeats, > 16 nodes): one warp per read, every
-        // window looked up, exact for any postings multiplicity; only reads that do not fit the
-        // 2-bit rows at all (non-ACGT, very long) are left for the ASCII tier
-        if (!c->spill.p) VSPE_TRY(c->spill.reserve(4u << 20));
+    VSPE_LAUNCH_CHECK(c);
+    if (pre_listed) {
         uint32_t* list2 = c->defer_list.p + n_reads;
         const uint32_t wgrid = (uint32_t)std::min<uint64_t>((n_reads + MW_WARPS - 1) / MW_WARPS, (uint64_t)c->sm_count * 16);
-#define VSPE_MW(S) k_map_windows<S><<<wgrid, MW_WARPS * 32, 0, c->stream>>>(v, d_rows, d_hdr, row_words, win_list, \
-                                                                      win_count, d_slots, list2, \
-                                                                      c->counters.p + CNT_WORK2, c->spill.p, c->spill.cap, c->counters.p)
+#define VSPE_MW(S) k_map_windows<S><<<wgrid, MW_WARPS * 32, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->worklist.p, c->counters.p + CNT_WORK, \
+                                                                      d_slots, list2, c->counters.p + CNT_WORK2, c->spill.p, c->spill.cap, c->counters.p)
         if (cap <= 160) VSPE_MW(13); else if (cap <= 256) VSPE_MW(19); else VSPE_MW(23);
 #undef VSPE_MW
         VSPE_LAUNCH_CHECK(c);
@@ -1155,34 +709,16 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     return VSPE_OK;
 }
 
-// After a stream synchronisation: look at how many of the sampled reads of the last k_map_first
-// launch had more than FL_MAX stretches and pick the walk-kernel variant for the next launch.
-// Both variants are exact; this only moves reads between tiers.
-int adapt_map_variant(Ctx* c) {
-    if (!c->big_pending) return VSPE_OK;
-    unsigned long long big = 0;
-    VSPE_CUDA(cudaMemcpy(&big, c->counters.p + CNT_BIG, 8, cudaMemcpyDeviceToHost));
-    c->big_pending = false;
-    if (c->big_sampled) c->map_general = big * 50 > c->big_sampled;      // more than 2 %
-    return VSPE_OK;
-}
-
 // packed-row capacity (bases) by the read length seen in the first records; longer reads bail
 uint32_t map_fast_cap(uint32_t hint) { return hint <= 160 ? 160 : hint <= 256 ? 256 : 320; }
 
 int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                    uint64_t n_reads, ReadSlot* d_slots) {
     if (c->index.split_len > 320) return map_reads_generic(c, d_buf, d_seq_start, d_seq_end, n_reads, d_slots);
-    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, nullptr, nullptr, 0, map_fast_cap(c->read_len_hint), n_reads, d_slots);
+    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, nullptr, nullptr, 0, map_fast_cap(c->read_len_hint), n_reads, d_slots, false);
 }
 
-int map_reads_packed(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
-                     const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                     uint64_t n_reads, ReadSlot* d_slots) {
-    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, row_words, cap, n_reads, d_slots);
-}
-
-// the reads k_scan_map left unresolved (listed in c->defer_list): full seed-and-extend kernel, then the
+// the reads k_walk left unresolved (listed in c->defer_list): full seed-and-extend kernel, then the
 // all-windows kernel, then the ASCII tier; results go to d_slots[r] for the listed r
 int map_reads_deferred(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                        const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,

@@ -1,13 +1,14 @@
-// scan_map.cu -- K1 + K2 + K4 in ONE pass over the raw FASTQ bytes: every input byte is read from
-// HBM once and a read costs 4 bytes on the way out (the handle of its node list, link.cuh).
+// scan_map.cu -- K1 + K2 (k_scan_rows) and the first tier of K4 (k_walk): the default path of a
+// FASTQ chunk from raw bytes to node-list handles.
 //
 // Replaces `readlines()` + `[s[:-1] ...]` (reference utils/VStrains_PE_Inference.py:149-159), the
 // per-character work of `fseq.count("N")` / k-mer slicing (:160, :25) and single_end_read_mapping
-// (:16-48) for every read whose result the walk below can PROVE; the rest (about 3 % on the bench
-// workloads: two or more sequencing errors, repeats, non-ACGT characters, very long reads) is handed,
-// packed, to the list-driven tiers of map_fast.cu / map_generic.cu.
+// (:16-48) for every read whose result the walk can PROVE; the rest (about 3 % on the bench
+// workloads: two or more sequencing errors, repeats, non-ACGT characters, very long reads) is
+// listed for the list-driven tiers of map_fast.cu / map_generic.cu.
 //
-// Per 40 KiB tile (one CTA of 10 warps, 3 CTAs per SM, tiles handed out by a ticket counter):
+// k_scan_rows -- ONE pass over the bytes, per 40 KiB tile (one CTA of 10 warps, 4 CTAs per SM, tiles
+// handed out by a ticket counter):
 //   1. one elected thread issues TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of the tile
 //      + a 16-byte front margin + a 512-byte back margin into shared memory;
 //   2. every lane tests its 16-byte vectors for bytes < 0x10 or >= 0x80 (two instructions per
@@ -16,17 +17,21 @@
 //   3. warp totals + one block exchange give the tile's terminator count; a decoupled look-back
 //      over the tiles' status words gives the line number of the tile's first line;
 //   4. terminators with line%4==0 start a sequence line, line%4==1 end it -> per-tile read table;
-//   5. 8 / 16 lanes per read pack each read the tile owns (its sequence line STARTS here) to
-//      2 bits/base straight from the tile into a shared-memory row (SIMD-in-word ACGT validity test,
-//      'N' flag);
-//   6. one thread per read walks its row through the index: seed window 0 (hash + probe + verify +
-//      uniq bit; on a miss the reverse complement is seeded from the other end), then a flat loop
-//      whose every turn compares 32 bases + 32 uniq bits on the current diagonal and, when the
-//      stretch is complete, books it and steps to the successor strand.  ONE mismatching base is
-//      tolerated when the substitution-hit bit proves that the windows covering it have no posting.
-//      The saturation predicate (:36-47, integer form) is applied as each stretch is booked;
-//   7. the kept node list is interned (link.cuh) and its handle stored; an unresolved read is
-//      stored packed for the next tier and listed.
+//   5. one thread per read packs the read the tile owns (its sequence line STARTS here) to 2 bits/base
+//      straight from the tile, 16 bases per step (SIMD-in-word ACGT validity test, 'N' flag), into a
+//      shared-memory row; each warp then copies its 32 rows to HBM with coalesced stores
+//      (48 / 64 / 80 bytes per read + a header word + the byte range).
+// k_walk -- one thread per read, 128-thread blocks, 8 blocks per SM (the walk is a chain of dependent
+// L2 accesses: it wants many warps and a large L1, which is why it is NOT fused into the scan kernel --
+// the fused variant was built, bit-exact, and 3x slower: 15 warps per SM, 31 % issue slots):
+//   6. seed window 0 (hash + probe + verify + uniq bit; on a miss the reverse complement is seeded from
+//      the other end), then a flat loop whose every turn compares 32 bases + 32 uniq bits on the current
+//      diagonal and, when the stretch is complete, books it and steps to the successor strand, whose
+//      table entry (text position, strand, strand end, node length: 16 bytes) was requested when the
+//      stretch was entered.  ONE mismatching base is tolerated when the substitution-hit bit proves that
+//      the windows covering it have no posting.  The saturation predicate (:36-47, integer form) is
+//      applied as each stretch is booked;
+//   7. the kept node list is interned (link.cuh) and its handle stored; an unresolved read is listed.
 // Why this is exact: see map_fast.cu (a window is counted without a table access only if its text
 // equality and the uniq bit of that text window were both checked; it is skipped only if the
 // index build already looked that k-mer up and found nothing).
@@ -37,15 +42,24 @@
 
 namespace vspe {
 
-static constexpr int SM_WARPS = 10;
+#ifndef VSPE_SM_WARPS
+#define VSPE_SM_WARPS 10
+#endif
+#ifndef VSPE_SM_ITERS
+#define VSPE_SM_ITERS 8
+#endif
+#ifndef VSPE_SM_MINB
+#define VSPE_SM_MINB 4
+#endif
+static constexpr int SM_WARPS = VSPE_SM_WARPS;
 static constexpr int SM_THREADS = SM_WARPS * 32;
-static constexpr int SM_ITERS = 8;                               // 512-byte warp rows per warp
+static constexpr int SM_ITERS = VSPE_SM_ITERS;                   // 512-byte warp rows per warp
 static constexpr int SM_TILE = SM_WARPS * SM_ITERS * 32 * 16;    // 40 KiB
 static constexpr int SM_FRONT = 16;                              // bytes kept before the tile
 static constexpr int SM_BACK = 512;                              // bytes kept after the tile (>= longest packed read + 1)
-static constexpr int SM_MAXREC = 576;                            // reads a tile may own (else the chunk takes the plain path)
-static constexpr int SM_QCAP = 96;                               // per warp: vectors that may hold a terminator
-static constexpr int SM_RPR = 160;                               // reads packed + walked per round
+static constexpr int SM_MAXREC = SM_TILE / 64 - 64;              // reads a tile may own (else the chunk takes the plain path): 576
+static constexpr int SM_QCAP = 12 * SM_ITERS;                    // per warp: vectors that may hold a terminator
+static constexpr int WK_THREADS = 128;                           // k_walk: reads per block
 static constexpr int SM_MAXST = 16;                              // stretches (nodes with hits) per read in the walk
 
 #define LB_AGG (1ull << 62)
@@ -64,8 +78,12 @@ __device__ __forceinline__ void masks_from_vec(uint4 v, uint32_t valid, uint32_t
     if (valid == 0xFFFFu && ((v.x | v.y | v.z | v.w) & 0x80808080u)) non_ascii = true;
     uint32_t nl = movemask4b(__vcmpeq4(v.x, 0x0A0A0A0Au)) | (movemask4b(__vcmpeq4(v.y, 0x0A0A0A0Au)) << 4) |
                   (movemask4b(__vcmpeq4(v.z, 0x0A0A0A0Au)) << 8) | (movemask4b(__vcmpeq4(v.w, 0x0A0A0A0Au)) << 12);
-    uint32_t cr = movemask4b(__vcmpeq4(v.x, 0x0D0D0D0Du)) | (movemask4b(__vcmpeq4(v.y, 0x0D0D0D0Du)) << 4) |
-                  (movemask4b(__vcmpeq4(v.z, 0x0D0D0D0Du)) << 8) | (movemask4b(__vcmpeq4(v.w, 0x0D0D0D0Du)) << 12);
+    // '\r' is rare: one zero-byte test over the four words decides whether its mask is needed at all
+    const uint32_t zx = v.x ^ 0x0D0D0D0Du, zy = v.y ^ 0x0D0D0D0Du, zz = v.z ^ 0x0D0D0D0Du, zw = v.w ^ 0x0D0D0D0Du;
+    uint32_t cr = 0;
+    if ((((zx - 0x01010101u) & ~zx) | ((zy - 0x01010101u) & ~zy) | ((zz - 0x01010101u) & ~zz) | ((zw - 0x01010101u) & ~zw)) & 0x80808080u)
+        cr = movemask4b(__vcmpeq4(v.x, 0x0D0D0D0Du)) | (movemask4b(__vcmpeq4(v.y, 0x0D0D0D0Du)) << 4) |
+             (movemask4b(__vcmpeq4(v.z, 0x0D0D0D0Du)) << 8) | (movemask4b(__vcmpeq4(v.w, 0x0D0D0D0Du)) << 12);
     if (valid != 0xFFFFu) {
         const uint32_t na = movemask4b(v.x) | (movemask4b(v.y) << 4) | (movemask4b(v.z) << 8) | (movemask4b(v.w) << 12);
         if (na & valid) non_ascii = true;
@@ -87,23 +105,19 @@ struct ScanMapArgs {
     uint64_t line_base;              // lines before this chunk
     uint64_t rec_first;              // record number of slot 0 of the outputs
     uint64_t n_slots;                // capacity of the per-read outputs
-    uint32_t* handles;               // [n_slots] node-list handle / H_N / H_SHORT / H_PENDING per read
-    // written for unresolved reads only (indexed like handles):
-    uint64_t* seq_start;             // chunk-relative byte range of the sequence line
+    uint64_t* seq_start;             // [n_slots] chunk-relative byte range of the sequence line
     uint64_t* seq_end;
     uint32_t* rows;                  // [n_slots][row_words] packed read
-    uint32_t* hdr;                   // rlen | flags << 24
-    uint32_t* defer_list;            // their indices, counters[CNT_DEFER] of them
+    uint32_t* hdr;                   // [n_slots] rlen | flags << 24
     uint32_t row_words;              // 12, 16 or 20
     uint32_t cap;                    // longest read (bases) a packed row holds
     unsigned long long* counters;
 };
 
 // The walk of step 6.  row: this thread's packed read (STRIDE words, zero padded); lst: its node list
-// column (entry i at lst[i * SM_RPR]).  Returns true when every window of the read is accounted for;
-// n_kept nodes that pass the saturation predicate are then at the front of the column.  On false
-// the row is unchanged (a reverse complement taken for seeding is undone).
-template <int STRIDE>
+// column (entry i at lst[i * LS]).  Returns true when every window of the read is accounted for;
+// n_kept nodes that pass the saturation predicate are then at the front of the column.
+template <int STRIDE, int LS>
 __device__ __forceinline__ bool walk_read(const IndexView& ix, uint32_t* row, const uint32_t rlen, uint32_t* lst, uint32_t& n_kept) {
     constexpr int NW = STRIDE - 3;
     const uint32_t L = ix.split_len;
@@ -122,17 +136,24 @@ __device__ __forceinline__ bool walk_read(const IndexView& ix, uint32_t* row, co
     bool err = false;
     int e = 0;
     uint32_t rb = 0;
-    uint32_t i0 = 0, p = L, q = 0, lim = 0, nn = 0, kept = 0;
-    unsigned long long seen = 0;                               // 64-bit filter over the nodes booked so far
+    uint32_t i0 = 0, p = L, q = 0, lim = 0, nn = 0, n_front = 0, nlen = 0;
+    unsigned long long seen = 0, seen2 = 0;                    // two 64-bit filters over the nodes booked so far
     int delta = 0;
-    // strand of window i0 = text position tp; false if the error's windows cannot be proven to miss there
-    auto enter = [&]() -> bool {
-        const uint32_t s1 = __ldg(ix.strand_start + 2 * node + 1);
-        const bool rcs = tp >= s1;
-        q = 2 * node + (rcs ? 1u : 0u);
-        const uint32_t send = rcs ? __ldg(ix.strand_start + 2 * node + 2) : s1;
-        delta = (int)tp - (int)i0;
-        lim = min(rlen, (uint32_t)((int)send - delta));        // read position where the strand ends
+    uint4 nxt = make_uint4(NONE32, 0, 0, 0);                   // successor entry of the current strand for the read's base at lim
+    // enter the strand q that holds text position tp_ (its end: send_, its node length: nlen_) at window i0;
+    // false if the error's windows cannot be proven to miss there
+    auto enter = [&](uint32_t tp_, uint32_t q_, uint32_t send_, uint32_t nlen_) -> bool {
+        q = q_;
+        node = q_ >> 1;
+        nlen = nlen_;
+        delta = (int)tp_ - (int)i0;
+        lim = min(rlen, (uint32_t)((int)send_ - delta));       // read position where the strand ends
+        if (lim < rlen) {
+            // the strand ends before the read: request the successor entry for the read's next base NOW, it is
+            // consumed when the stretch is booked (the chunk compares in between hide the access)
+            const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
+            nxt = __ldg(ix.succ16 + 4 * (size_t)q + b);
+        }
         // a strand entered after the error still holds windows covering it if it starts at or before e
         if (err && (int)i0 <= e) {
             const uint32_t te = (uint32_t)(e + delta);
@@ -140,7 +161,11 @@ __device__ __forceinline__ bool walk_read(const IndexView& ix, uint32_t* row, co
         }
         return true;
     };
-    if (running && !enter()) running = false;
+    if (running) {
+        const uint4 nr = __ldg(ix.node_rec + node);            // {forward start, rc start, end, node length}
+        const bool rcs = tp >= nr.y;
+        if (!enter(tp, 2 * node + (rcs ? 1u : 0u), rcs ? nr.z : nr.y, nr.w)) running = false;
+    }
     while (running) {
         if (p < lim) {
             const uint32_t n = min(32u, lim - p);
@@ -180,63 +205,106 @@ __device__ __forceinline__ bool walk_read(const IndexView& ix, uint32_t* row, co
             }
             if (c1 + c2 > 0) {
                 if (nn == (uint32_t)SM_MAXST) { running = false; break; }
-                // a node met twice (cyclic graph) needs its hits merged: next tier
-                const uint32_t hb = (node * 0x9E3779B1u) >> 26;
-                bool dup = false;
-                if ((seen >> hb) & 1ull)
-                    for (uint32_t i = 0; i < nn; i++) dup |= lst[i * SM_RPR] == node;
-                if (dup) { running = false; break; }
+                // a node met twice (cyclic graph) needs its hits merged by the next tier: two 64-bit filters gate
+                // the exact comparison with the nodes booked so far
+                const uint32_t hb = (node * 0x9E3779B1u) >> 26, hb2 = (node * 0x85EBCA77u) >> 26;
+                if (((seen >> hb) & (seen2 >> hb2)) & 1ull) {
+                    bool dup = false;
+                    for (uint32_t i = 0; i < n_front; i++) dup |= lst[i * LS] == node;
+                    for (uint32_t i = 0; i < nn - n_front; i++) dup |= lst[(SM_MAXST - 1 - i) * LS] == node;
+                    if (dup) { running = false; break; }
+                }
                 seen |= 1ull << hb;
+                seen2 |= 1ull << hb2;
                 const uint32_t v = (uint32_t)(c1 + c2), kmin = (uint32_t)(mirror ? npos - 1 - last_hit : first_hit);
-                if (keep_node_f(v, kmin, __ldg(ix.node_len + node), rlen, L)) kept |= 1u << nn;
-                lst[nn * SM_RPR] = node;
+                // kept nodes fill the column from the front, the others from the back
+                if (keep_node_f(v, kmin, nlen, rlen, L)) lst[(n_front++) * LS] = node;
+                else lst[(SM_MAXST - 1 - (nn - n_front)) * LS] = node;
                 nn++;
             }
             if (lim >= rlen) { resolved = true; running = false; break; }
-            // the strand ended before the read: successor window for the read's next base
-            const uint32_t b = (row[lim >> 4] >> ((lim & 15) * 2)) & 3u;
-            const uint2 sc = __ldg(reinterpret_cast<const uint2*>(ix.succ) + 4 * q + b);
-            if (sc.x == NONE32) { running = false; break; }
+            if (nxt.x == NONE32) { running = false; break; }       // no unique successor window for that base
             i0 = lim - L + 1;
-            tp = sc.x;
-            node = sc.y;
             p = lim + 1;
-            if (!enter()) { running = false; break; }
+            if (!enter(nxt.x, nxt.y, nxt.z, nxt.w)) { running = false; break; }
         }
     }
-    if (!resolved) {
-        if (mirror) revcomp_row<NW>(row, rlen);
-        return false;
-    }
-    uint32_t k = 0;
-    for (uint32_t i = 0; i < nn; i++)
-        if ((kept >> i) & 1u) { lst[k * SM_RPR] = lst[i * SM_RPR]; k++; }
-    n_kept = k;
+    if (!resolved) return false;
+    n_kept = n_front;
     return true;
 }
 
-template <int STRIDE>
-struct ScanMapSmem {
-    static constexpr uint32_t QUEUE_BYTES = SM_WARPS * SM_QCAP * 8;
-    static constexpr uint32_t ROUND_BYTES = SM_RPR * (STRIDE + SM_MAXST + 1) * 4;
-    static constexpr uint32_t UNION_BYTES = QUEUE_BYTES > ROUND_BYTES ? QUEUE_BYTES : ROUND_BYTES;
-    static constexpr uint32_t TOTAL = SM_FRONT + SM_TILE + SM_BACK + SM_MAXREC * 8 + UNION_BYTES + 64;
+// One thread per read of the chunk: pair-skipping classes, else the walk; what it cannot prove is listed.
+struct WalkArgs {
+    const uint32_t* rows;
+    const uint32_t* hdr;
+    uint32_t row_words;
+    uint64_t n_slots;                  // capacity of the per-read arrays
+    const unsigned long long* total;   // terminators of the chunk (written by k_scan_rows)
+    uint64_t line_base, rec_first;
+    uint32_t* handles;
+    uint32_t* defer_list;
+    unsigned long long* counters;
 };
 
+#ifndef VSPE_WK_MINB
+#define VSPE_WK_MINB 10
+#endif
 template <int STRIDE>
-__global__ void __launch_bounds__(SM_THREADS, 3)
-k_scan_map(const ScanMapArgs a, const IndexView ix, const LinkView lv) {
+__global__ void __launch_bounds__(WK_THREADS, VSPE_WK_MINB)
+k_walk(const WalkArgs a, const IndexView ix, const LinkView lv) {
+    __shared__ uint32_t s_rows[WK_THREADS * STRIDE];
+    __shared__ uint32_t s_lst[SM_MAXST * WK_THREADS];
+    // sequence lines of the chunk = #{l in [line_base, line_base + total) : l % 4 == 1}
+    const uint64_t n_lines1 = (uint64_t)(a.line_base + *a.total + 2) / 4 - a.rec_first;
+    const uint64_t n_reads = n_lines1 < a.n_slots ? n_lines1 : a.n_slots;
+    const uint64_t r = (uint64_t)blockIdx.x * WK_THREADS + threadIdx.x;
+    if (r >= n_reads) return;
+    if (r == 0) atomicAdd(&a.counters[CNT_FAST], (unsigned long long)n_reads);
+    const uint32_t h = __ldg(a.hdr + r);
+    const uint32_t rlen = h & 0xFFFFFF, L = ix.split_len;
+    uint32_t handle = H_PENDING;
+    bool defer = (h & (PH_LONG | PH_BAD)) != 0;
+    if (!(h & PH_LONG)) {
+        if (h & PH_N) handle = H_N;                                    // 'N' before the length (PE_Inference.py:160-163)
+        else if (rlen < L) handle = H_SHORT;
+    }
+    if (handle == H_PENDING && !defer) {
+        uint32_t* row = s_rows + threadIdx.x * STRIDE;
+        constexpr int NW = STRIDE - 3, XW = (NW + 3) / 4 * 4;
+        const uint4* src = reinterpret_cast<const uint4*>(a.rows + r * a.row_words);
+        uint32_t x[XW];
+#pragma unroll
+        for (int q = 0; q < XW / 4; q++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if ((uint32_t)(4 * q) < a.row_words) v = __ldg(src + q);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int w = 0; w < NW; w++) row[w] = x[w];
+        row[NW] = 0; row[NW + 1] = 0; row[NW + 2] = 0;
+        uint32_t n_kept = 0;
+        if (walk_read<STRIDE, WK_THREADS>(ix, row, rlen, s_lst + threadIdx.x, n_kept)) handle = intern_list(lv, n_kept, s_lst + threadIdx.x, WK_THREADS);
+        else defer = true;
+    }
+    if (handle == H_PENDING && defer) a.defer_list[atomicAdd(&a.counters[CNT_DEFER], 1ull)] = (uint32_t)r;
+    a.handles[r] = handle;
+}
+
+static constexpr uint32_t SM_QUEUE_BYTES = SM_WARPS * SM_QCAP * 8;
+static constexpr uint32_t SM_SMEM = SM_FRONT + SM_TILE + SM_BACK + SM_MAXREC * 8 + SM_QUEUE_BYTES + 64;
+
+template <int RW>                                                // row words in HBM: 12, 16 or 20 (a multiple of 4 >= cap / 16)
+__global__ void __launch_bounds__(SM_THREADS, VSPE_SM_MINB)
+k_scan_rows(const ScanMapArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_bytes = smem;                                           // [SM_FRONT + SM_TILE + SM_BACK]
     uint32_t* s_rs = reinterpret_cast<uint32_t*>(smem + SM_FRONT + SM_TILE + SM_BACK);   // read start (tile-relative)
     uint32_t* s_re = s_rs + SM_MAXREC;                                 // read end
-    uint32_t* s_un = s_re + SM_MAXREC;                                 // queues, later the rows of a round
+    uint32_t* s_un = s_re + SM_MAXREC;                                 // candidate queues
     uint32_t* s_qmk = s_un;                                            // [SM_WARPS][SM_QCAP] term | crlf << 16
     uint16_t* s_qid = reinterpret_cast<uint16_t*>(s_qmk + SM_WARPS * SM_QCAP);   // vector index in the tile
     uint16_t* s_qrk = s_qid + SM_WARPS * SM_QCAP;                      // rank of the vector's first terminator in the warp
-    uint32_t* s_rows = s_un;                                           // [SM_RPR][STRIDE]
-    uint32_t* s_lst = s_rows + SM_RPR * STRIDE;                        // [SM_MAXST][SM_RPR]
-    uint32_t* s_rhdr = s_lst + SM_MAXST * SM_RPR;                      // [SM_RPR] rlen | flags
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_wtot[SM_WARPS];
     __shared__ uint32_t s_tile;
@@ -350,6 +418,7 @@ k_scan_map(const ScanMapArgs a, const IndexView ix, const LinkView lv) {
     }
     if (bad) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_NON_ASCII);
     if (lane == 0) s_wtot[wib] = wcount | (q_over ? 0x80000000u : 0u);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)SM_MAXREC; i += SM_THREADS) s_re[i] = 0xFFFFFFFFu;   // "line end not seen in this tile"
     __syncthreads();
     uint32_t tile_total = 0, warp_base = 0;
     bool any_over = false;
@@ -424,9 +493,7 @@ k_scan_map(const ScanMapArgs a, const IndexView ix, const LinkView lv) {
         if (threadIdx.x == 0) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_TILE_FULL);
         return;
     }
-    for (uint32_t i = threadIdx.x; i < n_local; i += blockDim.x) s_re[i] = 0xFFFFFFFFu;
     if (chunk_starts_in_seq && threadIdx.x == 0) s_rs[0] = (uint32_t)a.head;   // buffer position 0, tile-relative
-    __syncthreads();
     // ---- emission: every queue entry knows its rank -> line numbers -> read table ---------------
     for (uint32_t i = lane; i < qn; i += 32) {
         uint32_t mask = q_mk[i] & 0xFFFFu;
@@ -450,136 +517,104 @@ k_scan_map(const ScanMapArgs a, const IndexView ix, const LinkView lv) {
             line++;
         }
     }
-    __syncthreads();                                                   // the queues are dead from here on: s_un holds rows
-    if (threadIdx.x == 0 && n_local) atomicAdd(&a.counters[CNT_FAST], (unsigned long long)n_local);
+    __syncthreads();
     const uint64_t r_loc0 = r_own0 - shift;                            // record number of local index 0
-    const uint32_t L = ix.split_len;
-    constexpr uint32_t LPRP = STRIDE > 19 ? 16u : 8u;                  // lanes per read in the pack step
-    constexpr uint32_t gpw = 32 / LPRP;                                // reads per warp step
-    const uint32_t grp = lane / LPRP, gl = lane % LPRP;
-    const uint32_t gmask = (LPRP == 16 ? 0xFFFFu : 0xFFu) << (grp * LPRP);
-    for (uint32_t base_li = 0; base_li < n_local; base_li += SM_RPR) {
-        const uint32_t n_round = min((uint32_t)SM_RPR, n_local - base_li);
-        // ---- pack: LPRP lanes per read, 32 bases (two 32-bit words) per lane -> s_rows --------------
-        for (uint32_t j0 = wib * gpw; j0 < n_round; j0 += SM_WARPS * gpw) {
-            const uint32_t jr = j0 + grp;                               // read of the round
-            const uint32_t li = base_li + jr;
-            const bool live = jr < n_round;
-            const uint32_t st = live ? s_rs[li] : 0;
-            uint32_t en = live ? s_re[li] : 0;
-            uint32_t flags = 0;
-            if (__any_sync(0xFFFFFFFFu, live && en == 0xFFFFFFFFu)) {
-                // some line ends beyond the tile: first '\n' or '\r' in the back margin, if any
-                for (uint32_t g = 0; g < gpw; g++) {
-                    const uint32_t en_g = __shfl_sync(0xFFFFFFFFu, en, g * LPRP);
-                    const bool live_g = __shfl_sync(0xFFFFFFFFu, (uint32_t)live, g * LPRP) != 0;
-                    if (!live_g || en_g != 0xFFFFFFFFu) continue;
-                    uint32_t found = 0xFFFFFFFFu;
-                    for (uint32_t k = 0; k < (uint32_t)SM_BACK && found == 0xFFFFFFFFu; k += 32) {
-                        const uint32_t j = SM_TILE + k + lane;
-                        const uint32_t ch = tb[j];
-                        const bool hit = (pos0 + j < nn) && (ch == '\n' || ch == '\r');
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-                        if (m) found = SM_TILE + k + (uint32_t)(__ffs((int)m) - 1);
-                    }
-                    if (grp == g) en = found;
+    // ---- pack: one thread per read, the row goes from registers to HBM with 16-byte stores -- no block
+    // barrier from here on.  16 bases = four words per step: code = (ascii >> 1) & 3; the only byte with
+    // code k is "ACTG"[k] = 0x41 + 2k (+15 when k == 2), which is the validity test.
+    constexpr int NW = RW == 12 ? 10 : RW;                             // row words that can hold bases (cap / 16)
+    for (uint32_t li = threadIdx.x; li < n_local; li += SM_THREADS) {
+        const uint64_t slot = r_loc0 + li - a.rec_first;
+        if (slot >= a.n_slots) { atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_SLOTS_FULL); continue; }
+        const uint32_t st = s_rs[li];
+        uint32_t en = s_re[li];
+        uint32_t h = 0;
+        if (en == 0xFFFFFFFFu) {
+            // the line ends beyond the tile: first '\n' or '\r' in the back margin, if any (four bytes per step:
+            // only a word with a byte < 0x10 is looked at byte by byte)
+            for (uint32_t j = SM_TILE; j < (uint32_t)(SM_TILE + SM_BACK) && en == 0xFFFFFFFFu; j += 4) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(tb + j);
+                if (!(((w - 0x10101010u) | w) & 0x80808080u) && pos0 + (int64_t)j + 4 <= nn) continue;
+                for (uint32_t k = 0; k < 4 && pos0 + (int64_t)(j + k) < nn; k++) {
+                    const uint32_t ch = (w >> (8 * k)) & 0xFF;
+                    if (ch == '\n' || ch == '\r') { en = j + k; break; }
                 }
-                if (live && en == 0xFFFFFFFFu) flags |= PH_LONG;
-                if (live && gl == 0) s_re[li] = en;                     // the walk step reports the resolved end
+                if (pos0 + (int64_t)j + 4 > nn) break;
             }
-            uint32_t rlen = (!live || (flags & PH_LONG)) ? 0u : en - st;
-            if (rlen > a.cap) { flags |= PH_LONG; rlen = 0; }
+            if (en == 0xFFFFFFFFu) h |= PH_LONG;
+        }
+        uint32_t rlen = (h & PH_LONG) ? 0u : en - st;
+        if (rlen > a.cap) { h |= PH_LONG; rlen = 0; }
+        const uint32_t a0 = SM_FRONT + st;                              // offset of the first base in s_bytes
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(s_bytes + (a0 & ~3u));
+        const uint32_t sh = (a0 & 3) * 8;
+        uint32_t carry = p[0], diff = 0;
+        uint32_t rw[RW];
+#pragma unroll
+        for (int v = 0; v < RW; v++) {
+            uint32_t word = 0;
+            if (v < NW && 16u * v < rlen) {
+                uint32_t x[5];
+                x[0] = carry;
+#pragma unroll
+                for (int q = 1; q < 5; q++) x[q] = p[4 * v + q];
+                carry = x[4];
+                const uint32_t rem = rlen - 16u * v;                    // bases left, >= 1
+                if (rem >= 16) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
+                        const uint32_t c2 = (c >> 1) & 0x03030303u;
+                        const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
+                        diff |= expect ^ c;
+                        word |= ((c2 * 0x01041040u) >> 24) << (8 * q);
+                    }
+                } else {                                                // the read ends inside this step: mask the bytes beyond it
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
+                        const uint32_t vm = rem >= 4u * q + 4 ? 0xFFFFFFFFu : rem <= 4u * q ? 0u : (0xFFFFFFFFu >> (8 * (4u * q + 4 - rem)));
+                        const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
+                        const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
+                        diff |= (expect ^ c) & vm;
+                        word |= ((c2 * 0x01041040u) >> 24) << (8 * q);
+                    }
+                }
+            }
+            rw[v] = word;
+        }
+        if (diff) {
+            // rare: some byte is not ACGT -- 'N' (pair skipped, PE_Inference.py:160) or anything else (exhaustive tier), word by word
             bool hasN = false, badc = false;
-            const uint32_t b0 = 32 * gl;
-            uint32_t w0 = 0, w1 = 0;
-            if (b0 < rlen) {
-                const uint32_t nb = min(32u, rlen - b0);
-                const uint32_t jb = SM_FRONT + st + b0;                     // offset in s_bytes (16-byte aligned base)
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(s_bytes + (jb & ~3u));
-                const uint32_t sh = (jb & 3) * 8;
-                uint32_t x[9];
-#pragma unroll
-                for (int q = 0; q < 9; q++) x[q] = p[q];
-                uint32_t diff = 0;
-                uint32_t pk[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
-                    // mask of the valid bytes of this word: 4 + 4q - nb of its top bytes lie beyond the lane's bases
-                    const uint32_t vm = __funnelshift_rc(0xFFFFFFFFu, 0u, 8u * (uint32_t)max(4 + 4 * q - (int)nb, 0));
-                    const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
-                    // the only byte with code k is "ACTG"[k] = 0x41 + 2k (+15 when k == 2)
-                    const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
-                    diff |= (expect ^ c) & vm;
-                    pk[q] = (c2 * 0x01041040u) >> 24;
-                }
-                w0 = pk[0] | (pk[1] << 8) | (pk[2] << 16) | (pk[3] << 24);
-                w1 = pk[4] | (pk[5] << 8) | (pk[6] << 16) | (pk[7] << 24);
-                if (diff) {                                                 // rare: some byte is not ACGT
-                    for (uint32_t q = 0; q < nb; q++) {
-                        const uint32_t c = s_bytes[jb + q];
-                        if (c == 'N') hasN = true;
-                        else if (!is_acgt(c)) badc = true;
-                    }
+            uint32_t cy = p[0];
+            for (uint32_t v4 = 0; 4 * v4 < rlen; v4++) {
+                const uint32_t nx = p[v4 + 1];
+                const uint32_t c = __funnelshift_r(cy, nx, sh);
+                cy = nx;
+                const uint32_t left = rlen - 4 * v4;
+                const uint32_t vm = left >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - left)));
+                const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
+                const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
+                uint32_t bad = (expect ^ c) & vm;                       // non-zero bytes = invalid characters
+                if (bad) {
+                    for (int k = 0; k < 4; k++)
+                        if ((bad >> (8 * k)) & 0xFF) { if (((c >> (8 * k)) & 0xFF) == 'N') hasN = true; else badc = true; }
                 }
             }
-            if (live) {
-                uint32_t* row = s_rows + jr * STRIDE;
-                if (2 * gl < (uint32_t)STRIDE) row[2 * gl] = w0;
-                if (2 * gl + 1 < (uint32_t)STRIDE) row[2 * gl + 1] = w1;
-                if (2 * LPRP < (uint32_t)STRIDE && 2 * LPRP + gl < (uint32_t)STRIDE) row[2 * LPRP + gl] = 0;
-            }
-            const uint32_t bN = __ballot_sync(0xFFFFFFFFu, hasN) & gmask, bB = __ballot_sync(0xFFFFFFFFu, badc) & gmask;
-            if (live && gl == 0) s_rhdr[jr] = rlen | flags | (bN ? PH_N : 0) | (bB ? PH_BAD : 0);
+            h |= (hasN ? PH_N : 0) | (badc ? PH_BAD : 0);
         }
-        __syncthreads();
-        // ---- walk: one thread per read of the round ---------------------------------------------------
-        if (threadIdx.x < n_round) {
-            const uint32_t jr = threadIdx.x, li = base_li + jr;
-            const uint64_t slot = r_loc0 + li - a.rec_first;
-            if (slot < a.n_slots) {
-                const uint32_t h = s_rhdr[jr];
-                const uint32_t rlen = h & 0xFFFFFF;
-                uint32_t* row = s_rows + jr * STRIDE;
-                uint32_t handle = H_PENDING;
-                bool defer = (h & (PH_LONG | PH_BAD)) != 0;
-                if (!(h & PH_LONG)) {
-                    if (h & PH_N) handle = H_N;                            // 'N' before the length (PE_Inference.py:160-163)
-                    else if (rlen < L) handle = H_SHORT;
-                }
-                if (handle == H_PENDING && !defer) {
-                    uint32_t n_kept = 0;
-                    if (walk_read<STRIDE>(ix, row, rlen, s_lst + jr, n_kept)) handle = intern_list(lv, n_kept, s_lst + jr, SM_RPR);
-                    else defer = true;
-                }
-                if (handle == H_PENDING && defer) {
-                    // unresolved: the packed row, its header and the byte range go to the list-driven tiers
-                    uint4* dst = reinterpret_cast<uint4*>(a.rows + slot * a.row_words);
-                    for (uint32_t w = 0; w < a.row_words; w += 4) {
-                        uint4 v;
-                        v.x = w < (uint32_t)STRIDE ? row[w] : 0u;
-                        v.y = w + 1 < (uint32_t)STRIDE ? row[w + 1] : 0u;
-                        v.z = w + 2 < (uint32_t)STRIDE ? row[w + 2] : 0u;
-                        v.w = w + 3 < (uint32_t)STRIDE ? row[w + 3] : 0u;
-                        dst[w >> 2] = v;
-                    }
-                    a.hdr[slot] = h;
-                    const uint32_t st = s_rs[li], en = s_re[li];
-                    a.seq_start[slot] = (uint64_t)((int64_t)st + pos0);    // chunk-relative start
-                    a.seq_end[slot] = en == 0xFFFFFFFFu ? ~0ull : (uint64_t)((int64_t)en + pos0);
-                    a.defer_list[atomicAdd(&a.counters[CNT_DEFER], 1ull)] = (uint32_t)slot;
-                }
-                a.handles[slot] = handle;
-            } else if (li < n_local) {
-                atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_SLOTS_FULL);
-            }
-        }
-        __syncthreads();                                               // the rows are reused by the next round
+        h |= rlen;
+        uint4* dst = reinterpret_cast<uint4*>(a.rows + slot * RW);
+#pragma unroll
+        for (int v = 0; v < RW; v += 4) dst[v >> 2] = make_uint4(rw[v], rw[v + 1], rw[v + 2], rw[v + 3]);
+        a.hdr[slot] = h;
+        a.seq_start[slot] = (uint64_t)((int64_t)st + pos0);            // chunk-relative start
+        a.seq_end[slot] = en == 0xFFFFFFFFu ? ~0ull : (uint64_t)((int64_t)en + pos0);
     }
 }
 
-// One launch over a device-resident chunk.  Returns the terminator count and the kernels' error flags
-// (transient *_FULL scan flags are cleared on the device; the caller repeats or falls back).
+// Both kernels over a device-resident chunk: k_scan_rows, then k_walk over up to n_slots reads (the walk
+// kernel reads the chunk's terminator count on the device, so no host synchronisation in between).
 int scan_map(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots, uint32_t* d_handles,
              uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t* d_defer_list, uint32_t row_words,
              uint32_t cap) {
@@ -595,27 +630,37 @@ int scan_map(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint6
     a.buf = d_buf; a.n = n; a.head = head; a.n_tiles = (uint32_t)n_tiles; a.status = status;
     a.ticket = reinterpret_cast<unsigned int*>(status + n_tiles + 1);
     a.total_out = status + n_tiles + 2;
-    a.line_base = line_base; a.rec_first = rec_first; a.n_slots = n_slots; a.handles = d_handles;
-    a.seq_start = d_seq_start; a.seq_end = d_seq_end; a.rows = d_rows; a.hdr = d_hdr; a.defer_list = d_defer_list;
+    a.line_base = line_base; a.rec_first = rec_first; a.n_slots = n_slots;
+    a.seq_start = d_seq_start; a.seq_end = d_seq_end; a.rows = d_rows; a.hdr = d_hdr;
     a.row_words = row_words; a.cap = cap; a.counters = c->counters.p;
     if (!c->scan_map_attr_set) {
-        VSPE_CUDA(cudaFuncSetAttribute(k_scan_map<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanMapSmem<13>::TOTAL));
-        VSPE_CUDA(cudaFuncSetAttribute(k_scan_map<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanMapSmem<19>::TOTAL));
-        VSPE_CUDA(cudaFuncSetAttribute(k_scan_map<23>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanMapSmem<23>::TOTAL));
-        for (auto& e : c->ev_scan[0]) if (!e) VSPE_CUDA(cudaEventCreate(&e));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_rows<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_rows<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+        for (auto& evs : c->ev_scan) for (auto& e : evs) if (!e) VSPE_CUDA(cudaEventCreate(&e));
         c->scan_map_attr_set = true;
     }
+    // both kernels are timed on their own (CUDA events on the launching stream; two launches may be in flight)
+    const int k = c->scan_map_events & 1;
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[0][2 * k], c->stream));
+    if (row_words == 12) k_scan_rows<12><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    else if (row_words == 16) k_scan_rows<16><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    else k_scan_rows<20><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    VSPE_LAUNCH_CHECK(c);
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[0][2 * k + 1], c->stream));
+    WalkArgs w;
+    w.rows = d_rows; w.hdr = d_hdr; w.row_words = row_words; w.n_slots = n_slots; w.total = a.total_out;
+    w.line_base = line_base; w.rec_first = rec_first; w.handles = d_handles; w.defer_list = d_defer_list; w.counters = c->counters.p;
     const IndexView ix = c->index.view();
     const LinkView lv = link_view(c);
-    // the dominant kernel is timed on its own (CUDA events on the launching stream)
-    cudaEvent_t e0 = c->ev_scan[0][c->scan_map_events & 1 ? 2 : 0], e1 = c->ev_scan[0][c->scan_map_events & 1 ? 3 : 1];
-    VSPE_CUDA(cudaEventRecord(e0, c->stream));
-    if (cap <= 160) k_scan_map<13><<<(uint32_t)n_tiles, SM_THREADS, ScanMapSmem<13>::TOTAL, c->stream>>>(a, ix, lv);
-    else if (cap <= 256) k_scan_map<19><<<(uint32_t)n_tiles, SM_THREADS, ScanMapSmem<19>::TOTAL, c->stream>>>(a, ix, lv);
-    else k_scan_map<23><<<(uint32_t)n_tiles, SM_THREADS, ScanMapSmem<23>::TOTAL, c->stream>>>(a, ix, lv);
+    const uint32_t grid = (uint32_t)((n_slots + WK_THREADS - 1) / WK_THREADS);
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[1][2 * k], c->stream));
+    if (cap <= 160) k_walk<13><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
+    else if (cap <= 256) k_walk<19><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
+    else k_walk<23><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
     VSPE_LAUNCH_CHECK(c);
-    VSPE_CUDA(cudaEventRecord(e1, c->stream));
-    c->scan_map_pending[c->scan_map_events & 1] = true;
+    VSPE_CUDA(cudaEventRecord(c->ev_scan[1][2 * k + 1], c->stream));
+    c->scan_map_pending[k] = true;
     c->scan_map_events++;
     return VSPE_OK;
 }
@@ -627,17 +672,15 @@ const unsigned long long* scan_map_total_ptr(Ctx* c, uint64_t n, const uint8_t* 
     return reinterpret_cast<unsigned long long*>(c->tile_base.p) + n_tiles + 2;
 }
 
-// fold the durations of the finished k_scan_map launches into the stats (call after a stream sync)
+// fold the durations of the finished k_scan_rows / k_walk launches into the stats (call after a stream sync)
 void scan_map_account(Ctx* c) {
     for (int k = 0; k < 2; k++) {
         if (!c->scan_map_pending[k]) continue;
-        cudaEvent_t e0 = c->ev_scan[0][k ? 2 : 0], e1 = c->ev_scan[0][k ? 3 : 1];
         float ms = 0;
-        if (cudaEventQuery(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) {
-            c->stats.ms_k_scan_pack += ms;
-            c->stats.n_k_scan_pack++;
-            c->scan_map_pending[k] = false;
-        }
+        if (cudaEventQuery(c->ev_scan[1][2 * k + 1]) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&ms, c->ev_scan[0][2 * k], c->ev_scan[0][2 * k + 1]) == cudaSuccess) { c->stats.ms_k_scan_rows += ms; c->stats.n_k_scan_rows++; }
+        if (cudaEventElapsedTime(&ms, c->ev_scan[1][2 * k], c->ev_scan[1][2 * k + 1]) == cudaSuccess) { c->stats.ms_k_walk += ms; c->stats.n_k_walk++; }
+        c->scan_map_pending[k] = false;
     }
     cudaGetLastError();
 }

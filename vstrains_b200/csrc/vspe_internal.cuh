@@ -57,9 +57,12 @@ struct IndexView {
     const uint64_t* text;
     const uint32_t* strand_start;   // [2N+1]
     const uint32_t* node_len;       // [N] full node length (also for nodes without k-mers)
+    const uint4* node_rec;          // [N] {strand_start[2n], [2n+1], [2n+2], node_len[n]}: everything a walk needs to enter a node
     const uint2* slots;
     const uint32_t* uniq;           // bitmap over text positions
     const uint32_t* succ;           // [2N][4] {text position, node} of the unique successor k-mer or {NONE32, 0}
+    const uint4* succ16;            // [2N][4] the same successor with what a walk needs to enter it: {text position, strand,
+                                    // strand end, node length} or {NONE32, 0, 0, 0}
     const uint32_t* subst;          // 4 bits per text base (or nullptr): bit b set iff some window of the strand that
                                     // covers the base, with the base replaced by code b, has a posting
     uint32_t text_len;              // bases
@@ -222,9 +225,11 @@ struct Index {
     DevBuf<uint64_t> text;
     DevBuf<uint32_t> strand_start;
     DevBuf<uint32_t> node_len;
+    DevBuf<uint4> node_rec;
     DevBuf<uint2> slots;
     DevBuf<uint32_t> uniq;
     DevBuf<uint32_t> succ;
+    DevBuf<uint4> succ16;
     DevBuf<uint32_t> subst;
     bool has_subst = false;
     uint32_t text_len = 0, slot_mask = 0, node_mask = 0, split_len = 0, n_nodes = 0;
@@ -232,8 +237,8 @@ struct Index {
     bool built = false;
     IndexView view() const {
         IndexView v;
-        v.text = text.p; v.strand_start = strand_start.p; v.node_len = node_len.p;
-        v.slots = slots.p; v.uniq = uniq.p; v.succ = succ.p; v.subst = has_subst ? subst.p : nullptr;
+        v.text = text.p; v.strand_start = strand_start.p; v.node_len = node_len.p; v.node_rec = node_rec.p;
+        v.slots = slots.p; v.uniq = uniq.p; v.succ = succ.p; v.succ16 = succ16.p; v.subst = has_subst ? subst.p : nullptr;
         v.text_len = text_len; v.slot_mask = slot_mask; v.node_mask = node_mask;
         v.split_len = split_len; v.n_nodes = n_nodes;
         return v;
@@ -244,7 +249,7 @@ struct Index {
 struct Records {
     DevBuf<uint64_t> seq_start;   // chunk-relative byte offset of the 2nd line of each record
     DevBuf<uint64_t> seq_end;     // one past its last content byte (~0: beyond the scan margin)
-    DevBuf<uint32_t> rows;        // [n][row_words] 2-bit packed reads written by k_scan_pack
+    DevBuf<uint32_t> rows;        // [n][row_words] 2-bit packed reads written by k_scan_rows
     DevBuf<uint32_t> hdr;         // [n] rlen | flags << 24
 };
 static constexpr uint32_t PH_N = 1u << 24, PH_BAD = 2u << 24, PH_LONG = 4u << 24;
@@ -262,15 +267,6 @@ int scan_index_records(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_b
 int scan_records_single_pass(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first,
                              uint64_t n_slots, uint64_t* d_seq_start, uint64_t* d_seq_end, uint64_t* n_terms, bool* overflow);
 
-int scan_pack(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
-              uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-              uint64_t* n_terms, unsigned long long* err_flags);
-
-int scan_pack_prepare_launch(Ctx* c, int mate, const uint8_t* d_buf, uint64_t n);
-int scan_pack_prepare_collect(Ctx* c, int mate, const uint8_t* d_buf, uint64_t n, uint64_t* n_terms, unsigned long long* err_flags);
-int scan_pack_finish(Ctx* c, int mate, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots,
-                     uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t row_words, uint32_t cap);
-void scan_pack_account(Ctx* c);
 int device_scan_u64(Ctx* c, const unsigned long long* in, unsigned long long* out, uint64_t n, unsigned long long* sums,
                     unsigned long long* total);
 
@@ -285,8 +281,6 @@ void scan_map_account(Ctx* c);
 int map_reads_generic(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                       uint64_t n_reads, ReadSlot* d_slots);
 
-// after a stream sync: choose the lean / general walk kernels for the next map launch
-int adapt_map_variant(Ctx* c);
 
 int sparse_merge_host(Ctx* c, const uint64_t* keys, const uint64_t* counts, uint64_t n);
 int sparse_merge_device(Ctx* c, const uint64_t* d_keys, const uint64_t* d_counts, uint64_t n);
