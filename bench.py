@@ -50,11 +50,26 @@ def peaks():
 
 
 def make_graph(cfg_name: str, pairs: int):
-    """Graph + strain genomes of a config (identical on every rank)."""
+    """Graph + strain genomes of a config (identical on every rank).  Under torchrun the multi-genome stress
+    graph is built once, by local rank 0, and handed to the other ranks through /dev/shm."""
+    import pickle
     cfg = synth.CONFIGS[cfg_name]
-    rng = np.random.default_rng(cfg.seed)
     depth = pairs * 2.0 * cfg.read_len / cfg.genome_len / max(cfg.n_genomes, 1)
-    g, genomes, ab = synth.make_graph(cfg, rng, depth)
+    world, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    share = world > 1 and cfg.n_genomes > 1
+    path = "/dev/shm/vspe_graph_%s_%d_%s.pkl" % (cfg_name, pairs, os.environ.get("MASTER_PORT", "0"))
+    if share and local != 0:
+        t0 = time.time()
+        while not os.path.exists(path + ".done") and time.time() - t0 < 900:
+            time.sleep(0.5)
+        with open(path, "rb") as fh:
+            g, genomes, ab = pickle.load(fh)
+        return cfg, g, genomes, ab
+    g, genomes, ab = synth.make_graph(cfg, np.random.default_rng(cfg.seed), depth)
+    if share:
+        with open(path, "wb") as fh:
+            pickle.dump((g, genomes, ab), fh, protocol=4)
+        open(path + ".done", "w").close()
     return cfg, g, genomes, ab
 
 
@@ -274,6 +289,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="pairs of the resident block per GPU (default: per config)")
     ap.add_argument("--replay", type=int, default=0, help="block passes per step (default: config pairs / block pairs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="experiments: skip the end-to-end leg")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (experiments)")
     args = ap.parse_args()
 
@@ -376,26 +392,27 @@ def main():
     lib_stream = torch.cuda.ExternalStream(ix.stream(), device=dev)
 
     def merge_sparse():
-        """One exchange step: all-gather of the run counts, all-gather of the (padded) runs, then every
-        rank merges the other ranks' runs on its device (sort + run-length reduce)."""
+        """One exchange step over NVLink: the key space is cut into `world` equal ranges; every rank sends the
+        runs of range r to rank r (all-to-all of the counts, then of keys and values) and merges what it
+        received (sort + run-length reduce).  The merged run list stays distributed by key range; the work per
+        rank does not grow with the number of ranks."""
         n_own, kptr, cptr = ix.sparse_device()
-        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-        own = torch.tensor([n_own], dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(sizes, own)
-        sz = [int(x) for x in sizes.tolist()]
-        cap_ = max(max(sz), 1)
-        buf = torch.zeros(2 * cap_, dtype=torch.int64, device=dev)
-        if n_own:
-            buf[:n_own] = torch.as_tensor(_Arr(kptr, n_own), device=dev)
-            buf[cap_: cap_ + n_own] = torch.as_tensor(_Arr(cptr, n_own), device=dev)
-        allb = torch.empty(world * 2 * cap_, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allb, buf)
+        keys_t = torch.as_tensor(_Arr(kptr, n_own), device=dev) if n_own else torch.zeros(0, dtype=torch.int64, device=dev)
+        vals_t = torch.as_tensor(_Arr(cptr, n_own), device=dev) if n_own else torch.zeros(0, dtype=torch.int64, device=dev)
+        cells = 2 * n_nodes * n_nodes
+        bounds = torch.tensor([cells * (q + 1) // world for q in range(world)], dtype=torch.int64, device=dev)
+        ends = torch.searchsorted(keys_t, bounds, right=False)             # the runs are sorted by key
+        send = torch.diff(ends, prepend=torch.zeros(1, dtype=torch.int64, device=dev))
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        s_list, r_list = [int(x) for x in send.tolist()], [int(x) for x in recv.tolist()]
+        rk = torch.empty(sum(r_list), dtype=torch.int64, device=dev)
+        rv = torch.empty(sum(r_list), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(rk, keys_t.clone(), r_list, s_list)
+        dist.all_to_all_single(rv, vals_t.clone(), r_list, s_list)
         torch.cuda.current_stream().synchronize()
-        for src in range(world):
-            if src == rank or sz[src] == 0:
-                continue
-            base = src * 2 * cap_
-            ix.sparse_merge_device(allb[base: base + sz[src]].data_ptr(), allb[base + cap_: base + cap_ + sz[src]].data_ptr(), sz[src])
+        ix.sparse_clear()
+        ix.sparse_merge_device(rk.data_ptr(), rv.data_ptr(), int(rk.numel()))
 
     d_f = torch.empty(f.size, dtype=torch.uint8, device=dev)
     d_r = torch.empty(r.size, dtype=torch.uint8, device=dev)
@@ -480,8 +497,11 @@ def main():
         msum = int(mats.sum().item())
         check = {"matrix_sum": msum, "n_keys_all_ranks": kt[0], "equal": msum == kt[0]}
     else:
-        keys_, counts_ = ix.sparse()
-        check = {"run_sum": int(counts_.sum()), "n_keys_all_ranks": kt[0], "equal": int(counts_.sum()) == kt[0], "runs": int(keys_.size)}
+        keys_, counts_ = ix.sparse()                    # (N > 1: this rank's key range of the merged runs)
+        rs = torch.tensor([int(counts_.sum()), int(keys_.size)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(rs)
+        check = {"run_sum": int(rs[0].item()), "n_keys_all_ranks": kt[0], "equal": int(rs[0].item()) == kt[0], "runs": int(rs[1].item())}
     assert check["equal"], "merged counts != link keys counted on all ranks: %r" % (check,)
     assert kt[2] == kt[1] + kt[3] + kt[4], "total != used + N + short"
 
@@ -515,14 +535,14 @@ def main():
     except Exception:
         pass
 
-    step_e2e()
+    out = step_e2e()
     barrier()
-    e2e_steps = max(2, min(args.steps, 3))
+    e2e_steps = 1 if args.no_e2e else max(2, min(args.steps, 3))
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(0 if args.no_e2e else e2e_steps):
         out = step_e2e()
     barrier()
-    dt = time.perf_counter() - t0
+    dt = max(time.perf_counter() - t0, 1e-9)
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -143,6 +143,9 @@ int vspe_write_info_sparse(const char* path, const char* const* ids, uint32_t n,
  * exchange the runs with ONE all-gather over NVLink instead of a host round trip. */
 int vspe_sparse_device(vspe_ctx* ctx, uint64_t* n_entries, uint64_t** d_keys, uint64_t** d_counts);
 int vspe_sparse_merge_device(vspe_ctx* ctx, const uint64_t* d_keys, const uint64_t* d_counts, uint64_t n_entries);
+/* Forget the context's runs (the counters stay): a rank that hands its runs to their key-range owners in an
+ * all-to-all exchange clears its list and merges what it received. */
+int vspe_sparse_clear(vspe_ctx* ctx);
 
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on.  Work a caller
  * enqueues on it (e.g. the NCCL allreduce of vspe_matrices_device) is ordered after the counting calls
@@ -171,6 +174,10 @@ void vspe_free_pinned(void* p);
  *   "scan_two_pass"  1: same as scan_mode 2
  *   "force_generic"  1: every read through the exhaustive ASCII tier (the reference's loop as is)
  *   "subst"          0: do not build / use the substitution-hit bitmap
+ *   "tier_overlap"   0: vspe_count_device maps the two mates strictly one after the other (default 1: the list-driven
+ *                    tiers of one mate run on a second stream beside the scan of the other)
+ *   "pair_cap_log2"  log2 of the first size of the pair table (default 21 = 32 MB, grown on demand); 0: size it by
+ *                    the pairs of a batch
  *   "dbg_counters"   profiling aid (tools/dbg_map.py) */
 int vspe_set_option(vspe_ctx* ctx, const char* name, int64_t value);
 

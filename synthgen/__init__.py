@@ -201,18 +201,42 @@ def build_dbg(strains: np.ndarray, k: int, weights: Optional[np.ndarray] = None,
     return seqs, cov, np.stack([u, v], axis=1).astype(np.int64) if u.size else np.zeros((0, 2), dtype=np.int64)
 
 
+def _one_genome(args):
+    cfg, g, depth = args
+    grng = np.random.default_rng([cfg.seed, 104729, g])
+    st = make_strains(cfg.genome_len, cfg.strains, cfg.divergence, grng)
+    seqs, cov, links = build_dbg(st, cfg.k, abundances(cfg.strains) * depth, seed=cfg.seed + g)
+    return st, seqs, cov, links
+
+
 def make_graph(cfg: Config, rng: np.random.Generator, depth: float = 1.0):
-    """Returns (Graph, list of strain arrays per genome, abundance per strain)."""
+    """Returns (Graph, list of strain arrays per genome, abundance per strain).  Multi-genome configs (the
+    200 000-node stress graph: 2 000 independent genomes) draw every genome from its own random stream, so
+    they can be built by a pool of worker processes."""
     all_seqs: List[bytes] = []
     all_cov: List[np.ndarray] = []
     all_links: List[np.ndarray] = []
     genomes = []
     ab = abundances(cfg.strains)
-    for g in range(cfg.n_genomes):
+    if cfg.n_genomes > 1:
+        jobs = [(cfg, g, depth) for g in range(cfg.n_genomes)]
+        n_proc = min(len(os.sched_getaffinity(0)), 32, cfg.n_genomes)
+        if n_proc > 1 and cfg.n_genomes >= 64:
+            import multiprocessing as mp
+            with mp.get_context("fork").Pool(n_proc) as pool:
+                parts = pool.map(_one_genome, jobs, chunksize=max(1, cfg.n_genomes // (4 * n_proc)))
+        else:
+            parts = [_one_genome(j) for j in jobs]
+        for st, seqs, cov, links in parts:
+            genomes.append(st)
+            all_links.append(links + len(all_seqs))
+            all_seqs.extend(seqs)
+            all_cov.append(cov)
+    else:
         st = make_strains(cfg.genome_len, cfg.strains, cfg.divergence, rng)
         genomes.append(st)
-        seqs, cov, links = build_dbg(st, cfg.k, ab * depth, seed=cfg.seed + g)
-        all_links.append(links + len(all_seqs))
+        seqs, cov, links = build_dbg(st, cfg.k, ab * depth, seed=cfg.seed)
+        all_links.append(links)
         all_seqs.extend(seqs)
         all_cov.append(cov)
     cov = np.concatenate(all_cov) if all_cov else np.zeros(0)

@@ -546,3 +546,76 @@ def test_many_long_node_lists_grow_the_pools():
     assert np.array_equal(short.astype(np.int64), oshort)
     for kk, v in ostats.items():
         assert stats[kk] == v
+
+
+@pytest.mark.skipif(not os.environ.get("VSPE_TEST_C5"), reason="opt-in (VSPE_TEST_C5=1): builds the 200 000-node graph and a C-oracle index over it")
+def test_c5_stress_graph_sparse_counts_match_oracle_on_a_subsample():
+    """BASELINE.json configs[4]: the 200 000-node stress graph (HBM-resident index, N*N matrices impossible: sparse
+    runs).  A 20 000-pair sub-sample is bit-exact against link counts built from the C oracle's per-read node
+    lists; 1 M pairs check the invariants (every key in the runs, the counters partition the pairs, two runs equal)."""
+    import bench
+    cfg, g, genomes, ab = bench.make_graph("C5", 1_000_000)
+    assert len(g.ids) == 200_000
+    f, r = bench.make_reads(cfg, genomes, ab, 1_000_000, 0)
+    gfa = g.to_gfa()
+    ids, seqs = pe_inference.parse_gfa_nodes(gfa)
+    n = len(ids)
+    sub = 20_000
+    fs, rs = bench.prefix_pairs(f, r, 0, sub, cfg.read_len)
+    with pe_inference.PEIndex(seqs, cfg.k) as ix:
+        assert ix.is_sparse
+        ix.count_host(fs, rs)
+        keys, counts = ix.sparse()
+        st = ix.stats()
+        ix.reset()
+        ix.count_host(f, r)
+        k1, c1 = ix.sparse()
+        st1 = ix.stats()
+        ix.reset()
+        ix.count_host(f, r)
+        k2, c2 = ix.sparse()
+    assert np.array_equal(k1, k2) and np.array_equal(c1, c2)
+    assert int(c1.sum()) == st1["n_keys"] and st1["total_pairs"] == 1_000_000 == st1["n_pairs"] + st1["short_pairs"] + st1["used_pairs"]
+    assert np.all(np.diff(k1.astype(np.int64)) > 0)
+    # oracle: per-read node lists of both mates -> the reference's accumulation loops (PE_Inference.py:160-188)
+    of, nf, sf = c_oracle.map_reads(gfa, fs, cfg.k)
+    orr, nr, sr = c_oracle.map_reads(gfa, rs, cfg.k)
+    exp = {}
+    used = n_skip = short_skip = 0
+    for p in range(sub):
+        if sf[p] == 1 or sr[p] == 1:
+            n_skip += 1
+            continue
+        if sf[p] == 2 or sr[p] == 2:
+            short_skip += 1
+            continue
+        used += 1
+        L = nf[of[p]:of[p + 1]].tolist()
+        R = nr[orr[p]:orr[p + 1]].tolist()
+        for lst in (L, R):
+            for a in range(len(lst)):
+                for b in range(a, len(lst)):
+                    kk = n * n + lst[a] * n + lst[b]
+                    exp[kk] = exp.get(kk, 0) + 1
+        for i in L:
+            for j in R:
+                kk = i * n + j
+                exp[kk] = exp.get(kk, 0) + 1
+    assert (st["used_pairs"], st["n_pairs"], st["short_pairs"]) == (used, n_skip, short_skip)
+    assert dict(zip(keys.tolist(), counts.tolist())) == exp
+
+
+def test_short_first_records_do_not_push_longer_reads_to_the_exhaustive_tier():
+    """the packed-row capacity is sized from samples across the input, not from its first lines only:
+    a file that starts with trimmed reads and continues with full-length ones still runs the packed tiers."""
+    cfg = synth.CONFIGS["C2"]
+    g, f, r = synth.generate(cfg, pairs=3000)
+    gfa = g.to_gfa()
+    short = _mk_fastq([b"ACGTACGTACGTACGTACGTAC"] * 40)
+    f2, r2 = short + f.tobytes(), short + r.tobytes()
+    ids, node, short_m, stats = pe_inference.pe_inference(gfa, f2, r2, cfg.k)
+    onode, oshort, ostats = c_oracle.run(gfa, f2, r2, cfg.k)
+    assert np.array_equal(node.astype(np.int64), onode) and np.array_equal(short_m.astype(np.int64), oshort)
+    assert stats["reads_generic"] == 0
+    for k, v in ostats.items():
+        assert stats[k] == v

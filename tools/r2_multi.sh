@@ -1,0 +1,6 @@
+# multi-GPU evidence: N>1 parity tests (CLI NCCL path dense + sparse, torchrun NCCL ranks) and the bench at N GPUs
+N=${1:-2}; O=gpurun_out/r2m$N; mkdir -p $O
+nvidia-smi topo -m > $O/topo.txt 2>&1
+(timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "torchrun or multi_gpu" 2>&1 | tail -15) > $O/tests.log 2>&1
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 bench.py --gpus $N --steps 5 --warmup 3 > $O/bench_c4_n$N.json 2> $O/bench_c4_n$N.err
+ls $O

@@ -75,6 +75,7 @@ def lib():
     L.vspe_sparse_merge.argtypes = [P, P, P, u64]
     L.vspe_sparse_device.argtypes = [P, ctypes.POINTER(u64), ctypes.POINTER(P), ctypes.POINTER(P)]
     L.vspe_sparse_merge_device.argtypes = [P, P, P, u64]
+    L.vspe_sparse_clear.argtypes = [P]
     L.vspe_stream.argtypes = [P]
     L.vspe_stream.restype = P
     L.vspe_write_info_sparse.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), u32, P, P, u64, i32]

@@ -10,6 +10,8 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "link.cuh"
@@ -32,7 +34,7 @@ int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, co
 int map_prepare_lists(Ctx* c, uint64_t n_reads);
 int map_reads_deferred(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                        const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                       uint64_t n_reads_cap, ReadSlot* d_slots);
+                       uint64_t n_reads_cap, ReadSlot* d_slots, const uint32_t* d_list, const unsigned long long* d_count);
 uint32_t map_fast_cap(uint32_t hint);
 int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len,
                   const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve, int n_gpus,
@@ -58,8 +60,6 @@ static int check_kernel_errors(Ctx* c) {
     return report_error_flags(e);
 }
 
-// One chunk of one mate's byte stream, resident on the device.  The chunk must start at a line
-// start and (unless it is the last chunk) end right after a terminator.
 static int scan_mode_of(Ctx* c) {
     // 0 (default): k_scan_rows + k_walk + list-driven tiers; 1: look-back record scan + raw-byte map kernels
     // (also the fallback of mode 0); 2: two-pass record scan + raw-byte map kernels (cross-check)
@@ -81,6 +81,50 @@ static int retry_after_pool_overflow(Ctx* c, unsigned long long flags, const uns
     return link_grow_overflow(c);
 }
 
+static inline uint64_t guess_reads(Ctx* c, uint64_t n) {
+    return n / (2ull * std::max<uint32_t>(c->read_len_hint, 20) + 8) * 21 / 20 + 4096;
+}
+
+// Queue the default path (scan_mode 0) for one chunk: k_scan_rows -> k_walk on the context's stream, then the
+// list-driven tiers on what the walk left unresolved and the interning of their slots -- on the same stream, or
+// (overlap) on the tier stream, so that they run beside the scan of the other mate.  Nothing is synchronised here.
+static int fused_launch(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t lb, uint64_t guess, bool overlap) {
+    MateBuf& mb = c->mate[m];
+    const uint64_t rec_first = seq_lines_before(lb);
+    const uint32_t cap = map_fast_cap(c->read_len_hint);
+    const uint32_t row_words = cap <= 160 ? 12 : cap <= 256 ? 16 : 20;
+    unsigned long long* d_count = c->counters.p + (m == 0 ? CNT_DEFER : CNT_DEFER1);
+    VSPE_TRY(mb.handles.reserve(rec_first + guess + 2, true, c->stream));
+    VSPE_TRY(mb.rec.seq_start.reserve(guess + 2));
+    VSPE_TRY(mb.rec.seq_end.reserve(guess + 2));
+    VSPE_TRY(mb.rec.hdr.reserve(guess + 2));
+    VSPE_TRY(mb.rec.rows.reserve((guess + 2) * row_words));
+    VSPE_TRY(mb.slots.reserve(guess + 2));                      // slots of the unresolved reads (chunk-local index)
+    VSPE_TRY(c->defer_m[m].reserve(guess + 2));
+    VSPE_CUDA(cudaMemsetAsync(d_count, 0, 8, c->stream));
+    VSPE_TRY(scan_map(c, m, d_buf, n, lb, rec_first, guess, mb.handles.p + rec_first, mb.rec.seq_start.p, mb.rec.seq_end.p,
+                      mb.rec.rows.p, mb.rec.hdr.p, c->defer_m[m].p, d_count, row_words, cap));
+    VSPE_CUDA(cudaEventRecord(c->ev_m[m][1], c->stream));
+    cudaStream_t main_stream = c->stream;
+    if (overlap) {
+        VSPE_CUDA(cudaEventRecord(c->ev_walk[m], main_stream));
+        VSPE_CUDA(cudaStreamWaitEvent(c->tier_stream, c->ev_walk[m], 0));
+        c->stream = c->tier_stream;                             // the tier launchers issue on the context's stream
+    }
+    c->cur_buf_n = n;
+    int rc = map_prepare_lists(c, guess + 2);
+    if (rc == VSPE_OK)
+        rc = map_reads_deferred(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p, row_words, cap, guess,
+                                mb.slots.p, c->defer_m[m].p, d_count);
+    if (rc == VSPE_OK) rc = intern_slots(c, mb.slots.p, guess, c->defer_m[m].p, d_count, mb.handles.p + rec_first);
+    if (rc == VSPE_OK && cudaEventRecord(c->ev_m[m][2], c->stream) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = VSPE_ERR_CUDA; }
+    if (overlap) {
+        if (rc == VSPE_OK && cudaEventRecord(c->ev_tier[m], c->tier_stream) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = VSPE_ERR_CUDA; }
+        c->stream = main_stream;
+    }
+    return rc;
+}
+
 // One chunk through the default path (scan_mode 0): k_scan_rows -> k_walk -> list-driven tiers on what the walk left
 // unresolved -> their slots interned -> one host sync (terminator count + error flags).  A launch whose
 // guessed table size was too small, or that ran out of list records / spill words, is repeated
@@ -88,32 +132,16 @@ static int retry_after_pool_overflow(Ctx* c, unsigned long long flags, const uns
 // (records of a few bytes): the caller takes the plain path for this chunk.
 static int feed_chunk_fused(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf, uint64_t n, bool* fell_back, uint64_t* n_terms_out,
                             uint64_t* n_seq_out) {
-    MateBuf& mb = c->mate[m];
     *fell_back = false;
     const uint64_t lb = ms.line_base, rec_first = seq_lines_before(lb);
-    const uint32_t cap = map_fast_cap(c->read_len_hint);
-    const uint32_t row_words = cap <= 160 ? 12 : cap <= 256 ? 16 : 20;
-    uint64_t guess = n / (2ull * std::max<uint32_t>(c->read_len_hint, 20) + 8) * 21 / 20 + 4096;
-    cudaEvent_t e0 = c->ev_m[m][0], e1 = c->ev_m[m][1], e2 = c->ev_m[m][2];
-    VSPE_CUDA(cudaEventRecord(e0, c->stream));
+    uint64_t guess = guess_reads(c, n);
+    VSPE_CUDA(cudaEventRecord(c->ev_m[m][0], c->stream));
     for (int attempt = 0;; attempt++) {
-        VSPE_TRY(mb.handles.reserve(rec_first + guess + 2, true, c->stream));
-        VSPE_TRY(mb.rec.seq_start.reserve(guess + 2));
-        VSPE_TRY(mb.rec.seq_end.reserve(guess + 2));
-        VSPE_TRY(mb.rec.hdr.reserve(guess + 2));
-        VSPE_TRY(mb.rec.rows.reserve((guess + 2) * row_words));
-        VSPE_TRY(mb.slots.reserve(guess + 2));                  // slots of the unresolved reads (chunk-local index)
-        VSPE_TRY(map_prepare_lists(c, guess + 2));
         unsigned long long cur0[2] = {0, 0}, h_total = 0, h_err = 0;
         VSPE_CUDA(cudaMemcpyAsync(&cur0[0], c->counters.p + CNT_SPILL_CURSOR, 8, cudaMemcpyDeviceToHost, c->stream));
         VSPE_CUDA(cudaMemcpyAsync(&cur0[1], c->counters.p + CNT_OVF, 8, cudaMemcpyDeviceToHost, c->stream));
-        VSPE_TRY(scan_map(c, d_buf, n, lb, rec_first, guess, mb.handles.p + rec_first, mb.rec.seq_start.p, mb.rec.seq_end.p,
-                          mb.rec.rows.p, mb.rec.hdr.p, c->defer_list.p, row_words, cap));
-        if (attempt == 0) VSPE_CUDA(cudaEventRecord(e1, c->stream));
-        VSPE_TRY(map_reads_deferred(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p, row_words, cap,
-                                    guess, mb.slots.p));
-        VSPE_TRY(intern_slots(c, mb.slots.p, guess, c->defer_list.p, c->counters.p + CNT_DEFER, mb.handles.p + rec_first));
-        VSPE_CUDA(cudaMemcpyAsync(&h_total, scan_map_total_ptr(c, n, d_buf), 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_TRY(fused_launch(c, m, d_buf, n, lb, guess, false));
+        VSPE_CUDA(cudaMemcpyAsync(&h_total, scan_map_total_ptr(c, m, n, d_buf), 8, cudaMemcpyDeviceToHost, c->stream));
         VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
         VSPE_CUDA(cudaStreamSynchronize(c->stream));
         scan_map_account(c);
@@ -134,7 +162,6 @@ static int feed_chunk_fused(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf,
         if (attempt < 8 && n_seq > guess) { guess = n_seq; continue; }          // the guessed table was too small
         break;
     }
-    VSPE_CUDA(cudaEventRecord(e2, c->stream));
     return VSPE_OK;
 }
 
@@ -293,22 +320,40 @@ static uint64_t cut_at_line(const uint8_t* p, uint64_t lo, uint64_t hi, uint64_t
     return lo;
 }
 
-// Longest 2nd-line length among the first records of a FASTQ prefix (sizes the packed rows of
-// the seed-and-extend tier; a wrong hint only sends longer reads to the exhaustive tier).
-static uint32_t seq_len_hint(const uint8_t* p, uint64_t n) {
+// Longest 2nd-line length among the records of a FASTQ sample (sizes the packed rows of the walk and
+// seed-and-extend tiers; a wrong hint only sends longer reads to the exhaustive tier).  `aligned`: the
+// sample starts at a line start, so line numbers are known; otherwise (a window from the middle of a
+// buffer) every line is a candidate except those that start with '@' or '+' -- an upper bound is all
+// that is needed.
+static uint32_t seq_len_hint(const uint8_t* p, uint64_t n, bool aligned = true) {
     uint64_t line = 0, start = 0, best = 0;
+    bool first = true;
     for (uint64_t i = 0; i < n && line < 64; i++) {
         uint8_t c = p[i];
         bool term = c == '\n' || (c == '\r' && !(i + 1 < n && p[i + 1] == '\n'));
         if (!term) continue;
-        if ((line & 3) == 1) {
+        const bool count = aligned ? (line & 3) == 1 : (!first && p[start] != '@' && p[start] != '+');
+        if (count) {
             uint64_t e = (c == '\n' && i > start && p[i - 1] == '\r') ? i - 1 : i;
             best = std::max(best, e - start);
         }
+        first = false;
         line++;
         start = i + 1;
     }
     return (uint32_t)std::min<uint64_t>(best, 1u << 20);
+}
+
+// the hint over a whole host buffer: its head plus windows at 1/4, 1/2, 3/4 and the tail, so that inputs whose
+// first records are short (adapter-trimmed reads) still get rows long enough for the rest
+static uint32_t seq_len_hint_sampled(const uint8_t* p, uint64_t n) {
+    const uint64_t W = 16384;
+    uint32_t best = seq_len_hint(p, std::min(n, W));
+    for (int q = 1; q <= 4 && n > 2 * W; q++) {
+        const uint64_t at = q == 4 ? n - W : n / 4 * q;
+        best = std::max(best, seq_len_hint(p + at, std::min(W, n - at), false));
+    }
+    return best;
 }
 
 static void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t n, unsigned max_threads) {
@@ -515,18 +560,140 @@ struct InputFile {
     std::vector<uint8_t> mem;
     const uint8_t* p = nullptr;
     uint64_t n = 0;
-    int open_ro(const char* path) {
-        VSPE_TRY(map.open_ro(path));
-        if (map.n >= 18 && map.p[0] == 0x1f && map.p[1] == 0x8b && map.p[2] == 8) {
-            VSPE_TRY(inflate_gzip(map.p, map.n, mem, path));
-            p = mem.data();
-            n = mem.size();
-        } else {
-            p = map.p;
-            n = map.n;
+    bool gz = false;          // map holds a gzip stream (p / n are only valid after inflate_all)
+    std::string path;
+    // inflate_now = false keeps a gzip file compressed: the single-GPU run streams it (GzipStream below)
+    int open_ro(const char* path_, bool inflate_now = true) {
+        path = path_;
+        VSPE_TRY(map.open_ro(path_));
+        gz = map.n >= 18 && map.p[0] == 0x1f && map.p[1] == 0x8b && map.p[2] == 8;
+        if (gz && inflate_now) return inflate_all();
+        if (!gz) { p = map.p; n = map.n; }
+        return VSPE_OK;
+    }
+    int inflate_all() {
+        VSPE_TRY(inflate_gzip(map.p, map.n, mem, path.c_str()));
+        p = mem.data();
+        n = mem.size();
+        return VSPE_OK;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// Streaming ingest of gzip inputs: one inflate thread per read file fills line-aligned
+// chunks in pinned host memory while the GPU works on the previous ones; the two files inflate side by
+// side and are fed alternately, so a C4-size .fastq.gz pair needs two chunks of host memory per file
+// instead of both files inflated in RAM.
+// ---------------------------------------------------------------------------------------
+struct GzipStream {
+    z_stream zs;
+    const uint8_t* src = nullptr;
+    uint64_t n = 0, in_pos = 0;
+    bool open = false, finished = false;
+    std::string path;
+    int begin(const uint8_t* p, uint64_t len, const char* path_) {
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, 15 + 16) != Z_OK) { set_error("zlib inflateInit2 failed"); return VSPE_ERR_IO; }
+        open = true; src = p; n = len; path = path_;
+        return VSPE_OK;
+    }
+    ~GzipStream() { if (open) inflateEnd(&zs); }
+    // up to cap bytes into dst; *got = 0 only at the end of the stream
+    int read(uint8_t* dst, uint64_t cap, uint64_t* got) {
+        *got = 0;
+        while (!finished && *got < cap) {
+            if (zs.avail_in == 0 && in_pos < n) {
+                const uint64_t part = std::min<uint64_t>(n - in_pos, 1u << 30);
+                zs.next_in = const_cast<Bytef*>(src + in_pos);
+                zs.avail_in = (uInt)part;
+                in_pos += part;
+            }
+            const uint64_t room = std::min<uint64_t>(cap - *got, 1u << 30);
+            zs.next_out = dst + *got;
+            zs.avail_out = (uInt)room;
+            const int z = inflate(&zs, Z_NO_FLUSH);
+            *got += room - zs.avail_out;
+            if (z == Z_STREAM_END) {
+                if ((uint64_t)zs.avail_in + (n - in_pos) == 0) { finished = true; break; }
+                if (inflateReset(&zs) != Z_OK) { set_error("zlib inflateReset failed on %s", path.c_str()); return VSPE_ERR_IO; }   // next member
+                continue;
+            }
+            if (z == Z_OK) continue;
+            if (z == Z_BUF_ERROR && zs.avail_in == 0 && in_pos == n) { set_error("%s: truncated gzip stream", path.c_str()); return VSPE_ERR_IO; }
+            if (z == Z_BUF_ERROR) continue;
+            set_error("%s: corrupt gzip stream (%s)", path.c_str(), zs.msg ? zs.msg : "zlib error");
+            return VSPE_ERR_IO;
         }
         return VSPE_OK;
     }
+};
+
+// Producer of line-aligned chunks of one inflating file: two pinned buffers, filled by its own thread.
+struct ChunkProducer {
+    GzipStream gz;
+    uint8_t* buf[2] = {nullptr, nullptr};
+    uint64_t cap = 0, len[2] = {0, 0};
+    bool last[2] = {false, false};
+    int state[2] = {0, 0};                 // 0 free, 1 filled
+    std::vector<uint8_t> carry;            // bytes after the last terminator of the previous chunk
+    std::mutex mu;
+    std::condition_variable cv;
+    std::thread th;
+    int rc = VSPE_OK;
+    std::string err;
+    bool stop = false;
+    ~ChunkProducer() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+        for (auto& b : buf) if (b) cudaFreeHost(b);
+    }
+    int start(const InputFile& in, uint64_t chunk) {
+        cap = chunk;
+        for (auto& b : buf) if (cudaMallocHost(&b, cap + 64) != cudaSuccess) { set_error("cudaMallocHost(%llu) failed", (unsigned long long)cap); return VSPE_ERR_CUDA; }
+        VSPE_TRY(gz.begin(in.map.p, in.map.n, in.path.c_str()));
+        th = std::thread([this] { run(); });
+        return VSPE_OK;
+    }
+    void run() {
+        int b = 0;
+        bool eof = false;
+        while (!eof) {
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[b] == 0 || stop; }); if (stop) return; }
+            uint64_t have = carry.size();
+            if (have > cap) { fail(VSPE_ERR_LIMIT, "a line of the gzip input is longer than the streaming chunk (raise chunk_mb)"); return; }
+            if (have) memcpy(buf[b], carry.data(), have);
+            carry.clear();
+            uint64_t got = 0;
+            const int r = gz.read(buf[b] + have, cap - have, &got);
+            if (r != VSPE_OK) { fail(r, get_error()); return; }
+            have += got;
+            eof = gz.finished || got == 0;
+            uint64_t cut = have;
+            if (!eof) {
+                // largest cut right after a terminator that cannot be the '\r' of a "\r\n" split by the chunk end
+                cut = have;
+                while (cut > 0) {
+                    const uint8_t ch = buf[b][cut - 1];
+                    if (ch == '\n') break;
+                    if (ch == '\r' && cut < have && buf[b][cut] != '\n') break;
+                    cut--;
+                }
+                if (cut == 0) { fail(VSPE_ERR_LIMIT, "a line of the gzip input is longer than the streaming chunk (raise chunk_mb)"); return; }
+                carry.assign(buf[b] + cut, buf[b] + have);
+            }
+            { std::lock_guard<std::mutex> lk(mu); len[b] = cut; last[b] = eof; state[b] = 1; }
+            cv.notify_all();
+            b ^= 1;
+        }
+    }
+    void fail(int code, const char* msg) {
+        { std::lock_guard<std::mutex> lk(mu); rc = code; err = msg; state[0] = state[1] = 1; len[0] = len[1] = 0; last[0] = last[1] = true; }
+        cv.notify_all();
+    }
+    // blocks until buffer b is filled
+    void wait_filled(int b) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[b] == 1; }); }
+    void release(int b) { { std::lock_guard<std::mutex> lk(mu); state[b] = 0; } cv.notify_all(); }
 };
 
 static inline char* put_u64(char* p, uint64_t v) {
@@ -569,11 +736,20 @@ int vspe_create(int device, vspe_ctx** out) {
     vspe_ctx* c = new vspe_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    VSPE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; b++) VSPE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream[b], cudaStreamNonBlocking));
-    for (auto& ev : c->ev) VSPE_CUDA(cudaEventCreate(&ev));
-    VSPE_TRY(c->counters.reserve(CNT_COUNT_));
-    VSPE_CUDA(cudaMemset(c->counters.p, 0, c->counters.cap * 8));
+    const int rc = [&]() -> int {
+        VSPE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) VSPE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream[b], cudaStreamNonBlocking));
+        VSPE_CUDA(cudaStreamCreateWithFlags(&c->tier_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            VSPE_CUDA(cudaEventCreateWithFlags(&c->ev_walk[b], cudaEventDisableTiming));
+            VSPE_CUDA(cudaEventCreateWithFlags(&c->ev_tier[b], cudaEventDisableTiming));
+        }
+        for (auto& ev : c->ev) VSPE_CUDA(cudaEventCreate(&ev));
+        VSPE_TRY(c->counters.reserve(CNT_COUNT_));
+        VSPE_CUDA(cudaMemset(c->counters.p, 0, c->counters.cap * 8));
+        return VSPE_OK;
+    }();
+    if (rc != VSPE_OK) { vspe_destroy(c); return rc; }         // nothing of a half-built context is leaked
     *out = c;
     return VSPE_OK;
 }
@@ -588,6 +764,9 @@ void vspe_destroy(vspe_ctx* c) {
     }
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& evs : c->ev_scan) for (auto& ev : evs) if (ev) cudaEventDestroy(ev);
+    for (auto& evs : c->ev_m) for (auto& ev : evs) if (ev) cudaEventDestroy(ev);
+    for (int b = 0; b < 2; b++) { if (c->ev_walk[b]) cudaEventDestroy(c->ev_walk[b]); if (c->ev_tier[b]) cudaEventDestroy(c->ev_tier[b]); }
+    if (c->tier_stream) cudaStreamDestroy(c->tier_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -655,7 +834,57 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
         }
     }
     c->read_len_hint = hint;
-    for (int m = 0; m < 2; m++) VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last[m], false));
+    // Default path, both mates non-empty: the two mates are queued back to back -- the list-driven tiers of the
+    // first one run on the tier stream beside the scan of the second one -- and collected with ONE host sync.
+    // Anything out of the ordinary (a guess that was too small, pools to grow, tiles with too many records)
+    // repeats the attempt or takes the serial per-mate path below.
+    bool done = false;
+    if (scan_mode_of(c) == 0 && ns[0] && ns[1] && c->opt_tier_overlap) {
+        uint64_t guess[2] = {guess_reads(c, ns[0]), guess_reads(c, ns[1])};
+        for (auto& e : c->ev_m) for (auto& ev : e) if (!ev) VSPE_CUDA(cudaEventCreate(&ev));
+        bool serial = false;
+        for (int attempt = 0; attempt < 8 && !done && !serial; attempt++) {
+            unsigned long long h_total[2] = {0, 0}, h_err = 0;
+            for (int m = 0; m < 2; m++) {
+                VSPE_CUDA(cudaEventRecord(c->ev_m[m][0], c->stream));
+                VSPE_TRY(fused_launch(c, m, bufs[m], ns[m], 0, guess[m], true));
+            }
+            for (int m = 0; m < 2; m++) {
+                VSPE_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tier[m], 0));
+                VSPE_CUDA(cudaMemcpyAsync(&h_total[m], scan_map_total_ptr(c, m, ns[m], bufs[m]), 8, cudaMemcpyDeviceToHost, c->stream));
+            }
+            VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
+            VSPE_CUDA(cudaStreamSynchronize(c->stream));
+            scan_map_account(c);
+            const unsigned long long redo = ERRF_SLOTS_FULL | ERRF_TILE_FULL | ERRF_LISTS_FULL | ERRF_SPILL_FULL;
+            if (h_err & redo) {
+                const unsigned long long cleared = h_err & ~redo;
+                const unsigned long long zero2[2] = {0, 0};
+                VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_ERR, &cleared, 8, cudaMemcpyHostToDevice, c->stream));
+                // the call started with empty pools (begin_call): a repeated attempt starts there again
+                VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_SPILL_CURSOR, &zero2[0], 8, cudaMemcpyHostToDevice, c->stream));
+                VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_OVF, &zero2[1], 8, cudaMemcpyHostToDevice, c->stream));
+                VSPE_CUDA(cudaStreamSynchronize(c->stream));
+            }
+            if (h_err & ERRF_TILE_FULL) { serial = true; break; }
+            bool again = false;
+            if (h_err & (ERRF_LISTS_FULL | ERRF_SPILL_FULL)) { VSPE_TRY(link_grow_overflow(c)); again = true; }
+            for (int m = 0; m < 2; m++) {
+                const uint64_t n_seq = seq_lines_before(h_total[m]);
+                if (n_seq > guess[m]) { guess[m] = n_seq; again = true; }
+            }
+            if (again) continue;
+            for (int m = 0; m < 2; m++) {
+                ms[m]->n_slots = seq_lines_before(h_total[m]);
+                ms[m]->line_base = h_total[m];
+                const bool term = last[m] == '\n' || last[m] == '\r';
+                ms[m]->lines = h_total[m] + (term ? 0 : 1);
+            }
+            done = true;
+        }
+    }
+    if (!done)
+        for (int m = 0; m < 2; m++) VSPE_TRY(feed_chunk(c, m, *ms[m], bufs[m], ns[m], true, last[m], false));
     VSPE_TRY(finish_pairs(c, f, r));
     VSPE_CUDA(cudaEventRecord(t1, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
@@ -683,7 +912,7 @@ int vspe_count_host(vspe_ctx* c, const uint8_t* fwd, uint64_t n_fwd, const uint8
     cudaEvent_t t0 = c->ev[7];
     VSPE_CUDA(cudaEventRecord(t0, c->stream));
     MateStream f, r;
-    c->read_len_hint = std::max(seq_len_hint(fwd, std::min<uint64_t>(n_fwd, 16384)), seq_len_hint(rve, std::min<uint64_t>(n_rve, 16384)));
+    c->read_len_hint = std::max(seq_len_hint_sampled(fwd, n_fwd), seq_len_hint_sampled(rve, n_rve));
     MateStream ms[2];
     const uint8_t* srcs[2] = {fwd, rve};
     const uint64_t ns[2] = {n_fwd, n_rve};
@@ -745,6 +974,13 @@ int vspe_sparse_merge_device(vspe_ctx* c, const uint64_t* d_keys, const uint64_t
     VSPE_TRY(require_index(c));
     if (!c->sparse.enabled) { set_error("this context counts densely"); return VSPE_ERR_ARG; }
     return sparse_merge_device(c, d_keys, d_counts, n_entries);
+}
+
+int vspe_sparse_clear(vspe_ctx* c) {
+    VSPE_TRY(require_index(c));
+    if (!c->sparse.enabled) { set_error("this context counts densely"); return VSPE_ERR_ARG; }
+    c->sparse.n_runs = 0;
+    return VSPE_OK;
 }
 
 void* vspe_stream(vspe_ctx* c) { return c ? reinterpret_cast<void*>(c->stream) : nullptr; }
@@ -878,7 +1114,7 @@ int vspe_map_reads(vspe_ctx* c, const uint8_t* fq, uint64_t n_bytes, uint64_t* n
     VSPE_TRY(require_index(c));
     begin_call(c);
     MateStream both[2];
-    c->read_len_hint = seq_len_hint(fq, std::min<uint64_t>(n_bytes, 16384));
+    c->read_len_hint = seq_len_hint_sampled(fq, n_bytes);
     {
         const uint8_t* srcs[2] = {fq, nullptr};
         const uint64_t ns[2] = {n_bytes, 0};
@@ -970,6 +1206,55 @@ int vspe_write_info(const char* path, const char* const* ids, uint32_t n, const 
     return rc;
 }
 
+// Both read files are gzip streams: count them chunk by chunk as they inflate (see ChunkProducer).
+static int count_gzip_streams(vspe_ctx* c, const InputFile& f, const InputFile& r) {
+    VSPE_TRY(require_index(c));
+    begin_call(c);
+    cudaEvent_t t0 = c->ev[7], t1 = c->ev[1];
+    VSPE_CUDA(cudaEventRecord(t0, c->stream));
+    const uint64_t chunk = (uint64_t)std::max<int64_t>(1, c->opt_chunk_mb) << 20;
+    ChunkProducer prod[2];
+    VSPE_TRY(prod[0].start(f, chunk));
+    VSPE_TRY(prod[1].start(r, chunk));
+    for (int m = 0; m < 2; m++) VSPE_TRY(c->dev_in[m].reserve(chunk + 64));
+    MateStream ms[2];
+    uint32_t hint = 0;
+    for (int m = 0; m < 2; m++) {                               // the first chunks size the packed rows
+        prod[m].wait_filled(0);
+        if (prod[m].rc != VSPE_OK) { set_error("%s", prod[m].err.c_str()); return prod[m].rc; }
+        hint = std::max(hint, seq_len_hint(prod[m].buf[0], std::min<uint64_t>(prod[m].len[0], 16384)));
+    }
+    c->read_len_hint = hint;
+    int b[2] = {0, 0};
+    bool done[2] = {false, false};
+    uint64_t bytes[2] = {0, 0};
+    while (!done[0] || !done[1]) {
+        for (int m = 0; m < 2; m++) {
+            if (done[m]) continue;
+            ChunkProducer& pr = prod[m];
+            pr.wait_filled(b[m]);
+            if (pr.rc != VSPE_OK) { set_error("%s", pr.err.c_str()); return pr.rc; }
+            const uint64_t n = pr.len[b[m]];
+            const bool last = pr.last[b[m]];
+            if (n) VSPE_CUDA(cudaMemcpyAsync(c->dev_in[m].p, pr.buf[b[m]], n, cudaMemcpyHostToDevice, c->stream));
+            VSPE_TRY(feed_chunk(c, m, ms[m], n ? c->dev_in[m].p : nullptr, n, last, n ? pr.buf[b[m]][n - 1] : -1));
+            bytes[m] += n;
+            pr.release(b[m]);
+            b[m] ^= 1;
+            done[m] = last;
+        }
+    }
+    VSPE_TRY(finish_pairs(c, ms[0], ms[1]));
+    VSPE_CUDA(cudaEventRecord(t1, c->stream));
+    VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    float ms_total = 0;
+    cudaEventElapsedTime(&ms_total, t0, t1);
+    c->stats.ms_total += ms_total;
+    c->stats.bytes_fwd += bytes[0];
+    c->stats.bytes_rve += bytes[1];
+    return VSPE_OK;
+}
+
 static int rm_rf(const std::string& dir) {
     // PE_Inference.py:95 `rm -rf DIR`: the script owns its output directory
     std::string cmd = "rm -rf -- '";
@@ -986,9 +1271,15 @@ int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, i
     if (!dir.empty() && dir.back() == '/') dir.pop_back();      // :93-94
     if (dir.empty()) { set_error("empty output directory"); return VSPE_ERR_ARG; }
     if (rm_rf(dir) != 0 || mkdir(dir.c_str(), 0777) != 0) {
-        // os.makedirs creates parents too
-        std::string cmd = "mkdir -p -- '" + dir + "'";
-        if (system(cmd.c_str()) != 0) { set_error("cannot create output directory %s", dir.c_str()); return VSPE_ERR_IO; }
+        // os.makedirs creates parents too: one mkdir(2) per path component (no shell involved)
+        bool ok = true;
+        for (size_t i = 1; i <= dir.size() && ok; i++) {
+            if (i != dir.size() && dir[i] != '/') continue;
+            const std::string part = dir.substr(0, i);
+            if (mkdir(part.c_str(), 0777) != 0 && errno != EEXIST) ok = false;
+        }
+        struct stat sb;
+        if (!ok || stat(dir.c_str(), &sb) != 0 || !S_ISDIR(sb.st_mode)) { set_error("cannot create output directory %s", dir.c_str()); return VSPE_ERR_IO; }
     }
     InputFile g, f, r;
     VSPE_TRY(g.open_ro(gfa_path));
@@ -997,12 +1288,18 @@ int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, i
     {   // the two read files are opened (and, if gzipped, inflated) side by side
         int rc_r = VSPE_OK;
         std::string err_r;
-        std::thread tr([&] { rc_r = r.open_ro(rve_path); if (rc_r != VSPE_OK) err_r = get_error(); });
-        const int rc_f = f.open_ro(fwd_path);
+        // (one GPU: gzip read files stay compressed here and are streamed; shards of several GPUs need the bytes)
+        const bool lazy = n_gpus == 1;
+        std::thread tr([&] { rc_r = r.open_ro(rve_path, !lazy); if (rc_r != VSPE_OK) err_r = get_error(); });
+        int rc_f = f.open_ro(fwd_path, !lazy);
         tr.join();
+        if (rc_f == VSPE_OK && rc_r == VSPE_OK && lazy && f.gz != r.gz) {     // only one of them is gzip: inflate it whole
+            if (f.gz) rc_f = f.inflate_all(); else { rc_r = r.inflate_all(); if (rc_r != VSPE_OK) err_r = get_error(); }
+        }
         if (rc_f != VSPE_OK) return rc_f;
         if (rc_r != VSPE_OK) { set_error("%s", err_r.c_str()); return rc_r; }
     }
+    const bool stream_gz = n_gpus == 1 && f.gz && r.gz && f.p == nullptr && r.p == nullptr;
     uint32_t N = (uint32_t)nodes.ids.size();
     std::vector<uint64_t> nm, sm, sk, sc;
     bool sparse_out = !dense_possible(N) || (getenv("VSPE_SPARSE") && atoi(getenv("VSPE_SPARSE")) != 0);
@@ -1014,7 +1311,7 @@ int vspe_run(const char* gfa_path, const char* fwd_path, const char* rve_path, i
         VSPE_TRY(vspe_create(0, &c));
         if (sparse_out) c->opt_sparse = 1;
         int rc = vspe_index_build(c, nodes.seqs.data(), nodes.off.data(), N, (uint32_t)kmer_size + 1);
-        if (rc == VSPE_OK) rc = vspe_count_host(c, f.p, f.n, r.p, r.n);
+        if (rc == VSPE_OK) rc = stream_gz ? count_gzip_streams(c, f, r) : vspe_count_host(c, f.p, f.n, r.p, r.n);
         if (rc == VSPE_OK && !sparse_out) {
             nm.assign((size_t)N * N, 0);
             sm.assign((size_t)N * N, 0);
@@ -1088,6 +1385,8 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
             }
         }
     }
+    else if (!strcmp(name, "tier_overlap")) c->opt_tier_overlap = value;
+    else if (!strcmp(name, "pair_cap_log2")) c->opt_pair_cap_log2 = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_counters")) {
         // profiling aid: copy the device counters (enum Counter order, CNT_COUNT_ words) to the host pointer `value`

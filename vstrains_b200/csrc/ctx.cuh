@@ -14,16 +14,17 @@ enum Counter {
     CNT_BAILED,              // reads the fast tier handed to the exhaustive tier
     CNT_DEFER,               // reads k_walk left for the list-driven tiers
     CNT_WORK2,               // reads k_map_windows left for the ASCII tier
-    CNT_DEFER2,              // (unused)
+    CNT_DEFER1,              // ... the same for the second mate file (the two mates' tiers may be in flight together)
     CNT_BIG,                 // (unused)
     CNT_LISTS,               // distinct node lists interned in the list table
     CNT_OVF,                 // private list records of this call (lists the table cannot hold)
     CNT_PAIR_OCC,            // distinct (left list, right list) combinations of the current batch
     CNT_EXP,                 // weighted keys the current batch expands to
     CNT_EXP_CURSOR,          // ... and the emit cursor over them
+    CNT_B_USED, CNT_B_N, CNT_B_SHORT,   // pair classes of the current batch (added to USED / N / SHORT once the batch is accepted)
     CNT_COUNT_
 };
-static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16, ERRF_LISTS_FULL = 32, ERRF_INTERNAL = 64;
+static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16, ERRF_LISTS_FULL = 32, ERRF_INTERNAL = 64, ERRF_PAIRS_FULL = 128;
 // flags that end the run (the *_FULL scan flags are transient: the host repeats or ignores the launch)
 static constexpr uint64_t ERRF_FATAL = ERRF_NON_ASCII | ERRF_SPILL_FULL | ERRF_KEYS_FULL | ERRF_LISTS_FULL | ERRF_INTERNAL;
 
@@ -47,6 +48,8 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaStream_t tier_stream = nullptr;  // list-driven tiers of one mate run here while the other mate is scanned on `stream`
+    cudaEvent_t ev_walk[2] = {}, ev_tier[2] = {};
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_scan[2][4] = {};     // events around the k_scan_rows [0] / k_walk [1] launches (two in flight each)
     Index index;
@@ -63,7 +66,9 @@ struct Ctx {
     bool scratch_valid = false;       // warp_scratch initialised for the current index
     DevBuf<uint32_t> spill;
     DevBuf<uint32_t> worklist;
-    DevBuf<uint32_t> defer_list;
+    DevBuf<uint32_t> defer_list;       // tier scratch: reads k_map_windows leaves for the ASCII tier
+    DevBuf<uint32_t> defer_m[2];       // per mate: reads k_walk left unresolved
+    DevBuf<uint64_t> tile_base_m[2];   // per mate: look-back status words, ticket and terminator total of k_scan_rows
     // K5/K6: list table + pair table (link.cuh)
     DevBuf<ListRec> list_recs;         // [list_T] table part + [list_ov_cap] private records
     DevBuf<uint32_t> list_occ;         // [list_T]
@@ -90,6 +95,8 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_tier_overlap = 1;      // device-resident calls: run one mate's list-driven tiers beside the other mate's scan
+    int64_t opt_pair_cap_log2 = 21;    // first size of the pair table (log2 entries); 0: size it by the pairs of the batch
     int64_t opt_stage_threads = 8;     // host threads that copy an unpinned input chunk into the pinned staging buffer
     int64_t opt_subst = 1;             // build / use the substitution-hit bitmap
     int64_t opt_scan_two_pass = 0;     // K1 as count + index passes (cross-check of the look-back kernel)

@@ -35,7 +35,7 @@ k_pack_text(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_o
 
 // --- one table entry per (k+1)-mer occurrence -----------------------------------------------
 __global__ void __launch_bounds__(256)
-k_index_insert(IndexView ix, unsigned long long* __restrict__ slots64) {
+k_index_insert(IndexView ix, unsigned long long* __restrict__ slots64, uint32_t* __restrict__ bloom) {
     uint32_t tp = blockIdx.x * blockDim.x + threadIdx.x;
     if (tp >= ix.text_len) return;
     uint32_t q = strand_of(ix.strand_start, 2 * ix.n_nodes, tp);
@@ -43,6 +43,13 @@ k_index_insert(IndexView ix, unsigned long long* __restrict__ slots64) {
     uint64_t h = hash_packed(ix.text, tp, ix.split_len);
     uint32_t meta = ((uint32_t)h & ~ix.node_mask) | (q >> 1);
     unsigned long long entry = ((unsigned long long)meta << 32) | tp;
+    if (bloom) {
+        uint32_t block, b0, b1, b2;
+        bloom_bits(h, ix.bloom_mask, block, b0, b1, b2);
+        atomicOr(bloom + 8 * (size_t)block + (b0 >> 5), 1u << (b0 & 31));
+        atomicOr(bloom + 8 * (size_t)block + (b1 >> 5), 1u << (b1 & 31));
+        atomicOr(bloom + 8 * (size_t)block + (b2 >> 5), 1u << (b2 & 31));
+    }
     uint32_t j = slot_of(h, ix.slot_mask);
     while (true) {
         unsigned long long old = atomicCAS(&slots64[j], EMPTY_SLOT, entry);
@@ -262,6 +269,17 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
     VSPE_CUDA(cudaMemsetAsync(ix.slots.p, 0xFF, slots * sizeof(uint2), st));
     VSPE_CUDA(cudaMemsetAsync(ix.uniq.p, 0, (size_t)n_words * 4, st));
 
+    // a slot table beyond L2 size (the 200 000-node stress graph: 2 GB) gets an L2-sized Bloom filter in front:
+    // about 8 bits per (k+1)-mer occurrence, three of them set
+    ix.has_bloom = false;
+    if (slots * sizeof(uint2) > (96ull << 20)) {
+        uint64_t blocks = 1024;
+        while (blocks * 256 < n_kmers * 6) blocks <<= 1;       // 6..12 bits per k-mer
+        VSPE_TRY(ix.bloom.reserve(blocks * 8));
+        VSPE_CUDA(cudaMemsetAsync(ix.bloom.p, 0, blocks * 32, st));
+        ix.bloom_mask = (uint32_t)(blocks - 1);
+        ix.has_bloom = true;
+    }
     ix.text_len = (uint32_t)text_len;
     ix.slot_mask = (uint32_t)(slots - 1);
     ix.node_mask = (1u << nbits) - 1;
@@ -275,7 +293,7 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
     VSPE_LAUNCH_CHECK(c);
     if (text_len) {
         uint32_t nb = (uint32_t)((text_len + 255) / 256);
-        k_index_insert<<<nb, 256, 0, st>>>(v, (unsigned long long*)ix.slots.p);
+        k_index_insert<<<nb, 256, 0, st>>>(v, (unsigned long long*)ix.slots.p, ix.has_bloom ? ix.bloom.p : nullptr);
         VSPE_LAUNCH_CHECK(c);
         k_index_unique<<<nb, 256, 0, st>>>(v, ix.uniq.p, n_words);
         VSPE_LAUNCH_CHECK(c);

@@ -149,7 +149,8 @@ __device__ __forceinline__ uint32_t mix64to32(unsigned long long k) {
 
 __global__ void __launch_bounds__(256)
 k_pair_agg(const uint32_t* __restrict__ hf, const uint32_t* __restrict__ hr, uint64_t n_pairs, PairEnt* __restrict__ tab,
-           uint32_t pmask, uint32_t* __restrict__ pocc, unsigned long long* __restrict__ counters, uint32_t h_limit) {
+           uint32_t pmask, uint32_t* __restrict__ pocc, unsigned long long* __restrict__ counters, uint32_t h_limit,
+           unsigned long long occ_limit, unsigned long long pocc_cap) {
     uint32_t c_used = 0, c_n = 0, c_short = 0;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t a = __ldg(hf + p), b = __ldg(hr + p);
@@ -166,9 +167,15 @@ k_pair_agg(const uint32_t* __restrict__ hf, const uint32_t* __restrict__ hr, uin
             PairEnt* e = tab + slot;
             unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&e->key1);
             if (k == 0) {
+                // a new combination: the table is kept at most half full (the host repeats the batch with a larger one)
+                if (*reinterpret_cast<volatile unsigned long long*>(counters + CNT_PAIR_OCC) >= occ_limit) {
+                    atomicOr(&counters[CNT_ERR], (unsigned long long)ERRF_PAIRS_FULL);
+                    break;
+                }
                 k = atomicCAS(&e->key1, 0ull, key1);
                 if (k == 0) {
-                    pocc[atomicAdd(&counters[CNT_PAIR_OCC], 1ull)] = slot;
+                    const unsigned long long at = atomicAdd(&counters[CNT_PAIR_OCC], 1ull);
+                    if (at < pocc_cap) pocc[at] = slot;       // (the limit can be overshot by the threads in flight, fewer than the slack)
                     k = key1;
                 }
             }
@@ -183,9 +190,9 @@ k_pair_agg(const uint32_t* __restrict__ hf, const uint32_t* __restrict__ hr, uin
         c_short += __shfl_xor_sync(0xFFFFFFFFu, c_short, d);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (c_used) atomicAdd(&counters[CNT_USED], (unsigned long long)c_used);
-        if (c_n) atomicAdd(&counters[CNT_N], (unsigned long long)c_n);
-        if (c_short) atomicAdd(&counters[CNT_SHORT], (unsigned long long)c_short);
+        if (c_used) atomicAdd(&counters[CNT_B_USED], (unsigned long long)c_used);
+        if (c_n) atomicAdd(&counters[CNT_B_N], (unsigned long long)c_n);
+        if (c_short) atomicAdd(&counters[CNT_B_SHORT], (unsigned long long)c_short);
     }
 }
 
@@ -204,6 +211,9 @@ __device__ __forceinline__ void add_exp(unsigned long long* counters, unsigned l
 __global__ void __launch_bounds__(256)
 k_comb_weigh(LinkView lv, const PairEnt* __restrict__ tab, const uint32_t* __restrict__ pocc) {
     const unsigned long long n = lv.counters[CNT_PAIR_OCC];
+    if (blockIdx.x == 0 && threadIdx.x < 3)                 // the batch was accepted: its pair classes count
+        atomicAdd(&lv.counters[CNT_USED + (threadIdx.x == 0 ? 0 : threadIdx.x == 1 ? CNT_N - CNT_USED : CNT_SHORT - CNT_USED)],
+                  lv.counters[CNT_B_USED + threadIdx.x]);
     unsigned long long exp = 0, keys = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const PairEnt e = tab[pocc[i]];
@@ -450,22 +460,37 @@ int count_links(Ctx* c, const uint32_t* d_hf, const uint32_t* d_hr, uint64_t tot
     const uint32_t grid_cap = (uint32_t)c->sm_count * 8;
     for (uint64_t off = 0; off < total; off += LINK_BATCH) {
         const uint64_t n = std::min<uint64_t>(LINK_BATCH, total - off);
-        // pair table: at most n distinct combinations at load <= 1/4; zero between batches (k_comb_emit cleans up)
-        uint64_t cap = 1u << 16;
-        while (cap < 4 * n) cap <<= 1;
-        if (cap > c->pair_cap) {
-            c->pair_tab.release();
-            VSPE_TRY(c->pair_tab.reserve(cap));
-            VSPE_CUDA(cudaMemsetAsync(c->pair_tab.p, 0, cap * sizeof(PairEnt), st));
-            c->pair_cap = cap;
-        }
-        VSPE_TRY(c->pair_occ.reserve(n));
-        VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_PAIR_OCC, 0, 3 * 8, st));     // PAIR_OCC, EXP, EXP_CURSOR
+        // pair table: sized for the distinct combinations, not for the pairs (it should stay L2 resident): it starts
+        // at 2^21 entries (32 MB) and a batch that fills it beyond one half is repeated with a table 4x larger, up to
+        // 4 n entries (n distinct combinations at load 1/4).  All zero between batches (k_comb_emit cleans up).
+        uint64_t cap_max = 1u << 16;
+        while (cap_max < 4 * n) cap_max <<= 1;
+        const uint64_t cap_first = c->opt_pair_cap_log2 > 0 ? 1ull << std::min<int64_t>(c->opt_pair_cap_log2, 40) : cap_max;
+        uint64_t cap = std::max<uint64_t>(std::min<uint64_t>(cap_max, cap_first), std::min<uint64_t>(c->pair_cap, cap_max));
         const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, grid_cap);
         const LinkView lv = link_view(c);
-        k_pair_agg<<<grid, 256, 0, st>>>(d_hf + off, d_hr + off, n, c->pair_tab.p, (uint32_t)(c->pair_cap - 1), c->pair_occ.p, c->counters.p,
-                                     c->list_T + c->list_ov_cap);
-        VSPE_LAUNCH_CHECK(c);
+        for (;;) {
+            if (cap != c->pair_cap) {
+                c->pair_tab.release();
+                VSPE_TRY(c->pair_tab.reserve(cap));
+                VSPE_CUDA(cudaMemsetAsync(c->pair_tab.p, 0, cap * sizeof(PairEnt), st));
+                c->pair_cap = cap;
+            }
+            const uint64_t pocc_cap = std::min<uint64_t>(n, cap / 2 + (1u << 19)) + 1;
+            VSPE_TRY(c->pair_occ.reserve(pocc_cap));
+            VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_PAIR_OCC, 0, 6 * 8, st));     // PAIR_OCC, EXP, EXP_CURSOR, B_USED, B_N, B_SHORT
+            k_pair_agg<<<grid, 256, 0, st>>>(d_hf + off, d_hr + off, n, c->pair_tab.p, (uint32_t)(c->pair_cap - 1), c->pair_occ.p, c->counters.p,
+                                         c->list_T + c->list_ov_cap, cap == cap_max ? ~0ull : cap / 2, pocc_cap);
+            VSPE_LAUNCH_CHECK(c);
+            unsigned long long h_err = 0;
+            VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, st));
+            VSPE_CUDA(cudaStreamSynchronize(st));
+            if (!(h_err & ERRF_PAIRS_FULL)) break;
+            const unsigned long long cleared = h_err & ~(unsigned long long)ERRF_PAIRS_FULL;
+            VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_ERR, &cleared, 8, cudaMemcpyHostToDevice, st));
+            VSPE_CUDA(cudaMemsetAsync(c->pair_tab.p, 0, c->pair_cap * sizeof(PairEnt), st));
+            cap = std::min<uint64_t>(cap * 4, cap_max);
+        }
         k_comb_weigh<<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_occ.p);
         VSPE_LAUNCH_CHECK(c);
         k_list_weigh<<<grid_cap, 256, 0, st>>>(lv);

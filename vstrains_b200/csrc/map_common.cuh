@@ -71,6 +71,7 @@ static __device__ __noinline__ int probe_window_rest(const IndexView& ix, const 
 __device__ __forceinline__ int probe_window(const IndexView& ix, const uint32_t* row, uint32_t b, uint32_t& tp, uint32_t& node) {
     const uint32_t L = ix.split_len;
     const uint64_t h = hash_read(row, b, L);
+    if (ix.bloom != nullptr && !bloom_maybe(ix.bloom, ix.bloom_mask, h)) return PROBE_MISS;
     uint32_t j = slot_of(h, ix.slot_mask);
     uint2 ent;
     while (true) {

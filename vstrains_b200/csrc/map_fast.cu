@@ -584,7 +584,11 @@ k_map_windows(IndexView ix, const uint32_t* __restrict__ rows, const uint32_t* _
             bool done = w >= npos;
             uint64_t hsh = 0;
             uint32_t j = 0;
-            if (!done) { hsh = hash_read(row, w, L); j = slot_of(hsh, ix.slot_mask); }
+            if (!done) {
+                hsh = hash_read(row, w, L);
+                j = slot_of(hsh, ix.slot_mask);
+                if (ix.bloom != nullptr && !bloom_maybe(ix.bloom, ix.bloom_mask, hsh)) done = true;   // proven miss
+            }
             while (true) {
                 // advance every lane to its next verified posting (or to the end of its cluster)
                 uint32_t node = NONE32;
@@ -654,9 +658,8 @@ int map_reads_generic_dev(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_st
 int map_prepare_lists(Ctx* c, uint64_t n_reads) {
     if (n_reads > 0xFFFFFFFFull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
     VSPE_TRY(c->worklist.reserve(n_reads + 1));
-    VSPE_TRY(c->defer_list.reserve(2 * n_reads + 2));
+    VSPE_TRY(c->defer_list.reserve(n_reads + 2));
     VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
-    VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_DEFER, 0, 8, c->stream));
     VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK2, 0, 8, c->stream));
     return VSPE_OK;
 }
@@ -672,7 +675,8 @@ static constexpr uint32_t LIST_SPREAD = 2;      // list-driven k_map_fast: every
 //   stage 3  k_map_generic  the exhaustive ASCII tier: any read length / alphabet
 static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                            const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                           uint64_t n_reads, ReadSlot* d_slots, bool pre_listed) {
+                           uint64_t n_reads, ReadSlot* d_slots, const uint32_t* pre_list, const unsigned long long* pre_count) {
+    const bool pre_listed = pre_list != nullptr;
     if (n_reads == 0) return VSPE_OK;
     if (n_reads > 0xFFFFFFFFull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
     if (!pre_listed) {
@@ -680,8 +684,8 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
     }
     IndexView v = c->index.view();
-    const uint32_t* in_list = pre_listed ? c->defer_list.p : nullptr;
-    const unsigned long long* in_count = pre_listed ? c->counters.p + CNT_DEFER : nullptr;
+    const uint32_t* in_list = pre_list;
+    const unsigned long long* in_count = pre_count;
     const uint32_t* to_generic = c->worklist.p;                 // reads the ASCII tier must map
     const unsigned long long* to_generic_n = c->counters.p + CNT_WORK;
     const uint32_t grid = pre_listed ? (uint32_t)std::min<uint64_t>((n_reads * LIST_SPREAD + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 8)
@@ -694,7 +698,7 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
 #undef VSPE_MF
     VSPE_LAUNCH_CHECK(c);
     if (pre_listed) {
-        uint32_t* list2 = c->defer_list.p + n_reads;
+        uint32_t* list2 = c->defer_list.p;
         const uint32_t wgrid = (uint32_t)std::min<uint64_t>((n_reads + MW_WARPS - 1) / MW_WARPS, (uint64_t)c->sm_count * 16);
 #define VSPE_MW(S) k_map_windows<S><<<wgrid, MW_WARPS * 32, 0, c->stream>>>(v, d_rows, d_hdr, row_words, c->worklist.p, c->counters.p + CNT_WORK, \
                                                                       d_slots, list2, c->counters.p + CNT_WORK2, c->spill.p, c->spill.cap, c->counters.p)
@@ -715,15 +719,15 @@ uint32_t map_fast_cap(uint32_t hint) { return hint <= 160 ? 160 : hint <= 256 ? 
 int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                    uint64_t n_reads, ReadSlot* d_slots) {
     if (c->index.split_len > 320) return map_reads_generic(c, d_buf, d_seq_start, d_seq_end, n_reads, d_slots);
-    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, nullptr, nullptr, 0, map_fast_cap(c->read_len_hint), n_reads, d_slots, false);
+    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, nullptr, nullptr, 0, map_fast_cap(c->read_len_hint), n_reads, d_slots, nullptr, nullptr);
 }
 
-// the reads k_walk left unresolved (listed in c->defer_list): full seed-and-extend kernel, then the
+// the reads k_walk left unresolved (d_list[0 .. *d_count)): full seed-and-extend kernel, then the
 // all-windows kernel, then the ASCII tier; results go to d_slots[r] for the listed r
 int map_reads_deferred(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                        const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                       uint64_t n_reads_cap, ReadSlot* d_slots) {
-    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, row_words, cap, n_reads_cap, d_slots, true);
+                       uint64_t n_reads_cap, ReadSlot* d_slots, const uint32_t* d_list, const unsigned long long* d_count) {
+    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, row_words, cap, n_reads_cap, d_slots, d_list, d_count);
 }
 
 }  // namespace vspe

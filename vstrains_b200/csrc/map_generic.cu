@@ -98,6 +98,7 @@ k_map_generic(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __r
             }
             if (!valid) continue;
             const uint64_t h = hs.finish();
+            if (ix.bloom != nullptr && !bloom_maybe(ix.bloom, ix.bloom_mask, h)) continue;   // proven miss
             uint32_t j = slot_of(h, ix.slot_mask);
             while (true) {
                 const uint2 ent = __ldg(ix.slots + j);

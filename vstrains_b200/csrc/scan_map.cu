@@ -244,6 +244,7 @@ struct WalkArgs {
     uint64_t line_base, rec_first;
     uint32_t* handles;
     uint32_t* defer_list;
+    unsigned long long* defer_count;
     unsigned long long* counters;
 };
 
@@ -287,7 +288,7 @@ k_walk(const WalkArgs a, const IndexView ix, const LinkView lv) {
         if (walk_read<STRIDE, WK_THREADS>(ix, row, rlen, s_lst + threadIdx.x, n_kept)) handle = intern_list(lv, n_kept, s_lst + threadIdx.x, WK_THREADS);
         else defer = true;
     }
-    if (handle == H_PENDING && defer) a.defer_list[atomicAdd(&a.counters[CNT_DEFER], 1ull)] = (uint32_t)r;
+    if (handle == H_PENDING && defer) a.defer_list[atomicAdd(a.defer_count, 1ull)] = (uint32_t)r;
     a.handles[r] = handle;
 }
 
@@ -615,16 +616,16 @@ k_scan_rows(const ScanMapArgs a) {
 
 // Both kernels over a device-resident chunk: k_scan_rows, then k_walk over up to n_slots reads (the walk
 // kernel reads the chunk's terminator count on the device, so no host synchronisation in between).
-int scan_map(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots, uint32_t* d_handles,
-             uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t* d_defer_list, uint32_t row_words,
-             uint32_t cap) {
+int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots, uint32_t* d_handles,
+             uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t* d_defer_list,
+             unsigned long long* d_defer_count, uint32_t row_words, uint32_t cap) {
     if (n == 0) return VSPE_OK;
     const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
     const uint64_t n_tiles = (n + head + SM_TILE - 1) / SM_TILE;
     if (n_tiles > 0x7FFFFFFFull) { set_error("buffer too large for one scan launch"); return VSPE_ERR_LIMIT; }
     if (n_slots > 0xFFFFFFF0ull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
-    VSPE_TRY(c->tile_base.reserve(n_tiles + 4));
-    unsigned long long* status = reinterpret_cast<unsigned long long*>(c->tile_base.p);
+    VSPE_TRY(c->tile_base_m[m].reserve(n_tiles + 4));
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(c->tile_base_m[m].p);
     VSPE_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 4) * 8, c->stream));
     ScanMapArgs a;
     a.buf = d_buf; a.n = n; a.head = head; a.n_tiles = (uint32_t)n_tiles; a.status = status;
@@ -650,7 +651,7 @@ int scan_map(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint6
     VSPE_CUDA(cudaEventRecord(c->ev_scan[0][2 * k + 1], c->stream));
     WalkArgs w;
     w.rows = d_rows; w.hdr = d_hdr; w.row_words = row_words; w.n_slots = n_slots; w.total = a.total_out;
-    w.line_base = line_base; w.rec_first = rec_first; w.handles = d_handles; w.defer_list = d_defer_list; w.counters = c->counters.p;
+    w.line_base = line_base; w.rec_first = rec_first; w.handles = d_handles; w.defer_list = d_defer_list; w.defer_count = d_defer_count; w.counters = c->counters.p;
     const IndexView ix = c->index.view();
     const LinkView lv = link_view(c);
     const uint32_t grid = (uint32_t)((n_slots + WK_THREADS - 1) / WK_THREADS);
@@ -666,10 +667,10 @@ int scan_map(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint6
 }
 
 // terminators of the chunk the last scan_map launch covered (device word, read after a stream sync)
-const unsigned long long* scan_map_total_ptr(Ctx* c, uint64_t n, const uint8_t* d_buf) {
+const unsigned long long* scan_map_total_ptr(Ctx* c, int m, uint64_t n, const uint8_t* d_buf) {
     const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
     const uint64_t n_tiles = (n + head + SM_TILE - 1) / SM_TILE;
-    return reinterpret_cast<unsigned long long*>(c->tile_base.p) + n_tiles + 2;
+    return reinterpret_cast<unsigned long long*>(c->tile_base_m[m].p) + n_tiles + 2;
 }
 
 // fold the durations of the finished k_scan_rows / k_walk launches into the stats (call after a stream sync)

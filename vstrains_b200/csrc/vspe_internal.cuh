@@ -63,6 +63,9 @@ struct IndexView {
     const uint32_t* succ;           // [2N][4] {text position, node} of the unique successor k-mer or {NONE32, 0}
     const uint4* succ16;            // [2N][4] the same successor with what a walk needs to enter it: {text position, strand,
                                     // strand end, node length} or {NONE32, 0, 0, 0}
+    const uint32_t* bloom;          // blocked Bloom filter over the indexed (k+1)-mers (nullptr when the slot table itself is
+                                    // L2 sized): one 32-byte block per hash, 3 bits per k-mer; a clear bit proves a miss
+    uint32_t bloom_mask;            // blocks - 1
     const uint32_t* subst;          // 4 bits per text base (or nullptr): bit b set iff some window of the strand that
                                     // covers the base, with the base replaced by code b, has a posting
     uint32_t text_len;              // bases
@@ -134,6 +137,24 @@ __device__ __forceinline__ uint64_t hash_packed(const uint64_t* __restrict__ t, 
 }
 
 __device__ __forceinline__ uint32_t slot_of(uint64_t h, uint32_t mask) { return (uint32_t)(h >> 32) & mask; }
+
+// Blocked Bloom filter: the block (eight 32-bit words = one 32-byte sector) and the three bit positions
+// inside it come from a remix of the hash, independent of the slot index and the fingerprint.
+__host__ __device__ __forceinline__ void bloom_bits(uint64_t h, uint32_t mask, uint32_t& block, uint32_t& b0, uint32_t& b1, uint32_t& b2) {
+    uint32_t m = KmerHash::fmix((uint32_t)h * 0x9E3779B1u ^ (uint32_t)(h >> 32));
+    block = m & mask;
+    m = KmerHash::fmix(m + 0x7F4A7C15u);
+    b0 = m & 255u; b1 = (m >> 8) & 255u; b2 = (m >> 16) & 255u;
+}
+// false: no indexed (k+1)-mer has this hash (a proof); true: look it up
+__device__ __forceinline__ bool bloom_maybe(const uint32_t* __restrict__ bloom, uint32_t mask, uint64_t h) {
+    uint32_t block, b0, b1, b2;
+    bloom_bits(h, mask, block, b0, b1, b2);
+    const uint4* p = reinterpret_cast<const uint4*>(bloom + 8 * (size_t)block);
+    const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    return ((w[b0 >> 5] >> (b0 & 31)) & (w[b1 >> 5] >> (b1 & 31)) & (w[b2 >> 5] >> (b2 & 31)) & 1u) != 0;
+}
 __device__ __forceinline__ bool fp_match(uint32_t meta, uint64_t h, uint32_t node_mask) {
     return (((uint32_t)h ^ meta) & ~node_mask) == 0;
 }
@@ -230,6 +251,9 @@ struct Index {
     DevBuf<uint32_t> uniq;
     DevBuf<uint32_t> succ;
     DevBuf<uint4> succ16;
+    DevBuf<uint32_t> bloom;
+    uint32_t bloom_mask = 0;
+    bool has_bloom = false;
     DevBuf<uint32_t> subst;
     bool has_subst = false;
     uint32_t text_len = 0, slot_mask = 0, node_mask = 0, split_len = 0, n_nodes = 0;
@@ -238,7 +262,7 @@ struct Index {
     IndexView view() const {
         IndexView v;
         v.text = text.p; v.strand_start = strand_start.p; v.node_len = node_len.p; v.node_rec = node_rec.p;
-        v.slots = slots.p; v.uniq = uniq.p; v.succ = succ.p; v.succ16 = succ16.p; v.subst = has_subst ? subst.p : nullptr;
+        v.slots = slots.p; v.uniq = uniq.p; v.succ = succ.p; v.succ16 = succ16.p; v.bloom = has_bloom ? bloom.p : nullptr; v.bloom_mask = bloom_mask; v.subst = has_subst ? subst.p : nullptr;
         v.text_len = text_len; v.slot_mask = slot_mask; v.node_mask = node_mask;
         v.split_len = split_len; v.n_nodes = n_nodes;
         return v;
@@ -271,10 +295,10 @@ int device_scan_u64(Ctx* c, const unsigned long long* in, unsigned long long* ou
                     unsigned long long* total);
 
 // K1+K2+K4 fused (scan_map.cu): one pass over a device-resident chunk -> handles + the unresolved reads, packed and listed
-int scan_map(Ctx* c, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots, uint32_t* d_handles,
-             uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t* d_defer_list, uint32_t row_words,
-             uint32_t cap);
-const unsigned long long* scan_map_total_ptr(Ctx* c, uint64_t n, const uint8_t* d_buf);
+int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots, uint32_t* d_handles,
+             uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t* d_defer_list,
+             unsigned long long* d_defer_count, uint32_t row_words, uint32_t cap);
+const unsigned long long* scan_map_total_ptr(Ctx* c, int m, uint64_t n, const uint8_t* d_buf);
 void scan_map_account(Ctx* c);
 
 // K2+K4: map reads [0, n_reads) of a chunk into slots[rec_off + r]

@@ -137,6 +137,10 @@ class PEIndex:
         """Add runs that live in this context's device memory (exact integer sums)."""
         check(self._L.vspe_sparse_merge_device(self._ctx, kptr, cptr, n))
 
+    def sparse_clear(self):
+        """Forget the runs of this context (its pair counters stay)."""
+        check(self._L.vspe_sparse_clear(self._ctx))
+
     def sparse_merge(self, keys: np.ndarray, counts: np.ndarray):
         """Add the runs of another context / rank (exact integer sums)."""
         k = np.ascontiguousarray(keys, dtype=np.uint64)
