@@ -178,7 +178,9 @@ void vspe_free_pinned(void* p);
  *                    tiers of one mate run on a second stream beside the scan of the other)
  *   "pair_cap_log2"  log2 of the first size of the pair table (default 21 = 32 MB, grown on demand); 0: size it by
  *                    the pairs of a batch
- *   "dbg_counters"   profiling aid (tools/dbg_map.py) */
+ *   "dbg_counters"   profiling aid (tools/dbg_map.py)
+ *   "dbg_scan_twice" measurement aid: k_scan_rows is launched twice per chunk and the second launch is the timed one
+ *                    (it finds every look-back word already published: the kernel without the look-back wait) */
 int vspe_set_option(vspe_ctx* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus

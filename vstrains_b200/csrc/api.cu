@@ -739,7 +739,13 @@ int vspe_create(int device, vspe_ctx** out) {
     const int rc = [&]() -> int {
         VSPE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (int b = 0; b < 2; b++) VSPE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream[b], cudaStreamNonBlocking));
-        VSPE_CUDA(cudaStreamCreateWithFlags(&c->tier_stream, cudaStreamNonBlocking));
+        {   // the list-driven tiers are short kernels that run beside a device-filling scan: with the higher
+            // priority their blocks take the SM slots the scan's blocks free, instead of queueing behind its whole grid
+            int prio_lo = 0, prio_hi = 0;
+            VSPE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            const char* e = getenv("VSPE_TIER_PRIO");
+            VSPE_CUDA(cudaStreamCreateWithPriority(&c->tier_stream, cudaStreamNonBlocking, (e && e[0] == '0') ? prio_lo : prio_hi));
+        }
         for (int b = 0; b < 2; b++) {
             VSPE_CUDA(cudaEventCreateWithFlags(&c->ev_walk[b], cudaEventDisableTiming));
             VSPE_CUDA(cudaEventCreateWithFlags(&c->ev_tier[b], cudaEventDisableTiming));
@@ -1386,6 +1392,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
         }
     }
     else if (!strcmp(name, "tier_overlap")) c->opt_tier_overlap = value;
+    else if (!strcmp(name, "dbg_scan_twice")) c->opt_dbg_scan_twice = value;
     else if (!strcmp(name, "pair_cap_log2")) c->opt_pair_cap_log2 = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_counters")) {

@@ -95,6 +95,7 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_dbg_scan_twice = 0;    // measurement aid (scan_map.cu)
     int64_t opt_tier_overlap = 1;      // device-resident calls: run one mate's list-driven tiers beside the other mate's scan
     int64_t opt_pair_cap_log2 = 21;    // first size of the pair table (log2 entries); 0: size it by the pairs of the batch
     int64_t opt_stage_threads = 8;     // host threads that copy an unpinned input chunk into the pinned staging buffer

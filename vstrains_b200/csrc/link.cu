@@ -28,7 +28,7 @@
 
 namespace vspe {
 
-static constexpr uint64_t LINK_BATCH = 8ull << 20;          // pairs per batch (weights stay below 2^32)
+static constexpr uint64_t LINK_BATCH = 32ull << 20;         // pairs per batch (weights -- up to two per pair and list -- stay below 2^32)
 
 LinkView link_view(Ctx* c) {
     LinkView v;
@@ -147,52 +147,82 @@ __device__ __forceinline__ uint32_t mix64to32(unsigned long long k) {
     return (uint32_t)(k >> 17);
 }
 
+// Four pairs per thread and turn: the handle loads are 16-byte vectors and the four first probes are in flight
+// together (the kernel is a chain of L2 round trips: table key -> claim -> count).  No shared counter is touched
+// inside the loop -- new combinations are counted in a register and added once per warp -- so nothing
+// serialises on one address.  max_probe bounds a probe sequence in a table that may be too small (the host
+// then repeats the batch with a larger one); the largest table (load <= 1/4) is probed without a bound.
 __global__ void __launch_bounds__(256)
 k_pair_agg(const uint32_t* __restrict__ hf, const uint32_t* __restrict__ hr, uint64_t n_pairs, PairEnt* __restrict__ tab,
-           uint32_t pmask, uint32_t* __restrict__ pocc, unsigned long long* __restrict__ counters, uint32_t h_limit,
-           unsigned long long occ_limit, unsigned long long pocc_cap) {
-    uint32_t c_used = 0, c_n = 0, c_short = 0;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t a = __ldg(hf + p), b = __ldg(hr + p);
-        if (a == H_N || b == H_N) { c_n++; continue; }                  // N before short (PE_Inference.py:160-163)
-        if (a == H_SHORT || b == H_SHORT) { c_short++; continue; }
-        if (a >= h_limit || b >= h_limit) {                              // a read no tier finished: never expected
-            atomicOr(&counters[CNT_ERR], (unsigned long long)ERRF_INTERNAL);
-            continue;
-        }
-        c_used++;
-        const unsigned long long key1 = (((unsigned long long)a << 32) | b) + 1ull;
-        uint32_t slot = mix64to32(key1) & pmask;
-        while (true) {
-            PairEnt* e = tab + slot;
-            unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&e->key1);
-            if (k == 0) {
-                // a new combination: the table is kept at most half full (the host repeats the batch with a larger one)
-                if (*reinterpret_cast<volatile unsigned long long*>(counters + CNT_PAIR_OCC) >= occ_limit) {
-                    atomicOr(&counters[CNT_ERR], (unsigned long long)ERRF_PAIRS_FULL);
-                    break;
-                }
-                k = atomicCAS(&e->key1, 0ull, key1);
-                if (k == 0) {
-                    const unsigned long long at = atomicAdd(&counters[CNT_PAIR_OCC], 1ull);
-                    if (at < pocc_cap) pocc[at] = slot;       // (the limit can be overshot by the threads in flight, fewer than the slack)
-                    k = key1;
-                }
+           uint32_t pmask, unsigned long long* __restrict__ counters, uint32_t h_limit, uint32_t max_probe) {
+    uint32_t c_used = 0, c_n = 0, c_short = 0, c_new = 0;
+    bool full = false, internal = false;
+    const bool vec = ((reinterpret_cast<uintptr_t>(hf) | reinterpret_cast<uintptr_t>(hr)) & 15) == 0;
+    const uint64_t span = (uint64_t)gridDim.x * blockDim.x * 4;
+    for (uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; p0 < n_pairs; p0 += span) {
+        uint32_t a[4], b[4];
+        const uint32_t n_here = (uint32_t)min((uint64_t)4, n_pairs - p0);
+        if (vec && n_here == 4) {
+            const uint4 va = __ldg(reinterpret_cast<const uint4*>(hf + p0)), vb = __ldg(reinterpret_cast<const uint4*>(hr + p0));
+            a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
+            b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                a[i] = (uint32_t)i < n_here ? __ldg(hf + p0 + i) : 0u;
+                b[i] = (uint32_t)i < n_here ? __ldg(hr + p0 + i) : 0u;
             }
-            if (k == key1) { atomicAdd(&e->count, 1u); break; }
-            slot = (slot + 1) & pmask;
+        }
+        unsigned long long key1[4], k[4];
+        uint32_t slot[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            key1[i] = 0;
+            slot[i] = 0;
+            if ((uint32_t)i >= n_here) continue;
+            if (a[i] == H_N || b[i] == H_N) { c_n++; continue; }                  // N before short (PE_Inference.py:160-163)
+            if (a[i] == H_SHORT || b[i] == H_SHORT) { c_short++; continue; }
+            if (a[i] >= h_limit || b[i] >= h_limit) { internal = true; continue; }   // a read no tier finished: never expected
+            c_used++;
+            key1[i] = (((unsigned long long)a[i] << 32) | b[i]) + 1ull;
+            slot[i] = mix64to32(key1[i]) & pmask;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            k[i] = 0;
+            if (key1[i]) k[i] = *reinterpret_cast<volatile unsigned long long*>(&tab[slot[i]].key1);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!key1[i]) continue;
+            uint32_t s = slot[i], probes = 0;
+            unsigned long long kk = k[i];
+            while (true) {
+                if (kk == 0) {
+                    kk = atomicCAS(&tab[s].key1, 0ull, key1[i]);
+                    if (kk == 0) { c_new++; kk = key1[i]; }
+                }
+                if (kk == key1[i]) { atomicAdd(&tab[s].count, 1u); break; }
+                if (++probes > max_probe) { full = true; break; }
+                s = (s + 1) & pmask;
+                kk = *reinterpret_cast<volatile unsigned long long*>(&tab[s].key1);
+            }
         }
     }
+    if (full) atomicOr(&counters[CNT_ERR], (unsigned long long)ERRF_PAIRS_FULL);
+    if (internal) atomicOr(&counters[CNT_ERR], (unsigned long long)ERRF_INTERNAL);
     // pair counters: one atomic per warp and counter
     for (int d = 16; d; d >>= 1) {
         c_used += __shfl_xor_sync(0xFFFFFFFFu, c_used, d);
         c_n += __shfl_xor_sync(0xFFFFFFFFu, c_n, d);
         c_short += __shfl_xor_sync(0xFFFFFFFFu, c_short, d);
+        c_new += __shfl_xor_sync(0xFFFFFFFFu, c_new, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (c_used) atomicAdd(&counters[CNT_B_USED], (unsigned long long)c_used);
         if (c_n) atomicAdd(&counters[CNT_B_N], (unsigned long long)c_n);
         if (c_short) atomicAdd(&counters[CNT_B_SHORT], (unsigned long long)c_short);
+        if (c_new) atomicAdd(&counters[CNT_PAIR_OCC], (unsigned long long)c_new);
     }
 }
 
@@ -209,14 +239,15 @@ __device__ __forceinline__ void add_exp(unsigned long long* counters, unsigned l
 
 // every distinct combination: weights of its lists, number of node_mat keys
 __global__ void __launch_bounds__(256)
-k_comb_weigh(LinkView lv, const PairEnt* __restrict__ tab, const uint32_t* __restrict__ pocc) {
-    const unsigned long long n = lv.counters[CNT_PAIR_OCC];
+k_comb_weigh(LinkView lv, const PairEnt* __restrict__ tab, uint64_t cap) {
+    const uint64_t n = cap;                                 // the whole table is visited: free entries are skipped
     if (blockIdx.x == 0 && threadIdx.x < 3)                 // the batch was accepted: its pair classes count
         atomicAdd(&lv.counters[CNT_USED + (threadIdx.x == 0 ? 0 : threadIdx.x == 1 ? CNT_N - CNT_USED : CNT_SHORT - CNT_USED)],
                   lv.counters[CNT_B_USED + threadIdx.x]);
     unsigned long long exp = 0, keys = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const PairEnt e = tab[pocc[i]];
+        const PairEnt e = tab[i];
+        if (e.key1 == 0) continue;
         const unsigned long long k = e.key1 - 1;
         const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
         atomicAdd(&lv.recs[a].used, e.count);
@@ -261,16 +292,16 @@ __device__ __forceinline__ unsigned long long warp_alloc(unsigned long long* cur
 }
 
 __global__ void __launch_bounds__(256)
-k_comb_emit(LinkView lv, PairEnt* __restrict__ tab, const uint32_t* __restrict__ pocc, uint64_t N,
+k_comb_emit(LinkView lv, PairEnt* __restrict__ tab, uint64_t cap, uint64_t N,
             unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
-    const unsigned long long n = lv.counters[CNT_PAIR_OCC];
+    const uint64_t n = cap;
     const uint64_t span = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < n; i0 += span) {      // warp-uniform trip count
         const uint64_t i = i0 + threadIdx.x;
         ListRef L = {nullptr, 0, 0}, R = {nullptr, 0, 0};
         unsigned long long w = 0;
-        if (i < n) {
-            PairEnt* e = tab + pocc[i];
+        PairEnt* e = tab + i;
+        if (i < n && e->key1 != 0) {
             const unsigned long long k = e->key1 - 1;
             w = e->count;
             L = list_ref(lv, (uint32_t)(k >> 32));
@@ -467,7 +498,7 @@ int count_links(Ctx* c, const uint32_t* d_hf, const uint32_t* d_hr, uint64_t tot
         while (cap_max < 4 * n) cap_max <<= 1;
         const uint64_t cap_first = c->opt_pair_cap_log2 > 0 ? 1ull << std::min<int64_t>(c->opt_pair_cap_log2, 40) : cap_max;
         uint64_t cap = std::max<uint64_t>(std::min<uint64_t>(cap_max, cap_first), std::min<uint64_t>(c->pair_cap, cap_max));
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, grid_cap);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 1023) / 1024, grid_cap);      // four pairs per thread and turn
         const LinkView lv = link_view(c);
         for (;;) {
             if (cap != c->pair_cap) {
@@ -476,22 +507,22 @@ int count_links(Ctx* c, const uint32_t* d_hf, const uint32_t* d_hr, uint64_t tot
                 VSPE_CUDA(cudaMemsetAsync(c->pair_tab.p, 0, cap * sizeof(PairEnt), st));
                 c->pair_cap = cap;
             }
-            const uint64_t pocc_cap = std::min<uint64_t>(n, cap / 2 + (1u << 19)) + 1;
-            VSPE_TRY(c->pair_occ.reserve(pocc_cap));
             VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_PAIR_OCC, 0, 6 * 8, st));     // PAIR_OCC, EXP, EXP_CURSOR, B_USED, B_N, B_SHORT
-            k_pair_agg<<<grid, 256, 0, st>>>(d_hf + off, d_hr + off, n, c->pair_tab.p, (uint32_t)(c->pair_cap - 1), c->pair_occ.p, c->counters.p,
-                                         c->list_T + c->list_ov_cap, cap == cap_max ? ~0ull : cap / 2, pocc_cap);
+            k_pair_agg<<<grid, 256, 0, st>>>(d_hf + off, d_hr + off, n, c->pair_tab.p, (uint32_t)(c->pair_cap - 1), c->counters.p,
+                                         c->list_T + c->list_ov_cap, cap == cap_max ? 0xFFFFFFFFu : 256u);
             VSPE_LAUNCH_CHECK(c);
-            unsigned long long h_err = 0;
+            unsigned long long h_err = 0, h_occ = 0;
             VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, st));
+            VSPE_CUDA(cudaMemcpyAsync(&h_occ, c->counters.p + CNT_PAIR_OCC, 8, cudaMemcpyDeviceToHost, st));
             VSPE_CUDA(cudaStreamSynchronize(st));
-            if (!(h_err & ERRF_PAIRS_FULL)) break;
+            // accepted: every probe sequence ended and the table is at most half full (the largest table is always accepted)
+            if (!(h_err & ERRF_PAIRS_FULL) && (cap == cap_max || h_occ <= cap / 2)) break;
             const unsigned long long cleared = h_err & ~(unsigned long long)ERRF_PAIRS_FULL;
             VSPE_CUDA(cudaMemcpyAsync(c->counters.p + CNT_ERR, &cleared, 8, cudaMemcpyHostToDevice, st));
             VSPE_CUDA(cudaMemsetAsync(c->pair_tab.p, 0, c->pair_cap * sizeof(PairEnt), st));
             cap = std::min<uint64_t>(cap * 4, cap_max);
         }
-        k_comb_weigh<<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_occ.p);
+        k_comb_weigh<<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_cap);
         VSPE_LAUNCH_CHECK(c);
         k_list_weigh<<<grid_cap, 256, 0, st>>>(lv);
         VSPE_LAUNCH_CHECK(c);
@@ -510,7 +541,7 @@ int count_links(Ctx* c, const uint32_t* d_hf, const uint32_t* d_hr, uint64_t tot
         VSPE_TRY(sparse_reserve(c, sp.n_runs + h_exp));
         unsigned long long* keys = sp.k[0].p + sp.n_runs;
         unsigned long long* vals = sp.v[0].p + sp.n_runs;
-        k_comb_emit<<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_occ.p, N, keys, vals);
+        k_comb_emit<<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_cap, N, keys, vals);
         VSPE_LAUNCH_CHECK(c);
         k_list_emit<<<grid_cap, 256, 0, st>>>(lv, N, keys, vals);
         VSPE_LAUNCH_CHECK(c);

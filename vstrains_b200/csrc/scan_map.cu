@@ -643,10 +643,20 @@ int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base
     }
     // both kernels are timed on their own (CUDA events on the launching stream; two launches may be in flight)
     const int k = c->scan_map_events & 1;
+    auto launch_scan = [&]() {
+        if (row_words == 12) k_scan_rows<12><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
+        else if (row_words == 16) k_scan_rows<16><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
+        else k_scan_rows<20><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    };
+    if (c->opt_dbg_scan_twice) {
+        // measurement aid: the timed launch below then finds every predecessor's inclusive word already published
+        // (same results), i.e. it shows the kernel without the look-back wait
+        launch_scan();
+        VSPE_LAUNCH_CHECK(c);
+        VSPE_CUDA(cudaMemsetAsync(a.ticket, 0, 4, c->stream));
+    }
     VSPE_CUDA(cudaEventRecord(c->ev_scan[0][2 * k], c->stream));
-    if (row_words == 12) k_scan_rows<12><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
-    else if (row_words == 16) k_scan_rows<16><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
-    else k_scan_rows<20><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    launch_scan();
     VSPE_LAUNCH_CHECK(c);
     VSPE_CUDA(cudaEventRecord(c->ev_scan[0][2 * k + 1], c->stream));
     WalkArgs w;
