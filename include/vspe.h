@@ -59,6 +59,8 @@ typedef struct vspe_stats {
     uint32_t n_k_scan_rows;   /* ... and how many launches that was                               */
     float ms_k_walk;          /* same for k_walk                                                  */
     uint32_t n_k_walk;
+    uint32_t scan_redo_tiles; /* tiles k_scan_redo packed again because their guessed line phase was wrong  */
+    uint32_t reserved0;
 } vspe_stats;
 
 typedef struct vspe_ctx vspe_ctx;
@@ -178,9 +180,7 @@ void vspe_free_pinned(void* p);
  *                    tiers of one mate run on a second stream beside the scan of the other)
  *   "pair_cap_log2"  log2 of the first size of the pair table (default 21 = 32 MB, grown on demand); 0: size it by
  *                    the pairs of a batch
- *   "dbg_counters"   profiling aid (tools/dbg_map.py)
- *   "dbg_scan_twice" measurement aid: k_scan_rows is launched twice per chunk and the second launch is the timed one
- *                    (it finds every look-back word already published: the kernel without the look-back wait) */
+ *   "dbg_counters"   profiling aid (tools/dbg_map.py) */
 int vspe_set_option(vspe_ctx* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus

@@ -341,6 +341,9 @@ def test_whole_path_edge_shapes(scan_mode):
         assert np.array_equal(short.astype(np.int64), oshort), name
         for k, v in ostats.items():
             assert stats[k] == v, (name, k)
+        if scan_mode == 0:
+            # tiles guess their line phase and a wrong guess is packed again: only the decoy text may (and must) cause that
+            assert (stats["scan_redo_tiles"] > 0) == (name == "decoy"), (name, stats["scan_redo_tiles"])
 
 
 @pytest.mark.parametrize("subst,scan_mode", [(1, 0), (0, 0), (1, 1), (0, 1)])

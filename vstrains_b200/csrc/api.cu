@@ -34,7 +34,7 @@ int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, co
 int map_prepare_lists(Ctx* c, uint64_t n_reads);
 int map_reads_deferred(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                        const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                       uint64_t n_reads_cap, ReadSlot* d_slots, const uint32_t* d_list, const unsigned long long* d_count);
+                       uint64_t n_reads_cap, ReadSlot* d_slots, const unsigned long long* d_count);
 uint32_t map_fast_cap(uint32_t hint);
 int run_multi_gpu(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_nodes, uint32_t split_len,
                   const uint8_t* fwd, uint64_t n_fwd, const uint8_t* rve, uint64_t n_rve, int n_gpus,
@@ -95,15 +95,9 @@ static int fused_launch(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_
     const uint32_t row_words = cap <= 160 ? 12 : cap <= 256 ? 16 : 20;
     unsigned long long* d_count = c->counters.p + (m == 0 ? CNT_DEFER : CNT_DEFER1);
     VSPE_TRY(mb.handles.reserve(rec_first + guess + 2, true, c->stream));
-    VSPE_TRY(mb.rec.seq_start.reserve(guess + 2));
-    VSPE_TRY(mb.rec.seq_end.reserve(guess + 2));
-    VSPE_TRY(mb.rec.hdr.reserve(guess + 2));
-    VSPE_TRY(mb.rec.rows.reserve((guess + 2) * row_words));
-    VSPE_TRY(mb.slots.reserve(guess + 2));                      // slots of the unresolved reads (chunk-local index)
-    VSPE_TRY(c->defer_m[m].reserve(guess + 2));
+    VSPE_TRY(mb.slots.reserve(guess + 2));                      // slots of the unresolved reads (compact index)
     VSPE_CUDA(cudaMemsetAsync(d_count, 0, 8, c->stream));
-    VSPE_TRY(scan_map(c, m, d_buf, n, lb, rec_first, guess, mb.handles.p + rec_first, mb.rec.seq_start.p, mb.rec.seq_end.p,
-                      mb.rec.rows.p, mb.rec.hdr.p, c->defer_m[m].p, d_count, row_words, cap));
+    VSPE_TRY(scan_map(c, m, d_buf, n, lb, rec_first, guess, mb.handles.p + rec_first, d_count, row_words, cap));
     VSPE_CUDA(cudaEventRecord(c->ev_m[m][1], c->stream));
     cudaStream_t main_stream = c->stream;
     if (overlap) {
@@ -114,8 +108,8 @@ static int fused_launch(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_
     c->cur_buf_n = n;
     int rc = map_prepare_lists(c, guess + 2);
     if (rc == VSPE_OK)
-        rc = map_reads_deferred(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.rec.rows.p, mb.rec.hdr.p, row_words, cap, guess,
-                                mb.slots.p, c->defer_m[m].p, d_count);
+        rc = map_reads_deferred(c, d_buf, mb.rec.seq_start.p, mb.rec.seq_end.p, mb.d_rows.p, mb.d_hdr.p, row_words, cap, guess,
+                                mb.slots.p, d_count);
     if (rc == VSPE_OK) rc = intern_slots(c, mb.slots.p, guess, c->defer_m[m].p, d_count, mb.handles.p + rec_first);
     if (rc == VSPE_OK && cudaEventRecord(c->ev_m[m][2], c->stream) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = VSPE_ERR_CUDA; }
     if (overlap) {
@@ -137,14 +131,16 @@ static int feed_chunk_fused(Ctx* c, int m, MateStream& ms, const uint8_t* d_buf,
     uint64_t guess = guess_reads(c, n);
     VSPE_CUDA(cudaEventRecord(c->ev_m[m][0], c->stream));
     for (int attempt = 0;; attempt++) {
-        unsigned long long cur0[2] = {0, 0}, h_total = 0, h_err = 0;
+        unsigned long long cur0[2] = {0, 0}, h_rt[2] = {0, 0}, h_err = 0;       // h_rt: {redo tiles, terminators}
         VSPE_CUDA(cudaMemcpyAsync(&cur0[0], c->counters.p + CNT_SPILL_CURSOR, 8, cudaMemcpyDeviceToHost, c->stream));
         VSPE_CUDA(cudaMemcpyAsync(&cur0[1], c->counters.p + CNT_OVF, 8, cudaMemcpyDeviceToHost, c->stream));
         VSPE_TRY(fused_launch(c, m, d_buf, n, lb, guess, false));
-        VSPE_CUDA(cudaMemcpyAsync(&h_total, scan_map_total_ptr(c, m, n, d_buf), 8, cudaMemcpyDeviceToHost, c->stream));
+        VSPE_CUDA(cudaMemcpyAsync(h_rt, scan_map_total_ptr(c, m, n, d_buf), 16, cudaMemcpyDeviceToHost, c->stream));
         VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
         VSPE_CUDA(cudaStreamSynchronize(c->stream));
         scan_map_account(c);
+        const unsigned long long h_total = h_rt[1];
+        if (!(h_err & ERRF_TILE_FULL)) c->stats.scan_redo_tiles += (uint32_t)h_rt[0];
         const uint64_t n_seq = seq_lines_before(lb + h_total) - rec_first;
         const unsigned long long transient = ERRF_SLOTS_FULL | ERRF_TILE_FULL;
         if (h_err & transient) {
@@ -850,18 +846,19 @@ int vspe_count_device(vspe_ctx* c, const uint8_t* d_fwd, uint64_t n_fwd, const u
         for (auto& e : c->ev_m) for (auto& ev : e) if (!ev) VSPE_CUDA(cudaEventCreate(&ev));
         bool serial = false;
         for (int attempt = 0; attempt < 8 && !done && !serial; attempt++) {
-            unsigned long long h_total[2] = {0, 0}, h_err = 0;
+            unsigned long long h_total[2] = {0, 0}, h_rt[2][2] = {{0, 0}, {0, 0}}, h_err = 0;   // h_rt: {redo tiles, terminators}
             for (int m = 0; m < 2; m++) {
                 VSPE_CUDA(cudaEventRecord(c->ev_m[m][0], c->stream));
                 VSPE_TRY(fused_launch(c, m, bufs[m], ns[m], 0, guess[m], true));
             }
             for (int m = 0; m < 2; m++) {
                 VSPE_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tier[m], 0));
-                VSPE_CUDA(cudaMemcpyAsync(&h_total[m], scan_map_total_ptr(c, m, ns[m], bufs[m]), 8, cudaMemcpyDeviceToHost, c->stream));
+                VSPE_CUDA(cudaMemcpyAsync(h_rt[m], scan_map_total_ptr(c, m, ns[m], bufs[m]), 16, cudaMemcpyDeviceToHost, c->stream));
             }
             VSPE_CUDA(cudaMemcpyAsync(&h_err, c->counters.p + CNT_ERR, 8, cudaMemcpyDeviceToHost, c->stream));
             VSPE_CUDA(cudaStreamSynchronize(c->stream));
             scan_map_account(c);
+            for (int m = 0; m < 2; m++) { h_total[m] = h_rt[m][1]; if (!(h_err & ERRF_TILE_FULL)) c->stats.scan_redo_tiles += (uint32_t)h_rt[m][0]; }
             const unsigned long long redo = ERRF_SLOTS_FULL | ERRF_TILE_FULL | ERRF_LISTS_FULL | ERRF_SPILL_FULL;
             if (h_err & redo) {
                 const unsigned long long cleared = h_err & ~redo;
@@ -1392,7 +1389,6 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
         }
     }
     else if (!strcmp(name, "tier_overlap")) c->opt_tier_overlap = value;
-    else if (!strcmp(name, "dbg_scan_twice")) c->opt_dbg_scan_twice = value;
     else if (!strcmp(name, "pair_cap_log2")) c->opt_pair_cap_log2 = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_counters")) {

@@ -40,6 +40,7 @@ struct Sparse {
 struct MateBuf {
     Records rec;
     DevBuf<ReadSlot> slots;
+    DevBuf<uint32_t> d_hdr, d_rows;   // compact copies (header, packed row) of the reads k_walk deferred
     DevBuf<uint32_t> handles;  // [n_recs] list handle (or H_N / H_SHORT) per read
     uint64_t n_recs = 0;      // complete records = lines / 4
 };
@@ -68,13 +69,13 @@ struct Ctx {
     DevBuf<uint32_t> worklist;
     DevBuf<uint32_t> defer_list;       // tier scratch: reads k_map_windows leaves for the ASCII tier
     DevBuf<uint32_t> defer_m[2];       // per mate: reads k_walk left unresolved
-    DevBuf<uint64_t> tile_base_m[2];   // per mate: look-back status words, ticket and terminator total of k_scan_rows
+    DevBuf<uint64_t> tile_base_m[2];   // per mate: k_scan_rows' tile records, k_tile_fix's redo list + count, terminator total
+    DevBuf<uint32_t> tile_idx_m[2];    // per mate: first read of every tile, first tile of every k_walk block (k_tile_fix)
     // K5/K6: list table + pair table (link.cuh)
     DevBuf<ListRec> list_recs;         // [list_T] table part + [list_ov_cap] private records
     DevBuf<uint32_t> list_occ;         // [list_T]
     uint32_t list_T = 0, list_ov_cap = 0;
     DevBuf<PairEnt> pair_tab;          // [pair_cap] (power of two), all zero between batches
-    DevBuf<uint32_t> pair_occ;
     uint64_t pair_cap = 0;
     DevBuf<uint32_t> wk_hist, wk_keys;   // dense accumulation scratch: bucket histogram / segments, partitioned (digit, weight)
     bool link_attr_set = false;
@@ -95,7 +96,6 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
-    int64_t opt_dbg_scan_twice = 0;    // measurement aid (scan_map.cu)
     int64_t opt_tier_overlap = 1;      // device-resident calls: run one mate's list-driven tiers beside the other mate's scan
     int64_t opt_pair_cap_log2 = 21;    // first size of the pair table (log2 entries); 0: size it by the pairs of the batch
     int64_t opt_stage_threads = 8;     // host threads that copy an unpinned input chunk into the pinned staging buffer

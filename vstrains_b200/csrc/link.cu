@@ -86,8 +86,8 @@ k_intern_slots(LinkView lv, const ReadSlot* __restrict__ slots, uint64_t n_arg, 
                const unsigned long long* __restrict__ n_dev, uint32_t* __restrict__ handles) {
     const uint64_t n = n_dev ? *n_dev : n_arg;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t r = scatter ? scatter[i] : i;                  // listed reads: slot and handle share the index
-        const ReadSlot* s = slots + r;
+        const uint64_t r = scatter ? scatter[i] : i;                  // deferred reads: compact slot i belongs to read scatter[i]
+        const ReadSlot* s = slots + i;
         const uint32_t hdr = s->hdr, st = hdr & 0xFF, cnt = hdr >> 8;
         uint32_t h;
         if (st == ST_N) h = H_N;

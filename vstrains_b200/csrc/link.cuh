@@ -140,7 +140,7 @@ LinkView link_view(Ctx* c);
 int link_setup(Ctx* c);                                     // after the index build: size + zero the tables
 int link_reset(Ctx* c);                                     // forget every list (vspe_reset)
 int link_grow_overflow(Ctx* c);                             // after ERRF_LISTS_FULL / ERRF_SPILL_FULL
-// ReadSlots of the slot-writing tiers -> handles: reads [0, n), or the listed reads d_scatter[0 .. *d_n)
+// ReadSlots of the slot-writing tiers -> handles: d_handles[i] for slots [0, n), or d_handles[d_scatter[i]] for the compact slots [0, *d_n)
 int intern_slots(Ctx* c, const ReadSlot* d_slots, uint64_t n, const uint32_t* d_scatter, const unsigned long long* d_n, uint32_t* d_handles);
 // handles -> ReadSlots with ascending ids (vspe_map_reads)
 int export_slots(Ctx* c, const uint32_t* d_handles, uint64_t n, ReadSlot* d_slots);

@@ -281,11 +281,11 @@ template <int STRIDE, int LPR, bool PACKED>
 __device__ __forceinline__ void
 map_fast_block(const IndexView& ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
                const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr,
-               uint32_t row_words, uint64_t n_reads, const uint32_t* __restrict__ in_list, uint32_t spread,
+               uint32_t row_words, uint64_t n_reads, const bool listed, uint32_t spread,
                ReadSlot* __restrict__ slots, uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters,
                const uint32_t block_id) {
     // One block's worth of reads: MF_THREADS / spread of them, read block_id * that onwards.
-    // in_list != nullptr: they are in_list[...] (the reads the first tiers deferred).  Those are
+    // listed: they are the reads the first tiers deferred, compact [0, n_reads).  Those are
     // few and each is a long serial chain (passes, range probes): only every spread-th thread
     // takes a read, which spreads them over `spread` times more warps.
     if ((uint64_t)block_id * (MF_THREADS / spread) >= n_reads) return;
@@ -307,7 +307,7 @@ map_fast_block(const IndexView& ix, const uint8_t* __restrict__ buf, const uint6
         const bool live = (t % spread) == 0 && r0 + t / spread < n_reads;
         uint32_t lfv = F_NONE;
         if (live) {
-            const uint64_t r = in_list ? (uint64_t)in_list[r0 + t / spread] : r0 + t;
+            const uint64_t r = listed ? r0 + t / spread : r0 + t;
             const uint32_t h = __ldg(hdr + r);
             if (h & PH_LONG) lfv = F_LONG;
             else {
@@ -406,7 +406,7 @@ map_fast_block(const IndexView& ix, const uint8_t* __restrict__ buf, const uint6
     // ---- phase 2: one thread per read, passes A and B ---------------------------------------
     const uint32_t t = threadIdx.x;
     uint32_t lf = s_len[t];
-    const uint64_t r = (lf & F_NONE) ? 0 : in_list ? (uint64_t)in_list[r0 + t / spread] : r0 + t;
+    const uint64_t r = (lf & F_NONE) ? 0 : listed ? r0 + t / spread : r0 + t;
     const uint32_t rlen = lf & 0xFFFFFF;
     const uint32_t* row = s_fwd + t * STRIDE;
     uint32_t nn = 0;
@@ -476,7 +476,7 @@ map_fast_block(const IndexView& ix, const uint8_t* __restrict__ buf, const uint6
 
     // ---- phase 4: finalize -----------------------------------------------------------------
     if (lf & F_NONE) return;
-    if (t == 0 && block_id == 0 && !in_list) atomicAdd(&counters[CNT_FAST], (unsigned long long)n_reads);
+    if (t == 0 && block_id == 0 && !listed) atomicAdd(&counters[CNT_FAST], (unsigned long long)n_reads);
     ReadSlot* out = slots + r;
     if (!(lf & F_LONG)) {
         if (lf & F_N) { out->hdr = ST_N; return; }
@@ -520,17 +520,17 @@ map_fast_block(const IndexView& ix, const uint8_t* __restrict__ buf, const uint6
     out->hdr = ST_OK | (n_out << 8);
 }
 
-// Direct mode (in_list == nullptr): one block per MF_THREADS reads.  List mode: a fixed grid walks
-// the device-side worklist (its length is only known on the device), so no empty blocks are launched.
+// Direct mode (in_count == nullptr): one block per MF_THREADS reads.  List mode: a fixed grid walks the compact
+// arrays of the deferred reads (their number is only known on the device), so no empty blocks are launched.
 template <int STRIDE, int LPR, bool PACKED>
 __global__ void __launch_bounds__(MF_THREADS)
 k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
            const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr,
-           uint32_t row_words, uint64_t n_reads_arg, const uint32_t* __restrict__ in_list,
+           uint32_t row_words, uint64_t n_reads_arg,
            const unsigned long long* __restrict__ in_count, uint32_t list_spread, ReadSlot* __restrict__ slots,
            uint32_t* __restrict__ worklist, unsigned long long* __restrict__ counters) {
-    if (!in_list) {
-        map_fast_block<STRIDE, LPR, PACKED>(ix, buf, seq_start, seq_end, rows, hdr, row_words, n_reads_arg, nullptr, 1u, slots, worklist,
+    if (!in_count) {
+        map_fast_block<STRIDE, LPR, PACKED>(ix, buf, seq_start, seq_end, rows, hdr, row_words, n_reads_arg, false, 1u, slots, worklist,
                                             counters, blockIdx.x);
         return;
     }
@@ -538,7 +538,7 @@ k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __rest
     const uint64_t per_block = MF_THREADS / list_spread;
     const uint64_t n_blocks = (n_items + per_block - 1) / per_block;
     for (uint64_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
-        map_fast_block<STRIDE, LPR, PACKED>(ix, buf, seq_start, seq_end, rows, hdr, row_words, n_items, in_list, list_spread, slots,
+        map_fast_block<STRIDE, LPR, PACKED>(ix, buf, seq_start, seq_end, rows, hdr, row_words, n_items, true, list_spread, slots,
                                             worklist, counters, (uint32_t)b);
         __syncthreads();                                   // the block's shared-memory rows are reused by the next round
     }
@@ -666,8 +666,8 @@ int map_prepare_lists(Ctx* c, uint64_t n_reads) {
 
 static constexpr uint32_t LIST_SPREAD = 2;      // list-driven k_map_fast: every 2nd thread takes a read (long serial chains)
 
-// The tiers behind the walk.  pre_listed: the reads to map are the counters[CNT_DEFER] entries of c->defer_list
-// (written by k_walk after map_prepare_lists) and their packed rows exist; otherwise every read [0, n_reads) goes
+// The tiers behind the walk.  pre_count != nullptr: the reads to map are the *pre_count deferred reads k_walk copied
+// to compact arrays (rows, headers, byte ranges; slots are compact too); otherwise every read [0, n_reads) goes
 // through the full seed-and-extend kernel, which packs the raw bytes itself.
 //   stage 1  k_map_fast     seed-and-extend in both directions + cooperative confirmation probes
 //   stage 2  k_map_windows  what stage 1 could not prove (repeats, > 16 nodes): one warp per read, every window looked up
@@ -675,8 +675,8 @@ static constexpr uint32_t LIST_SPREAD = 2;      // list-driven k_map_fast: every
 //   stage 3  k_map_generic  the exhaustive ASCII tier: any read length / alphabet
 static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                            const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                           uint64_t n_reads, ReadSlot* d_slots, const uint32_t* pre_list, const unsigned long long* pre_count) {
-    const bool pre_listed = pre_list != nullptr;
+                           uint64_t n_reads, ReadSlot* d_slots, const unsigned long long* pre_count) {
+    const bool pre_listed = pre_count != nullptr;
     if (n_reads == 0) return VSPE_OK;
     if (n_reads > 0xFFFFFFFFull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
     if (!pre_listed) {
@@ -684,14 +684,13 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
         VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, 8, c->stream));
     }
     IndexView v = c->index.view();
-    const uint32_t* in_list = pre_list;
     const unsigned long long* in_count = pre_count;
     const uint32_t* to_generic = c->worklist.p;                 // reads the ASCII tier must map
     const unsigned long long* to_generic_n = c->counters.p + CNT_WORK;
     const uint32_t grid = pre_listed ? (uint32_t)std::min<uint64_t>((n_reads * LIST_SPREAD + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 8)
                                      : (uint32_t)((n_reads + MF_THREADS - 1) / MF_THREADS);
 #define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
-                                                                              row_words, n_reads, in_list, in_count, LIST_SPREAD, d_slots, \
+                                                                              row_words, n_reads, in_count, LIST_SPREAD, d_slots, \
                                                                               c->worklist.p, c->counters.p)
     if (pre_listed) { if (cap <= 160) VSPE_MF(13, 16, true); else if (cap <= 256) VSPE_MF(19, 16, true); else VSPE_MF(23, 32, true); }
     else { if (cap <= 160) VSPE_MF(13, 16, false); else if (cap <= 256) VSPE_MF(19, 16, false); else VSPE_MF(23, 32, false); }
@@ -719,15 +718,15 @@ uint32_t map_fast_cap(uint32_t hint) { return hint <= 160 ? 160 : hint <= 256 ? 
 int map_reads_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                    uint64_t n_reads, ReadSlot* d_slots) {
     if (c->index.split_len > 320) return map_reads_generic(c, d_buf, d_seq_start, d_seq_end, n_reads, d_slots);
-    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, nullptr, nullptr, 0, map_fast_cap(c->read_len_hint), n_reads, d_slots, nullptr, nullptr);
+    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, nullptr, nullptr, 0, map_fast_cap(c->read_len_hint), n_reads, d_slots, nullptr);
 }
 
-// the reads k_walk left unresolved (d_list[0 .. *d_count)): full seed-and-extend kernel, then the
-// all-windows kernel, then the ASCII tier; results go to d_slots[r] for the listed r
+// the *d_count reads k_walk left unresolved (compact arrays): full seed-and-extend kernel, then the
+// all-windows kernel, then the ASCII tier; results go to d_slots[i], i < *d_count
 int map_reads_deferred(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_start, const uint64_t* d_seq_end,
                        const uint32_t* d_rows, const uint32_t* d_hdr, uint32_t row_words, uint32_t cap,
-                       uint64_t n_reads_cap, ReadSlot* d_slots, const uint32_t* d_list, const unsigned long long* d_count) {
-    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, row_words, cap, n_reads_cap, d_slots, d_list, d_count);
+                       uint64_t n_reads_cap, ReadSlot* d_slots, const unsigned long long* d_count) {
+    return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, row_words, cap, n_reads_cap, d_slots, d_count);
 }
 
 }  // namespace vspe

@@ -7,20 +7,28 @@
 // workloads: two or more sequencing errors, repeats, non-ACGT characters, very long reads) is
 // listed for the list-driven tiers of map_fast.cu / map_generic.cu.
 //
-// k_scan_rows -- ONE pass over the bytes, per 40 KiB tile (one CTA of 10 warps, 4 CTAs per SM, tiles
-// handed out by a ticket counter):
+// k_scan_rows -- ONE pass over the bytes, one 40 KiB tile per CTA (10 warps, 4 CTAs per SM); NO tile waits on
+// another one:
 //   1. one elected thread issues TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of the tile
 //      + a 16-byte front margin + a 512-byte back margin into shared memory;
 //   2. every lane tests its 16-byte vectors for bytes < 0x10 or >= 0x80 (two instructions per
 //      32-bit word); candidate vectors go to a per-warp queue (warp ballots) and only they get exact
-//      terminator masks (universal newlines: '\n', "\r\n" once, lone '\r'); a warp scan ranks them;
-//   3. warp totals + one block exchange give the tile's terminator count; a decoupled look-back
-//      over the tiles' status words gives the line number of the tile's first line;
-//   4. terminators with line%4==0 start a sequence line, line%4==1 end it -> per-tile read table;
-//   5. one thread per read packs the read the tile owns (its sequence line STARTS here) to 2 bits/base
-//      straight from the tile, 16 bases per step (SIMD-in-word ACGT validity test, 'N' flag), into a
-//      shared-memory row; each warp then copies its 32 rows to HBM with coalesced stores
-//      (48 / 64 / 80 bytes per read + a header word + the byte range).
+//      terminator masks (universal newlines: '\n', "\r\n" once, lone '\r'); a warp scan ranks them and
+//      every terminator's position is stored at its rank; warp totals + one block exchange merge the
+//      warps' tables into the tile's terminator table and give the tile's terminator count;
+//   3. which of the tile's lines are sequence lines depends on the number of lines before the tile
+//      (mod 4).  Instead of waiting for the earlier tiles (a decoupled look-back was 40 % of the
+//      kernel's warp time, profiles/r02_ncu_c4_block.txt) the tile GUESSES that phase from its own
+//      bytes ('@' / '+' at the starts of its first 32 lines), packs its reads into TILE-LOCAL slots
+//      and records {terminator count, guessed phase};
+//   4. one thread per read packs the read the tile owns (its sequence line STARTS here) to 2 bits/base
+//      straight from the tile, 16 bases per step (SIMD-in-word ACGT validity test, 'N' flag), and stores
+//      the row from registers with 16-byte stores (48 / 64 / 80 bytes per read + a header word).
+// k_tile_fix -- one CTA: exact prefix sum of the tiles' terminator counts -> first read of every tile,
+//      first tile of every k_walk block, terminator total; every guess is CHECKED against the exact
+//      phase and a tile that guessed wrong (text that merely looks like FASTQ structure) is listed;
+// k_scan_redo -- the listed tiles again with their exact phase (normally none): the results never
+//      depend on a guess.
 // k_walk -- one thread per read, 128-thread blocks, 8 blocks per SM (the walk is a chain of dependent
 // L2 accesses: it wants many warps and a large L1, which is why it is NOT fused into the scan kernel --
 // the fused variant was built, bit-exact, and 3x slower: 15 warps per SM, 31 % issue slots):
@@ -31,7 +39,8 @@
 //      stretch was entered.  ONE mismatching base is tolerated when the substitution-hit bit proves that
 //      the windows covering it have no posting.  The saturation predicate (:36-47, integer form) is
 //      applied as each stretch is booked;
-//   7. the kept node list is interned (link.cuh) and its handle stored; an unresolved read is listed.
+//   7. the kept node list is interned (link.cuh) and its handle stored; an unresolved read is copied (row,
+//      header, byte range) to the compact arrays the list-driven tiers work on.
 // Why this is exact: see map_fast.cu (a window is counted without a table access only if its text
 // equality and the uniq bit of that text window were both checked; it is skipped only if the
 // index build already looked that k-mer up and found nothing).
@@ -69,12 +78,10 @@ static constexpr int SM_MAXST = 16;                              // stretches (n
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t movemask4b(uint32_t cmp) { return ((cmp & 0x80808080u) * 0x00204081u) >> 28; }
 
-// terminator / crlf masks of one 16-byte vector held in registers; `valid` = bitmask of the
-// bytes that belong to the buffer; next/prev = the neighbouring bytes (0 if outside)
-__device__ __forceinline__ void masks_from_vec(uint4 v, uint32_t valid, uint32_t next_byte, uint32_t prev_byte,
-                                               bool& non_ascii, uint32_t& term, uint32_t& crlf) {
+// terminator mask of one 16-byte vector held in registers (universal newlines: '\n', '\r' unless a '\n' follows);
+// `valid` = bitmask of the bytes that belong to the buffer; next_byte = the byte after the vector (0 if outside)
+__device__ __forceinline__ void masks_from_vec(uint4 v, uint32_t valid, uint32_t next_byte, bool& non_ascii, uint32_t& term) {
     term = 0;
-    crlf = 0;
     if (valid == 0xFFFFu && ((v.x | v.y | v.z | v.w) & 0x80808080u)) non_ascii = true;
     uint32_t nl = movemask4b(__vcmpeq4(v.x, 0x0A0A0A0Au)) | (movemask4b(__vcmpeq4(v.y, 0x0A0A0A0Au)) << 4) |
                   (movemask4b(__vcmpeq4(v.z, 0x0A0A0A0Au)) << 8) | (movemask4b(__vcmpeq4(v.w, 0x0A0A0A0Au)) << 12);
@@ -91,7 +98,6 @@ __device__ __forceinline__ void masks_from_vec(uint4 v, uint32_t valid, uint32_t
         cr &= valid;
     }
     term = nl | (cr & ~((nl >> 1) | (next_byte == '\n' ? 0x8000u : 0u)));
-    crlf = nl & ((cr << 1) | (prev_byte == '\r' ? 1u : 0u));
 }
 
 struct ScanMapArgs {
@@ -99,20 +105,18 @@ struct ScanMapArgs {
     uint64_t n;                      // chunk bytes
     uint32_t head;                   // address of buf mod 16
     uint32_t n_tiles;
-    unsigned long long* status;      // look-back words, one per tile (zeroed)
-    unsigned int* ticket;
-    unsigned long long* total_out;   // terminators in the chunk
     uint64_t line_base;              // lines before this chunk
-    uint64_t rec_first;              // record number of slot 0 of the outputs
-    uint64_t n_slots;                // capacity of the per-read outputs
-    uint64_t* seq_start;             // [n_slots] chunk-relative byte range of the sequence line
-    uint64_t* seq_end;
-    uint32_t* rows;                  // [n_slots][row_words] packed read
-    uint32_t* hdr;                   // [n_slots] rlen | flags << 24
-    uint32_t row_words;              // 12, 16 or 20
+    unsigned long long* tile_info;   // [n_tiles] out: terminators | phase << 32 | overflow << 40
+    const unsigned long long* redo;  // list-driven launch: [*n_redo] tile | exact phase << 32
+    const unsigned long long* n_redo;
+    uint32_t* rows;                  // [n_tiles * tcap][row_words] packed reads, tile-local slots
+    uint32_t* hdr;                   // [n_tiles * tcap] rlen | SH_* flags | first base (tile-relative) << 16
+    uint32_t tcap;                   // slots per tile
     uint32_t cap;                    // longest read (bases) a packed row holds
     unsigned long long* counters;
 };
+// header word of a tile-local slot
+static constexpr uint32_t SH_RLEN = 0xFFFu, SH_N = 1u << 12, SH_BAD = 1u << 13, SH_LONG = 1u << 14;
 
 // The walk of step 6.  row: this thread's packed read (STRIDE words, zero padded); lst: its node list
 // column (entry i at lst[i * LS]).  Returns true when every window of the read is accounted for;
@@ -234,16 +238,24 @@ __device__ __forceinline__ bool walk_read(const IndexView& ix, uint32_t* row, co
     return true;
 }
 
-// One thread per read of the chunk: pair-skipping classes, else the walk; what it cannot prove is listed.
+// One thread per read of the chunk: pair-skipping classes, else the walk.  A read the walk cannot prove is copied
+// (row, header, byte range) to the compact arrays of the list-driven tiers.
 struct WalkArgs {
-    const uint32_t* rows;
+    const uint32_t* rows;              // tile-local slots written by k_scan_rows
     const uint32_t* hdr;
-    uint32_t row_words;
+    uint32_t row_words, tcap;
+    const uint32_t* r_first;           // [n_tiles + 1] chunk-local index of each tile's first read (k_tile_fix)
+    const uint32_t* blk_tile;          // [blocks] tile of the first read of each k_walk block
+    uint32_t head;                     // chunk start address mod 16 (tile t starts at buffer position t * SM_TILE - head)
     uint64_t n_slots;                  // capacity of the per-read arrays
-    const unsigned long long* total;   // terminators of the chunk (written by k_scan_rows)
+    const unsigned long long* total;   // terminators of the chunk (written by k_tile_fix)
     uint64_t line_base, rec_first;
     uint32_t* handles;
-    uint32_t* defer_list;
+    uint32_t* d_read;                  // deferred reads, compact: chunk-local read index,
+    uint32_t* d_hdr;                   //   rlen | PH_* flags,
+    uint32_t* d_rows;                  //   packed row,
+    uint64_t* d_start;                 //   chunk-relative byte range of the sequence line (~0: end not seen)
+    uint64_t* d_end;
     unsigned long long* defer_count;
     unsigned long long* counters;
 };
@@ -261,19 +273,26 @@ k_walk(const WalkArgs a, const IndexView ix, const LinkView lv) {
     const uint64_t n_reads = n_lines1 < a.n_slots ? n_lines1 : a.n_slots;
     const uint64_t r = (uint64_t)blockIdx.x * WK_THREADS + threadIdx.x;
     if (r >= n_reads) return;
+    // a tile overflowed: the host repeats the chunk on the plain path, nothing of this launch is used
+    if (*reinterpret_cast<const volatile unsigned long long*>(a.counters + CNT_ERR) & ERRF_TILE_FULL) return;
     if (r == 0) atomicAdd(&a.counters[CNT_FAST], (unsigned long long)n_reads);
-    const uint32_t h = __ldg(a.hdr + r);
-    const uint32_t rlen = h & 0xFFFFFF, L = ix.split_len;
+    // the read's slot: its tile (the block's first tile, or one of the next ones) and its index there
+    uint32_t t = __ldg(a.blk_tile + blockIdx.x);
+    uint32_t f0 = __ldg(a.r_first + t), f1 = __ldg(a.r_first + t + 1);
+    while ((uint32_t)r >= f1) { t++; f0 = f1; f1 = __ldg(a.r_first + t + 1); }
+    const uint64_t slot = (uint64_t)t * a.tcap + ((uint32_t)r - f0);
+    const uint32_t h = __ldg(a.hdr + slot);
+    const uint32_t rlen = h & SH_RLEN, L = ix.split_len;
     uint32_t handle = H_PENDING;
-    bool defer = (h & (PH_LONG | PH_BAD)) != 0;
-    if (!(h & PH_LONG)) {
-        if (h & PH_N) handle = H_N;                                    // 'N' before the length (PE_Inference.py:160-163)
+    bool defer = (h & (SH_LONG | SH_BAD)) != 0;
+    if (!(h & SH_LONG)) {
+        if (h & SH_N) handle = H_N;                                    // 'N' before the length (PE_Inference.py:160-163)
         else if (rlen < L) handle = H_SHORT;
     }
+    constexpr int NW = STRIDE - 3, XW = (NW + 3) / 4 * 4;
+    const uint4* src = reinterpret_cast<const uint4*>(a.rows + slot * a.row_words);
     if (handle == H_PENDING && !defer) {
         uint32_t* row = s_rows + threadIdx.x * STRIDE;
-        constexpr int NW = STRIDE - 3, XW = (NW + 3) / 4 * 4;
-        const uint4* src = reinterpret_cast<const uint4*>(a.rows + r * a.row_words);
         uint32_t x[XW];
 #pragma unroll
         for (int q = 0; q < XW / 4; q++) {
@@ -288,37 +307,38 @@ k_walk(const WalkArgs a, const IndexView ix, const LinkView lv) {
         if (walk_read<STRIDE, WK_THREADS>(ix, row, rlen, s_lst + threadIdx.x, n_kept)) handle = intern_list(lv, n_kept, s_lst + threadIdx.x, WK_THREADS);
         else defer = true;
     }
-    if (handle == H_PENDING && defer) a.defer_list[atomicAdd(a.defer_count, 1ull)] = (uint32_t)r;
+    if (handle == H_PENDING && defer) {
+        // (the walk may have reverse-complemented its copy of the row: the tiers get the row as it was scanned)
+        const unsigned long long d = atomicAdd(a.defer_count, 1ull);
+        a.d_read[d] = (uint32_t)r;
+        a.d_hdr[d] = rlen | ((h & SH_N) ? PH_N : 0u) | ((h & SH_BAD) ? PH_BAD : 0u) | ((h & SH_LONG) ? PH_LONG : 0u);
+        const uint64_t st = (uint64_t)t * SM_TILE + (h >> 16) - a.head;
+        a.d_start[d] = st;
+        a.d_end[d] = (h & SH_LONG) ? ~0ull : st + rlen;
+        uint4* dst = reinterpret_cast<uint4*>(a.d_rows + d * a.row_words);
+        for (uint32_t q = 0; 4 * q < a.row_words; q++) dst[q] = __ldg(src + q);
+    }
     a.handles[r] = handle;
 }
 
-static constexpr uint32_t SM_QUEUE_BYTES = SM_WARPS * SM_QCAP * 8;
-static constexpr uint32_t SM_SMEM = SM_FRONT + SM_TILE + SM_BACK + SM_MAXREC * 8 + SM_QUEUE_BYTES + 64;
+static constexpr int SM_MAXTERM = 4 * SM_MAXREC + 8;                  // terminators a tile may hold (else the chunk takes the plain path)
+static constexpr int SM_WTERM = 256;                                  // ... and a warp's 4 KiB share of it
+static constexpr uint32_t SM_SMEM = SM_FRONT + SM_TILE + SM_BACK + SM_MAXTERM * 2 + SM_WARPS * SM_WTERM * 2 + 64;
+static_assert(SM_WARPS * SM_QCAP <= SM_MAXTERM, "the candidate queues alias the terminator table");
+static_assert(SM_WARPS <= 32, "warp totals are scanned by one warp's lanes");
 
-template <int RW>                                                // row words in HBM: 12, 16 or 20 (a multiple of 4 >= cap / 16)
-__global__ void __launch_bounds__(SM_THREADS, VSPE_SM_MINB)
-k_scan_rows(const ScanMapArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+// One tile.  forced_phase < 0: the line phase of the tile (line number of its first line mod 4) is GUESSED from
+// the bytes -- k_tile_fix checks the guess against the exact prefix sum afterwards and lists the tile for a
+// second, exact launch if it was wrong; forced_phase >= 0: that phase is used as is.  parity: of the mbarrier.
+template <int RW>
+__device__ __forceinline__ void scan_tile(const ScanMapArgs& a, const uint32_t tile, const int forced_phase, const uint32_t parity,
+                                          uint8_t* smem, unsigned long long* s_bar, uint32_t* s_wtot) {
     uint8_t* s_bytes = smem;                                           // [SM_FRONT + SM_TILE + SM_BACK]
-    uint32_t* s_rs = reinterpret_cast<uint32_t*>(smem + SM_FRONT + SM_TILE + SM_BACK);   // read start (tile-relative)
-    uint32_t* s_re = s_rs + SM_MAXREC;                                 // read end
-    uint32_t* s_un = s_re + SM_MAXREC;                                 // candidate queues
-    uint32_t* s_qmk = s_un;                                            // [SM_WARPS][SM_QCAP] term | crlf << 16
-    uint16_t* s_qid = reinterpret_cast<uint16_t*>(s_qmk + SM_WARPS * SM_QCAP);   // vector index in the tile
-    uint16_t* s_qrk = s_qid + SM_WARPS * SM_QCAP;                      // rank of the vector's first terminator in the warp
-    __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ uint32_t s_wtot[SM_WARPS];
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_excl;
+    uint16_t* s_tp = reinterpret_cast<uint16_t*>(smem + SM_FRONT + SM_TILE + SM_BACK);   // [SM_MAXTERM] terminator positions by rank in the tile
+    uint16_t* s_qid = s_tp;                                            // [SM_WARPS][SM_QCAP] candidate vectors (dead before s_tp is written)
+    uint16_t* s_tpw = s_tp + SM_MAXTERM;                               // [SM_WARPS][SM_WTERM] terminator positions by rank in the warp's share
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 
-    if (threadIdx.x == 0) {
-        s_tile = atomicAdd(a.ticket, 1u);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const uint32_t tile = s_tile;
     // aligned coordinates: byte `off` of the aligned stream is buffer position off - head
     const uint64_t A = ((uint64_t)a.head + a.n + 15) & ~15ull;         // aligned stream length
     const uint64_t t_lo = (uint64_t)tile * SM_TILE;
@@ -327,14 +347,14 @@ k_scan_rows(const ScanMapArgs a) {
     const uint32_t s_off0 = tile == 0 ? SM_FRONT : 0;                  // where ld_lo lands in s_bytes
     if (threadIdx.x == 0) {
         const uint32_t bytes = (uint32_t)(ld_hi - ld_lo);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_bar)), "r"(bytes) : "memory");
         const uint8_t* src = a.buf - a.head + ld_lo;
         uint32_t done = 0;
         while (done < bytes) {
             const uint32_t part = min(bytes - done, 16384u);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_u32(s_bytes + s_off0 + done)),
-                         "l"(__cvta_generic_to_global(src + done)), "r"(part), "r"(smem_u32(&s_bar))
+                         "l"(__cvta_generic_to_global(src + done)), "r"(part), "r"(smem_u32(s_bar))
                          : "memory");
             done += part;
         }
@@ -343,7 +363,7 @@ k_scan_rows(const ScanMapArgs a) {
         uint32_t ok = 0;
         while (!ok) {
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(ok) : "r"(smem_u32(&s_bar)), "r"(0) : "memory");
+                         : "=r"(ok) : "r"(smem_u32(s_bar)), "r"(parity) : "memory");
         }
     }
     // tile byte j (0 <= j < SM_TILE) lives at s_bytes[SM_FRONT + j]; its buffer position is t_lo + j - head
@@ -356,12 +376,11 @@ k_scan_rows(const ScanMapArgs a) {
     };
 
     uint16_t* q_id = s_qid + wib * SM_QCAP;
-    uint32_t* q_mk = s_qmk + wib * SM_QCAP;
-    uint16_t* q_rk = s_qrk + wib * SM_QCAP;
+    uint16_t* tpw = s_tpw + wib * SM_WTERM;
     const bool interior = pos0 >= 1 && pos0 + SM_TILE + 16 <= nn;   // CTA-uniform
     const uint32_t lt = (1u << lane) - 1;
     uint32_t qn = 0, wcount = 0;
-    bool bad = false, q_over = false;
+    bool bad = false;
     // ---- M1: which 16-byte vectors can hold a terminator?  ('\n' and '\r' are < 0x10) -----------
     // Warp w owns tile bytes [w*4K, (w+1)*4K) as 8 coalesced 512-byte rows.  (x - 0x10) | x has bit 7
     // set in every byte that is < 0x10 or >= 0x80 (a borrow can only add false positives next to a true
@@ -386,16 +405,16 @@ k_scan_rows(const ScanMapArgs a) {
         }
         qn += __popc(bm);
     }
-    q_over = qn > (uint32_t)SM_QCAP;
-    if (q_over) qn = SM_QCAP;
+    bool w_over = qn > (uint32_t)SM_QCAP;
+    if (w_over) qn = SM_QCAP;
     __syncwarp();
-    // ---- M2: exact terminator / crlf masks of the candidates + their ranks inside the warp -----
+    // ---- M2: exact terminator masks of the candidates (universal newlines); every terminator's position goes to
+    // the warp's table at its rank (warp scan of the per-vector counts) ---------------------------------------
     for (uint32_t i0 = 0; i0 < qn; i0 += 32) {
         const uint32_t i = i0 + lane;
-        uint32_t term = 0, crlf = 0;
+        uint32_t term = 0, j = 0;
         if (i < qn) {
-            const uint32_t vid = q_id[i];
-            const uint32_t j = vid * 16;
+            j = (uint32_t)q_id[i] * 16;
             const uint4 v = *reinterpret_cast<const uint4*>(tb + j);
             uint32_t valid = 0xFFFFu;
             if (!interior) {
@@ -403,9 +422,7 @@ k_scan_rows(const ScanMapArgs a) {
                 if (p < 0) valid &= 0xFFFFu << (uint32_t)(-p);
                 if (p + 16 > nn) valid &= 0xFFFFu >> (uint32_t)(p + 16 - nn);
             }
-            masks_from_vec(v, valid, interior ? (uint32_t)tb[j + 16] : byte_at((int64_t)j + 16),
-                           interior ? (uint32_t)tb[(int)j - 1] : byte_at((int64_t)j - 1), bad, term, crlf);
-            q_mk[i] = term | (crlf << 16);
+            masks_from_vec(v, valid, interior ? (uint32_t)tb[j + 16] : byte_at((int64_t)j + 16), bad, term);
         }
         const uint32_t c = __popc(term);
         uint32_t inc = c;
@@ -414,123 +431,87 @@ k_scan_rows(const ScanMapArgs a) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
             if (lane >= (uint32_t)d) inc += y;
         }
-        if (i < qn) q_rk[i] = (uint16_t)(wcount + inc - c);
+        uint32_t rk = wcount + inc - c;
+        while (term) {
+            const uint32_t k = (uint32_t)__ffs((int)term) - 1;
+            term &= term - 1;
+            if (rk < (uint32_t)SM_WTERM) tpw[rk] = (uint16_t)(j + k);
+            rk++;
+        }
         wcount += __shfl_sync(0xFFFFFFFFu, inc, 31);
     }
     if (bad) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_NON_ASCII);
-    if (lane == 0) s_wtot[wib] = wcount | (q_over ? 0x80000000u : 0u);
-    for (uint32_t i = threadIdx.x; i < (uint32_t)SM_MAXREC; i += SM_THREADS) s_re[i] = 0xFFFFFFFFu;   // "line end not seen in this tile"
+    w_over |= wcount > (uint32_t)SM_WTERM;
+    if (lane == 0) s_wtot[wib] = wcount | (w_over ? 0x80000000u : 0u);
     __syncthreads();
-    uint32_t tile_total = 0, warp_base = 0;
-    bool any_over = false;
+    // warp totals -> this warp's first rank and the tile's terminator count (one scan over SM_WARPS lanes)
+    uint32_t tile_total, warp_base;
+    bool too_many;
+    {
+        const uint32_t xw = lane < (uint32_t)SM_WARPS ? s_wtot[lane] : 0u;
+        const uint32_t xc = xw & 0x7FFFFFFFu;
+        uint32_t inc = xc;
 #pragma unroll
-    for (int w = 0; w < SM_WARPS; w++) {
-        const uint32_t x = s_wtot[w];
-        any_over |= (x >> 31) != 0;
-        if (w < (int)wib) warp_base += x & 0x7FFFFFFFu;
-        tile_total += x & 0x7FFFFFFFu;
-    }
-    // ---- decoupled look-back (warp 0), 128 predecessors per hop -------------------------------
-    if (wib == 0) {
-        volatile unsigned long long* vs = a.status;
-        if (tile == 0) {
-            if (lane == 0) { vs[0] = LB_INC | tile_total; s_excl = 0; }
-        } else {
-            if (lane == 0) vs[tile] = LB_AGG | tile_total;
-            unsigned long long excl = 0;
-            int64_t look = (int64_t)tile - 1;                      // closest predecessor not yet summed
-            while (true) {
-                unsigned long long st[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int64_t idx = look - 4 * (int64_t)lane - k;
-                    st[k] = idx >= 0 ? vs[idx] : LB_INC;
-                }
-                while (true) {
-                    bool missing = false;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if ((st[k] >> 62) == 0) {
-                            st[k] = vs[look - 4 * (int64_t)lane - k];
-                            missing |= (st[k] >> 62) == 0;
-                        }
-                    }
-                    if (!__any_sync(0xFFFFFFFFu, missing)) break;
-                }
-                // this lane: sum up to and including its closest inclusive word, if it has one
-                unsigned long long c = 0;
-                bool has_inc = false;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (!has_inc) {
-                        c += st[k] & LB_VAL;
-                        has_inc = (st[k] >> 62) == 2;
-                    }
-                }
-                const uint32_t inc = __ballot_sync(0xFFFFFFFFu, has_inc);
-                const int first = inc ? __ffs((int)inc) - 1 : 32;
-                if ((int)lane > first) c = 0;
-                for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
-                excl += c;
-                if (inc) break;
-                look -= 128;
-            }
-            if (lane == 0) { vs[tile] = LB_INC | (excl + tile_total); s_excl = excl; }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
         }
-        if (lane == 0 && tile == a.n_tiles - 1) *a.total_out = s_excl + tile_total;
+        warp_base = __shfl_sync(0xFFFFFFFFu, inc - xc, wib);
+        tile_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        too_many = __any_sync(0xFFFFFFFFu, (xw >> 31) != 0) || tile_total > (uint32_t)SM_MAXTERM;
     }
+    if (!too_many)
+        for (uint32_t k = lane; k < wcount; k += 32) s_tp[warp_base + k] = tpw[k];
     __syncthreads();
-    const uint64_t base = a.line_base + s_excl;                        // line number of the tile's first line
-    // reads owned by this tile: sequence lines that START here = header terminators (line%4==0)
-    // in the tile; record numbers are consecutive from r_own0
-    const uint64_t r_own0 = (base + 3) >> 2;
-    const uint64_t last_line = base + tile_total;                      // one past the tile's last terminator
-    uint32_t n_own = (uint32_t)(((last_line + 3) >> 2) - r_own0);      // #{l in [base, last_line) : l%4 == 0}
+    // ---- line phase: terminator i of the tile ends line number base + i of the chunk's file; i ends a header line iff
+    // (base + i) % 4 == 0.  b = base % 4 is not known here (it needs every earlier tile): it is guessed from the first
+    // byte of the 32 lines that follow the tile's first terminators -- a header line starts with '@', a separator line
+    // with '+' -- as the smallest b without a contradiction.  Any guess is safe: k_tile_fix verifies it.
+    uint32_t b = 0;
+    if (forced_phase >= 0) b = (uint32_t)forced_phase;
+    else if (!too_many) {
+        uint32_t viol = 0;
+        if (lane < tile_total) {
+            const uint32_t j = (uint32_t)s_tp[lane] + 1;
+            if (pos0 + (int64_t)j < nn) {
+                const uint32_t ch = tb[j];
+                if (ch != '@') viol |= 1u << ((3u - lane) & 3u);       // the phase under which this line is a header
+                if (ch != '+') viol |= 1u << ((1u - lane) & 3u);       // ... a separator
+            }
+        }
+        viol = __reduce_or_sync(0xFFFFFFFFu, viol);
+        b = viol == 0xFu ? 0u : (uint32_t)__ffs((int)(~viol & 0xFu)) - 1;
+    }
+    // reads owned by this tile: sequence lines that START here, i.e. follow a header terminator i = h0, h0 + 4, ...
+    const uint32_t h0 = (4u - b) & 3u;
+    const uint32_t n_own = tile_total > h0 ? (tile_total - h0 + 3) >> 2 : 0u;
     const bool chunk_starts_in_seq = tile == 0 && (a.line_base & 3) == 1;   // chunk begins with a sequence line
     const uint32_t shift = chunk_starts_in_seq ? 1u : 0u;              // that read becomes local index 0
     const uint32_t n_local = n_own + shift;
-    const bool too_many = n_local > (uint32_t)SM_MAXREC || any_over;
+    too_many |= n_local > a.tcap;
+    if (threadIdx.x == 0) a.tile_info[tile] = (unsigned long long)tile_total | ((unsigned long long)b << 32) | (too_many ? 1ull << 40 : 0ull);
     if (too_many) {
         if (threadIdx.x == 0) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_TILE_FULL);
         return;
     }
-    if (chunk_starts_in_seq && threadIdx.x == 0) s_rs[0] = (uint32_t)a.head;   // buffer position 0, tile-relative
-    // ---- emission: every queue entry knows its rank -> line numbers -> read table ---------------
-    for (uint32_t i = lane; i < qn; i += 32) {
-        uint32_t mask = q_mk[i] & 0xFFFFu;
-        const uint32_t crlf = q_mk[i] >> 16;
-        const uint32_t j0 = (uint32_t)q_id[i] * 16;
-        uint64_t line = base + warp_base + q_rk[i];
-        while (mask) {
-            const int k = __ffs((int)mask) - 1;
-            mask &= mask - 1;
-            const uint32_t j = j0 + k;                                   // tile-relative terminator position
-            const uint32_t phase = (uint32_t)line & 3;
-            if (phase == 0) {
-                s_rs[(uint32_t)((line >> 2) - r_own0) + shift] = j + 1;
-            } else if (phase == 1) {
-                const uint64_t r = line >> 2;
-                const uint32_t e = ((crlf >> k) & 1) ? j - 1 : j;
-                if (r >= r_own0) s_re[(uint32_t)(r - r_own0) + shift] = e;
-                else if (chunk_starts_in_seq && r + 1 == r_own0) s_re[0] = e;
-                // (a sequence line that started in the previous tile is packed by that tile)
-            }
-            line++;
-        }
-    }
-    __syncthreads();
-    const uint64_t r_loc0 = r_own0 - shift;                            // record number of local index 0
-    // ---- pack: one thread per read, the row goes from registers to HBM with 16-byte stores -- no block
-    // barrier from here on.  16 bases = four words per step: code = (ascii >> 1) & 3; the only byte with
-    // code k is "ACTG"[k] = 0x41 + 2k (+15 when k == 2), which is the validity test.
+    // ---- pack: one thread per read, the row goes from registers to HBM with 16-byte stores.  16 bases = four words
+    // per step: code = (ascii >> 1) & 3; the only byte with code k is "ACTG"[k] = 0x41 + 2k (+15 when k == 2), which
+    // is the validity test.
     constexpr int NW = RW == 12 ? 10 : RW;                             // row words that can hold bases (cap / 16)
     for (uint32_t li = threadIdx.x; li < n_local; li += SM_THREADS) {
-        const uint64_t slot = r_loc0 + li - a.rec_first;
-        if (slot >= a.n_slots) { atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_SLOTS_FULL); continue; }
-        const uint32_t st = s_rs[li];
-        uint32_t en = s_re[li];
+        uint32_t st, en = 0xFFFFFFFFu;
+        if (li < shift) {
+            st = a.head;                                                // buffer position 0, tile-relative
+            if (tile_total > 0) en = s_tp[0];
+        } else {
+            const uint32_t i = h0 + 4 * (li - shift);
+            st = (uint32_t)s_tp[i] + 1;
+            if (i + 1 < tile_total) en = s_tp[i + 1];
+        }
         uint32_t h = 0;
-        if (en == 0xFFFFFFFFu) {
+        if (en != 0xFFFFFFFFu) {
+            if (en > st && tb[en] == '\n' && tb[en - 1] == '\r') en--;  // "\r\n": the '\r' is not part of the line
+        } else {
             // the line ends beyond the tile: first '\n' or '\r' in the back margin, if any (four bytes per step:
             // only a word with a byte < 0x10 is looked at byte by byte)
             for (uint32_t j = SM_TILE; j < (uint32_t)(SM_TILE + SM_BACK) && en == 0xFFFFFFFFu; j += 4) {
@@ -542,10 +523,10 @@ k_scan_rows(const ScanMapArgs a) {
                 }
                 if (pos0 + (int64_t)j + 4 > nn) break;
             }
-            if (en == 0xFFFFFFFFu) h |= PH_LONG;
+            if (en == 0xFFFFFFFFu) h |= SH_LONG;
         }
-        uint32_t rlen = (h & PH_LONG) ? 0u : en - st;
-        if (rlen > a.cap) { h |= PH_LONG; rlen = 0; }
+        uint32_t rlen = (h & SH_LONG) ? 0u : en - st;
+        if (rlen > a.cap) { h |= SH_LONG; rlen = 0; }
         const uint32_t a0 = SM_FRONT + st;                              // offset of the first base in s_bytes
         const uint32_t* p = reinterpret_cast<const uint32_t*>(s_bytes + (a0 & ~3u));
         const uint32_t sh = (a0 & 3) * 8;
@@ -596,75 +577,207 @@ k_scan_rows(const ScanMapArgs a) {
                 const uint32_t vm = left >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - left)));
                 const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
                 const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
-                uint32_t bad = (expect ^ c) & vm;                       // non-zero bytes = invalid characters
-                if (bad) {
+                uint32_t badm = (expect ^ c) & vm;                      // non-zero bytes = invalid characters
+                if (badm) {
                     for (int k = 0; k < 4; k++)
-                        if ((bad >> (8 * k)) & 0xFF) { if (((c >> (8 * k)) & 0xFF) == 'N') hasN = true; else badc = true; }
+                        if ((badm >> (8 * k)) & 0xFF) { if (((c >> (8 * k)) & 0xFF) == 'N') hasN = true; else badc = true; }
                 }
             }
-            h |= (hasN ? PH_N : 0) | (badc ? PH_BAD : 0);
+            h |= (hasN ? SH_N : 0) | (badc ? SH_BAD : 0);
         }
-        h |= rlen;
+        const uint64_t slot = (uint64_t)tile * a.tcap + li;
         uint4* dst = reinterpret_cast<uint4*>(a.rows + slot * RW);
 #pragma unroll
         for (int v = 0; v < RW; v += 4) dst[v >> 2] = make_uint4(rw[v], rw[v + 1], rw[v + 2], rw[v + 3]);
-        a.hdr[slot] = h;
-        a.seq_start[slot] = (uint64_t)((int64_t)st + pos0);            // chunk-relative start
-        a.seq_end[slot] = en == 0xFFFFFFFFu ? ~0ull : (uint64_t)((int64_t)en + pos0);
+        a.hdr[slot] = h | rlen | (st << 16);
     }
 }
 
-// Both kernels over a device-resident chunk: k_scan_rows, then k_walk over up to n_slots reads (the walk
-// kernel reads the chunk's terminator count on the device, so no host synchronisation in between).
+// k_scan_rows: one tile per CTA, no tile waits on another.  k_scan_redo: the tiles k_tile_fix listed, with their exact phase
+// (a fixed grid walks the device-side list; normally it is empty).
+template <int RW>                                                // row words in HBM: 12, 16 or 20 (a multiple of 4 >= cap / 16)
+__global__ void __launch_bounds__(SM_THREADS, VSPE_SM_MINB)
+k_scan_rows(const ScanMapArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_wtot[SM_WARPS];
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t tile = blockIdx.x;
+    scan_tile<RW>(a, tile, tile == 0 ? (int)(a.line_base & 3) : -1, 0u, smem, &s_bar, s_wtot);
+}
+
+template <int RW>
+__global__ void __launch_bounds__(SM_THREADS, VSPE_SM_MINB)
+k_scan_redo(const ScanMapArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_wtot[SM_WARPS];
+    const unsigned long long n = *a.n_redo;
+    if (blockIdx.x >= n) return;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    for (unsigned long long i = blockIdx.x; i < n; i += gridDim.x, parity ^= 1u) {
+        const unsigned long long e = a.redo[i];
+        scan_tile<RW>(a, (uint32_t)e, (int)((e >> 32) & 3), parity, smem, &s_bar, s_wtot);
+        __syncthreads();                                               // the tile buffer and the tables are reused by the next round
+    }
+}
+
+// Exact line numbers for every tile from the tiles' terminator counts: k_tile_sum adds up 1024 tiles per CTA,
+// k_tile_fix (same grid) turns the sums before its CTA into its base, scans its 1024 tiles and writes
+//   r_first[t]   chunk-local index of the first read tile t owns (r_first[n_tiles]: one past the last read),
+//   blk_tile[b]  the tile that holds read 128 b (where k_walk block b starts looking),
+//   redo list    tiles whose guessed phase differs from the exact one,
+//   total        terminators of the chunk.
+struct TileFixArgs {
+    const unsigned long long* tile_info;
+    uint32_t n_tiles;
+    uint64_t line_base, rec_first;
+    unsigned long long* part;          // [ceil(n_tiles / 1024)] terminators per CTA
+    uint32_t* r_first;
+    uint32_t* blk_tile;
+    uint32_t n_blk;
+    unsigned long long* redo;
+    unsigned long long* n_redo;        // zeroed before the launch
+    unsigned long long* total;
+};
+
+__device__ __forceinline__ unsigned long long block_sum_1024(unsigned long long x, unsigned long long* s_warp) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+    __syncthreads();
+    if (lane == 0) s_warp[wid] = x;
+    __syncthreads();
+    unsigned long long t = 0;
+    for (uint32_t w = 0; w < 32; w++) t += s_warp[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(1024)
+k_tile_sum(const TileFixArgs a) {
+    __shared__ unsigned long long s_warp[32];
+    const uint32_t t = blockIdx.x * 1024 + threadIdx.x;
+    const unsigned long long x = t < a.n_tiles ? (unsigned long long)(uint32_t)a.tile_info[t] : 0ull;
+    const unsigned long long tot = block_sum_1024(x, s_warp);
+    if (threadIdx.x == 0) a.part[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024)
+k_tile_fix(const TileFixArgs a) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_scan[32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // terminators before this CTA's tiles (and, in the last CTA, the chunk's total)
+    unsigned long long before = 0;
+    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += 1024) before += a.part[i];
+    before = block_sum_1024(before, s_warp);
+    const uint32_t t = blockIdx.x * 1024 + threadIdx.x;
+    const unsigned long long info = t < a.n_tiles ? a.tile_info[t] : 0ull;
+    const uint32_t tot = (uint32_t)info, ph = (uint32_t)(info >> 32) & 3u;
+    unsigned long long inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += y;
+    }
+    if (lane == 31) s_scan[wid] = inc;
+    __syncthreads();
+    unsigned long long wbase = 0;
+    for (uint32_t w = 0; w < wid; w++) wbase += s_scan[w];
+    if (t >= a.n_tiles) return;
+    const unsigned long long run = before + wbase + inc - tot;         // terminators before tile t
+    const uint64_t base = a.line_base + run;                           // line number of the tile's first line
+    const uint32_t shift = (t == 0 && (a.line_base & 3) == 1) ? 1u : 0u;
+    const uint32_t rf = (uint32_t)(((base + 3) >> 2) - shift - a.rec_first);
+    const uint32_t rn = (uint32_t)(((base + tot + 3) >> 2) - a.rec_first);       // = r_first[t + 1]
+    a.r_first[t] = rf;
+    if (t != 0 && ph != ((uint32_t)base & 3u)) a.redo[atomicAdd(a.n_redo, 1ull)] = (unsigned long long)t | ((unsigned long long)(base & 3) << 32);
+    for (uint32_t bk = (rf + WK_THREADS - 1) / WK_THREADS; bk < a.n_blk && bk * WK_THREADS < rn; bk++) a.blk_tile[bk] = t;
+    if (t + 1 == a.n_tiles) {
+        a.r_first[t + 1] = rn;
+        *a.total = run + tot;
+    }
+}
+
+// The default path over a device-resident chunk: k_scan_rows -> k_tile_fix -> k_scan_redo -> k_walk over up to n_slots
+// reads (every size the later kernels need is read on the device, so there is no host synchronisation in between).
 int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots, uint32_t* d_handles,
-             uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t* d_defer_list,
              unsigned long long* d_defer_count, uint32_t row_words, uint32_t cap) {
     if (n == 0) return VSPE_OK;
     const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
     const uint64_t n_tiles = (n + head + SM_TILE - 1) / SM_TILE;
     if (n_tiles > 0x7FFFFFFFull) { set_error("buffer too large for one scan launch"); return VSPE_ERR_LIMIT; }
     if (n_slots > 0xFFFFFFF0ull) { set_error("more than 2^32 reads in one chunk"); return VSPE_ERR_LIMIT; }
-    VSPE_TRY(c->tile_base_m[m].reserve(n_tiles + 4));
-    unsigned long long* status = reinterpret_cast<unsigned long long*>(c->tile_base_m[m].p);
-    VSPE_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 4) * 8, c->stream));
+    MateBuf& mb = c->mate[m];
+    // slots per tile: four times what a tile holds when every read has the hinted length (shorter reads, e.g. trimmed
+    // ones, make more records per tile; the slots are address space, only the used ones are ever touched); a tile that
+    // still overflows sends the chunk to the plain path
+    uint32_t tcap = 4 * (SM_TILE / (2 * std::max<uint32_t>(c->read_len_hint, 1) + 6) + 2);
+    tcap = std::min<uint32_t>((tcap + 7) & ~7u, SM_MAXREC);
+    const uint64_t n_blk = (n_slots + WK_THREADS - 1) / WK_THREADS;
+    VSPE_TRY(mb.rec.rows.reserve(n_tiles * tcap * row_words));
+    VSPE_TRY(mb.rec.hdr.reserve(n_tiles * tcap));
+    const uint64_t n_part = (n_tiles + 1023) / 1024;
+    VSPE_TRY(c->tile_base_m[m].reserve(2 * n_tiles + 4 + n_part));      // tile_info, redo list, redo count, total, per-CTA sums
+    VSPE_TRY(c->tile_idx_m[m].reserve(n_tiles + 1 + n_blk));            // r_first, blk_tile
+    VSPE_TRY(mb.rec.seq_start.reserve(n_slots + 2));                    // compact arrays of the deferred reads
+    VSPE_TRY(mb.rec.seq_end.reserve(n_slots + 2));
+    VSPE_TRY(mb.d_hdr.reserve(n_slots + 2));
+    VSPE_TRY(mb.d_rows.reserve((n_slots + 2) * row_words));
+    VSPE_TRY(c->defer_m[m].reserve(n_slots + 2));
+    unsigned long long* info = reinterpret_cast<unsigned long long*>(c->tile_base_m[m].p);
     ScanMapArgs a;
-    a.buf = d_buf; a.n = n; a.head = head; a.n_tiles = (uint32_t)n_tiles; a.status = status;
-    a.ticket = reinterpret_cast<unsigned int*>(status + n_tiles + 1);
-    a.total_out = status + n_tiles + 2;
-    a.line_base = line_base; a.rec_first = rec_first; a.n_slots = n_slots;
-    a.seq_start = d_seq_start; a.seq_end = d_seq_end; a.rows = d_rows; a.hdr = d_hdr;
-    a.row_words = row_words; a.cap = cap; a.counters = c->counters.p;
+    a.buf = d_buf; a.n = n; a.head = head; a.n_tiles = (uint32_t)n_tiles; a.line_base = line_base;
+    a.tile_info = info; a.redo = info + n_tiles; a.n_redo = info + 2 * n_tiles;
+    a.rows = mb.rec.rows.p; a.hdr = mb.rec.hdr.p; a.tcap = tcap; a.cap = cap; a.counters = c->counters.p;
+    TileFixArgs f;
+    f.tile_info = info; f.n_tiles = (uint32_t)n_tiles; f.line_base = line_base; f.rec_first = rec_first;
+    f.r_first = c->tile_idx_m[m].p; f.blk_tile = f.r_first + n_tiles + 1; f.n_blk = (uint32_t)n_blk;
+    f.redo = info + n_tiles; f.n_redo = info + 2 * n_tiles; f.total = info + 2 * n_tiles + 1; f.part = info + 2 * n_tiles + 4;
     if (!c->scan_map_attr_set) {
         VSPE_CUDA(cudaFuncSetAttribute(k_scan_rows<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
         VSPE_CUDA(cudaFuncSetAttribute(k_scan_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
         VSPE_CUDA(cudaFuncSetAttribute(k_scan_rows<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_redo<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_redo<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+        VSPE_CUDA(cudaFuncSetAttribute(k_scan_redo<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
         for (auto& evs : c->ev_scan) for (auto& e : evs) if (!e) VSPE_CUDA(cudaEventCreate(&e));
         c->scan_map_attr_set = true;
     }
-    // both kernels are timed on their own (CUDA events on the launching stream; two launches may be in flight)
+    VSPE_CUDA(cudaMemsetAsync(info + 2 * n_tiles, 0, 16, c->stream));
+    // both big kernels are timed on their own (CUDA events on the launching stream; two launches may be in flight)
     const int k = c->scan_map_events & 1;
-    auto launch_scan = [&]() {
-        if (row_words == 12) k_scan_rows<12><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
-        else if (row_words == 16) k_scan_rows<16><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
-        else k_scan_rows<20><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
-    };
-    if (c->opt_dbg_scan_twice) {
-        // measurement aid: the timed launch below then finds every predecessor's inclusive word already published
-        // (same results), i.e. it shows the kernel without the look-back wait
-        launch_scan();
-        VSPE_LAUNCH_CHECK(c);
-        VSPE_CUDA(cudaMemsetAsync(a.ticket, 0, 4, c->stream));
-    }
     VSPE_CUDA(cudaEventRecord(c->ev_scan[0][2 * k], c->stream));
-    launch_scan();
+    if (row_words == 12) k_scan_rows<12><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    else if (row_words == 16) k_scan_rows<16><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    else k_scan_rows<20><<<(uint32_t)n_tiles, SM_THREADS, SM_SMEM, c->stream>>>(a);
     VSPE_LAUNCH_CHECK(c);
     VSPE_CUDA(cudaEventRecord(c->ev_scan[0][2 * k + 1], c->stream));
+    k_tile_sum<<<(uint32_t)n_part, 1024, 0, c->stream>>>(f);
+    VSPE_LAUNCH_CHECK(c);
+    k_tile_fix<<<(uint32_t)n_part, 1024, 0, c->stream>>>(f);
+    VSPE_LAUNCH_CHECK(c);
+    const uint32_t redo_grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * VSPE_SM_MINB);
+    if (row_words == 12) k_scan_redo<12><<<redo_grid, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    else if (row_words == 16) k_scan_redo<16><<<redo_grid, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    else k_scan_redo<20><<<redo_grid, SM_THREADS, SM_SMEM, c->stream>>>(a);
+    VSPE_LAUNCH_CHECK(c);
     WalkArgs w;
-    w.rows = d_rows; w.hdr = d_hdr; w.row_words = row_words; w.n_slots = n_slots; w.total = a.total_out;
-    w.line_base = line_base; w.rec_first = rec_first; w.handles = d_handles; w.defer_list = d_defer_list; w.defer_count = d_defer_count; w.counters = c->counters.p;
+    w.rows = mb.rec.rows.p; w.hdr = mb.rec.hdr.p; w.row_words = row_words; w.tcap = tcap; w.r_first = f.r_first; w.blk_tile = f.blk_tile;
+    w.head = head; w.n_slots = n_slots; w.total = f.total; w.line_base = line_base; w.rec_first = rec_first; w.handles = d_handles;
+    w.d_read = c->defer_m[m].p; w.d_hdr = mb.d_hdr.p; w.d_rows = mb.d_rows.p; w.d_start = mb.rec.seq_start.p; w.d_end = mb.rec.seq_end.p;
+    w.defer_count = d_defer_count; w.counters = c->counters.p;
     const IndexView ix = c->index.view();
     const LinkView lv = link_view(c);
-    const uint32_t grid = (uint32_t)((n_slots + WK_THREADS - 1) / WK_THREADS);
+    const uint32_t grid = (uint32_t)n_blk;
     VSPE_CUDA(cudaEventRecord(c->ev_scan[1][2 * k], c->stream));
     if (cap <= 160) k_walk<13><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
     else if (cap <= 256) k_walk<19><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
@@ -676,11 +789,11 @@ int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base
     return VSPE_OK;
 }
 
-// terminators of the chunk the last scan_map launch covered (device word, read after a stream sync)
+// {tiles listed for k_scan_redo, terminators of the chunk} of the last scan_map launch (two device words, read after a stream sync)
 const unsigned long long* scan_map_total_ptr(Ctx* c, int m, uint64_t n, const uint8_t* d_buf) {
     const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(d_buf) & 15);
     const uint64_t n_tiles = (n + head + SM_TILE - 1) / SM_TILE;
-    return reinterpret_cast<unsigned long long*>(c->tile_base_m[m].p) + n_tiles + 2;
+    return reinterpret_cast<unsigned long long*>(c->tile_base_m[m].p) + 2 * n_tiles;
 }
 
 // fold the durations of the finished k_scan_rows / k_walk launches into the stats (call after a stream sync)

@@ -271,10 +271,10 @@ struct Index {
 
 // per-mate record table produced by K1 for one chunk
 struct Records {
-    DevBuf<uint64_t> seq_start;   // chunk-relative byte offset of the 2nd line of each record
+    DevBuf<uint64_t> seq_start;   // chunk-relative byte offset of the 2nd line of each record (default path: of each deferred read)
     DevBuf<uint64_t> seq_end;     // one past its last content byte (~0: beyond the scan margin)
-    DevBuf<uint32_t> rows;        // [n][row_words] 2-bit packed reads written by k_scan_rows
-    DevBuf<uint32_t> hdr;         // [n] rlen | flags << 24
+    DevBuf<uint32_t> rows;        // [tiles][slots per tile][row_words] 2-bit packed reads written by k_scan_rows
+    DevBuf<uint32_t> hdr;         // [tiles][slots per tile] rlen | SH_* flags | first base << 16 (scan_map.cu)
 };
 static constexpr uint32_t PH_N = 1u << 24, PH_BAD = 2u << 24, PH_LONG = 4u << 24;
 
@@ -296,7 +296,6 @@ int device_scan_u64(Ctx* c, const unsigned long long* in, unsigned long long* ou
 
 // K1+K2+K4 fused (scan_map.cu): one pass over a device-resident chunk -> handles + the unresolved reads, packed and listed
 int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base, uint64_t rec_first, uint64_t n_slots, uint32_t* d_handles,
-             uint64_t* d_seq_start, uint64_t* d_seq_end, uint32_t* d_rows, uint32_t* d_hdr, uint32_t* d_defer_list,
              unsigned long long* d_defer_count, uint32_t row_words, uint32_t cap);
 const unsigned long long* scan_map_total_ptr(Ctx* c, int m, uint64_t n, const uint8_t* d_buf);
 void scan_map_account(Ctx* c);
