@@ -61,6 +61,7 @@ typedef struct vspe_stats {
     uint32_t n_k_walk;
     uint32_t scan_redo_tiles; /* tiles k_scan_redo packed again because their guessed line phase was wrong  */
     uint32_t reserved0;
+    uint64_t reads_memo;      /* reads whose node list came from the read memo (an identical read was walked before) */
 } vspe_stats;
 
 typedef struct vspe_ctx vspe_ctx;
@@ -176,6 +177,7 @@ void vspe_free_pinned(void* p);
  *   "scan_two_pass"  1: same as scan_mode 2
  *   "force_generic"  1: every read through the exhaustive ASCII tier (the reference's loop as is)
  *   "subst"          0: do not build / use the substitution-hit bitmap
+ *   "memo"           0: do not use the read memo (every read is walked, as if no read repeated)
  *   "tier_overlap"   0: vspe_count_device maps the two mates strictly one after the other (default 1: the list-driven
  *                    tiers of one mate run on a second stream beside the scan of the other)
  *   "pair_cap_log2"  log2 of the first size of the pair table (default 21 = 32 MB, grown on demand); 0: size it by

@@ -20,6 +20,7 @@ pytestmark = pytest.mark.gpu
 VARIANTS = [
     {"scan_mode": 0},                                   # default: k_scan_rows + k_walk + list-driven tiers
     {"scan_mode": 0, "subst": 0},                       # ... without the substitution-hit bitmap (no error tolerance in the walk)
+    {"scan_mode": 0, "memo": 0},                        # ... without the read memo (every read walked)
     {"scan_mode": 1},                                   # look-back record scan + raw-byte seed-and-extend kernel
     {"scan_mode": 1, "subst": 0},
     {"scan_mode": 1, "force_generic": 1},               # exhaustive ASCII tier only
@@ -622,3 +623,46 @@ def test_short_first_records_do_not_push_longer_reads_to_the_exhaustive_tier():
     assert stats["reads_generic"] == 0
     for k, v in ostats.items():
         assert stats[k] == v
+
+
+def _records(fq):
+    lines = bytes(fq).split(b"\n")
+    assert lines[-1] == b""
+    return [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines) - 1, 4)]
+
+
+def test_read_memo_is_exact_and_used():
+    """Repeated reads (deep coverage) take their node list from the read memo; the counts are those of walking every
+    read, within one call, over several calls on the same context, and after a reset (which forgets the memo)."""
+    for name in ("C2", "C4"):
+        cfg = synth.CONFIGS[name]
+        g, f, r = synth.generate(cfg, pairs=1500)
+        rf, rr = _records(f), _records(r)
+        order = np.random.default_rng(5).permutation(np.repeat(np.arange(len(rf)), 40))
+        f2, r2 = b"".join(rf[i] for i in order), b"".join(rr[i] for i in order)
+        gfa = g.to_gfa()
+        onode, oshort, ostats = c_oracle.run(gfa, f2, r2, cfg.k)
+        ids, seqs = pe_inference.parse_gfa_nodes(gfa)
+        for memo in (1, 0):
+            with pe_inference.PEIndex(seqs, cfg.k) as ix:
+                ix.set_option("memo", memo)
+                ix.count_host(f2, r2)
+                node, short = ix.matrices()
+                st = ix.stats()
+                assert np.array_equal(node.astype(np.int64), onode) and np.array_equal(short.astype(np.int64), oshort), (name, memo)
+                for k, v in ostats.items():
+                    assert st[k] == v, (name, memo, k)
+                # a second call adds the same counts again, now with a warm memo (a round of reads asks the memo before
+                # that round's walks fill it, and this input is a single round); a reset starts over
+                ix.count_host(f2, r2)
+                node2, short2 = ix.matrices()
+                assert np.array_equal(node2.astype(np.int64), 2 * onode) and np.array_equal(short2.astype(np.int64), 2 * oshort), (name, memo)
+                st2 = ix.stats()
+                if memo:
+                    assert st2["reads_memo"] > len(order), (name, st2["reads_memo"])     # more than half of the second call's 2 x len(order) reads
+                else:
+                    assert st2["reads_memo"] == 0
+                ix.reset()
+                ix.count_host(f2, r2)
+                node3, short3 = ix.matrices()
+                assert np.array_equal(node3.astype(np.int64), onode) and np.array_equal(short3.astype(np.int64), oshort), (name, memo)

@@ -1,0 +1,10 @@
+O=gpurun_out/r2u; mkdir -p $O
+(timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -25) > $O/tests.log 2>&1
+b() { tag=$1; shift; timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e "$@" > $O/bench_$tag.json 2> $O/bench_$tag.err; }
+b c4
+b c4_memo0 --opt memo=0
+b c3 --config C3
+b c2 --config C2
+b c5 --config C5 --steps 2
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $O/launches_c4.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $O/launches_bench.log 2>&1
+ls $O

@@ -26,7 +26,7 @@ class Stats(ctypes.Structure):
         "n_kmers", "table_slots", "reads_fast", "reads_generic", "n_keys", "kernel_launches")] + \
         [(n, ctypes.c_float) for n in ("ms_index", "ms_h2d", "ms_scan", "ms_map", "ms_count", "ms_total", "ms_k_scan_rows")] + \
         [("n_k_scan_rows", ctypes.c_uint32), ("ms_k_walk", ctypes.c_float), ("n_k_walk", ctypes.c_uint32),
-         ("scan_redo_tiles", ctypes.c_uint32), ("reserved0", ctypes.c_uint32)]
+         ("scan_redo_tiles", ctypes.c_uint32), ("reserved0", ctypes.c_uint32), ("reads_memo", ctypes.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -284,7 +284,12 @@ static int finish_pairs(Ctx* c, const MateStream& f, const MateStream& r) {
     c->err_flags_fresh = false;
     VSPE_TRY(count_links(c, c->mate[0].handles.p, c->mate[1].handles.p, total));
     VSPE_CUDA(cudaEventRecord(e1, c->stream));
+    unsigned long long h_fast = 0, h_hit = 0;
+    VSPE_CUDA(cudaMemcpyAsync(&h_fast, c->counters.p + CNT_FAST, 8, cudaMemcpyDeviceToHost, c->stream));
+    VSPE_CUDA(cudaMemcpyAsync(&h_hit, c->counters.p + CNT_MEMO_HIT, 8, cudaMemcpyDeviceToHost, c->stream));
     VSPE_CUDA(cudaStreamSynchronize(c->stream));
+    // an input that does not repeat reads (shallow coverage of a large graph) only pays for the memo: stop asking it
+    if (c->opt_memo && !c->memo_off && h_fast >= (4ull << 20) && h_hit * 20 < h_fast) c->memo_off = true;
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->stats.ms_count += ms;
@@ -1045,6 +1050,7 @@ int vspe_get_stats(vspe_ctx* c, vspe_stats* out) {
     c->stats.n_keys = h[CNT_KEYS];
     c->stats.reads_fast = h[CNT_FAST] - h[CNT_BAILED];
     c->stats.reads_generic = h[CNT_GENERIC];
+    c->stats.reads_memo = h[CNT_MEMO_HIT];
     c->stats.kernel_launches = c->launches;
     *out = c->stats;
     return VSPE_OK;
@@ -1389,6 +1395,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
         }
     }
     else if (!strcmp(name, "tier_overlap")) c->opt_tier_overlap = value;
+    else if (!strcmp(name, "memo")) c->opt_memo = value;
     else if (!strcmp(name, "pair_cap_log2")) c->opt_pair_cap_log2 = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_counters")) {

@@ -22,6 +22,8 @@ enum Counter {
     CNT_EXP,                 // weighted keys the current batch expands to
     CNT_EXP_CURSOR,          // ... and the emit cursor over them
     CNT_B_USED, CNT_B_N, CNT_B_SHORT,   // pair classes of the current batch (added to USED / N / SHORT once the batch is accepted)
+    CNT_WALK, CNT_WALK1,     // per mate: reads k_memo listed for k_walk
+    CNT_MEMO_HIT,            // reads whose handle came from the read memo
     CNT_COUNT_
 };
 static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16, ERRF_LISTS_FULL = 32, ERRF_INTERNAL = 64, ERRF_PAIRS_FULL = 128;
@@ -70,6 +72,10 @@ struct Ctx {
     DevBuf<uint32_t> defer_list;       // tier scratch: reads k_map_windows leaves for the ASCII tier
     DevBuf<uint32_t> defer_m[2];       // per mate: reads k_walk left unresolved
     DevBuf<uint64_t> tile_base_m[2];   // per mate: k_scan_rows' tile records, k_tile_fix's redo list + count, terminator total
+    DevBuf<uint2> walk_list_m[2];      // per mate: {read, slot} of the reads k_memo left for k_walk
+    DevBuf<uint32_t> memo;             // read memo: packed row -> list handle (scan_map.cu)
+    uint32_t memo_stride = 0;          // words per memo entry (4 + row words)
+    bool memo_off = false;             // switched off for this index: the input does not repeat reads
     DevBuf<uint32_t> tile_idx_m[2];    // per mate: first read of every tile, first tile of every k_walk block (k_tile_fix)
     // K5/K6: list table + pair table (link.cuh)
     DevBuf<ListRec> list_recs;         // [list_T] table part + [list_ov_cap] private records
@@ -96,6 +102,7 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_memo = 1;              // ask / fill the read memo (scan_map.cu)
     int64_t opt_tier_overlap = 1;      // device-resident calls: run one mate's list-driven tiers beside the other mate's scan
     int64_t opt_pair_cap_log2 = 21;    // first size of the pair table (log2 entries); 0: size it by the pairs of the batch
     int64_t opt_stage_threads = 8;     // host threads that copy an unpinned input chunk into the pinned staging buffer

@@ -64,6 +64,9 @@ int link_setup(Ctx* c) {
 int link_reset(Ctx* c) {
     if (!c->list_recs.p) return VSPE_OK;
     VSPE_CUDA(cudaMemsetAsync(c->list_recs.p, 0, (uint64_t)c->list_T * sizeof(ListRec), c->stream));
+    // the read memo holds list handles: it is forgotten with the lists
+    if (c->memo.p) VSPE_CUDA(cudaMemsetAsync(c->memo.p, 0, c->memo.cap * sizeof(uint32_t), c->stream));
+    c->memo_off = false;
     return VSPE_OK;                                         // (the counters are zeroed by vspe_reset)
 }
 

@@ -122,7 +122,7 @@ static constexpr uint32_t SH_RLEN = 0xFFFu, SH_N = 1u << 12, SH_BAD = 1u << 13, 
 // column (entry i at lst[i * LS]).  Returns true when every window of the read is accounted for;
 // n_kept nodes that pass the saturation predicate are then at the front of the column.
 template <int STRIDE, int LS>
-__device__ __forceinline__ bool walk_read(const IndexView& ix, uint32_t* row, const uint32_t rlen, uint32_t* lst, uint32_t& n_kept) {
+__device__ __forceinline__ bool walk_read(const IndexView& ix, uint32_t* row, const uint32_t rlen, uint32_t* lst, uint32_t& n_kept, bool& clean) {
     constexpr int NW = STRIDE - 3;
     const uint32_t L = ix.split_len;
     const int npos = (int)(rlen - L + 1);
@@ -235,22 +235,97 @@ __device__ __forceinline__ bool walk_read(const IndexView& ix, uint32_t* row, co
     }
     if (!resolved) return false;
     n_kept = n_front;
+    clean = !err;                                              // every base of the read equals the graph's text
     return true;
 }
 
-// One thread per read of the chunk: pair-skipping classes, else the walk.  A read the walk cannot prove is copied
-// (row, header, byte range) to the compact arrays of the list-driven tiers.
+// ---------------------------------------------------------------------------------------------
+// Read memo.  Deep sequencing (what a strain-level viral graph is built from) repeats reads: every read
+// without a sequencing error is a substring of a strain, and there are only about 2 x genome length x strains
+// distinct ones, each seen coverage / read length times.  The memo is a hash table packed row -> list handle,
+// filled by k_walk with reads it resolved WITHOUT tolerating an error (so it stays bounded by the graph, not by
+// the input) and asked by k_memo before any walk.  A hit is exact: the whole row and its length are compared,
+// and the handle is the one intern_list gave that same sequence.  Entry = 4 + row_words words:
+//   [0] tag (hash high half | 1; 0 = free)   [1] handle + 1 (0 = not yet published)   [2] rlen   [4..] row
+// ---------------------------------------------------------------------------------------------
+static constexpr int MEMO_PROBES = 4;
+static constexpr uint32_t MEMO_ENTRIES = 1u << 20;
+struct MemoView {
+    uint32_t* tab;                     // nullptr: memo off
+    uint32_t mask;                     // entries - 1
+    uint32_t stride;                   // words per entry
+};
+
+template <int XW>
+__device__ __forceinline__ uint64_t memo_hash(const uint32_t (&x)[XW], uint32_t rlen) {
+    KmerHash hs;
+#pragma unroll
+    for (int w = 0; w < XW; w++) hs.add(x[w]);
+    hs.add(rlen);
+    return hs.finish();
+}
+
+// handle of an equal read, or H_PENDING
+template <int XW>
+__device__ __forceinline__ uint32_t memo_find(const MemoView& mv, const uint32_t (&x)[XW], uint32_t rlen, uint64_t h) {
+    const uint32_t tag = (uint32_t)(h >> 32) | 1u;
+    uint32_t slot = (uint32_t)h & mv.mask;
+#pragma unroll 1
+    for (int probe = 0; probe < MEMO_PROBES; probe++, slot = (slot + 1) & mv.mask) {
+        const uint32_t* e = mv.tab + (size_t)slot * mv.stride;
+        const uint4 w0 = __ldcg(reinterpret_cast<const uint4*>(e));            // tag, handle + 1, rlen, -
+        if (w0.x == 0) return H_PENDING;
+        if (w0.x != tag || w0.y == 0 || w0.z != rlen) continue;
+        __threadfence();                                                        // the row was written before the handle
+        bool eq = true;
+#pragma unroll
+        for (int q = 0; q < XW / 4; q++) {
+            const uint4 w = __ldcg(reinterpret_cast<const uint4*>(e) + 1 + q);
+            eq &= w.x == x[4 * q] && w.y == x[4 * q + 1] && w.z == x[4 * q + 2] && w.w == x[4 * q + 3];
+        }
+        if (eq) return w0.y - 1;
+    }
+    return H_PENDING;
+}
+
+template <int XW>
+__device__ __forceinline__ void memo_insert(const MemoView& mv, const uint32_t (&x)[XW], uint32_t rlen, uint64_t h, uint32_t handle) {
+    const uint32_t tag = (uint32_t)(h >> 32) | 1u;
+    uint32_t slot = (uint32_t)h & mv.mask;
+#pragma unroll 1
+    for (int probe = 0; probe < MEMO_PROBES; probe++, slot = (slot + 1) & mv.mask) {
+        uint32_t* e = mv.tab + (size_t)slot * mv.stride;
+        uint32_t t = *reinterpret_cast<volatile uint32_t*>(e);
+        if (t == 0) t = atomicCAS(e, 0u, tag);
+        if (t == 0) {                                                           // this thread owns the entry
+            e[2] = rlen;
+#pragma unroll
+            for (int q = 0; q < XW / 4; q++)
+                reinterpret_cast<uint4*>(e)[1 + q] = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(e + 1) = handle + 1;         // publish
+            return;
+        }
+        if (t == tag) return;                                                   // (very likely) the same read, entered by someone else
+    }
+}
+
+// The per-read arrays shared by k_memo and k_walk.
 struct WalkArgs {
     const uint32_t* rows;              // tile-local slots written by k_scan_rows
     const uint32_t* hdr;
     uint32_t row_words, tcap;
     const uint32_t* r_first;           // [n_tiles + 1] chunk-local index of each tile's first read (k_tile_fix)
-    const uint32_t* blk_tile;          // [blocks] tile of the first read of each k_walk block
+    const uint32_t* blk_tile;          // [blocks of WK_THREADS reads] tile of the block's first read
     uint32_t head;                     // chunk start address mod 16 (tile t starts at buffer position t * SM_TILE - head)
     uint64_t n_slots;                  // capacity of the per-read arrays
+    uint64_t r_lo, r_hi;               // reads of this k_memo / k_walk round (the memo a round fills serves the next ones)
     const unsigned long long* total;   // terminators of the chunk (written by k_tile_fix)
     uint64_t line_base, rec_first;
+    uint32_t split_len;
     uint32_t* handles;
+    uint2* walk_list;                  // reads the walk has to do: {chunk-local read index, slot}
+    unsigned long long* walk_count;
     uint32_t* d_read;                  // deferred reads, compact: chunk-local read index,
     uint32_t* d_hdr;                   //   rlen | PH_* flags,
     uint32_t* d_rows;                  //   packed row,
@@ -258,8 +333,104 @@ struct WalkArgs {
     uint64_t* d_end;
     unsigned long long* defer_count;
     unsigned long long* counters;
+    MemoView memo;
 };
 
+// a read no tier before the list-driven ones can finish: row, header and byte range go to their compact arrays
+__device__ __forceinline__ void defer_read(const WalkArgs& a, unsigned long long d, uint32_t r, uint64_t slot, uint32_t h) {
+    const uint32_t rlen = h & SH_RLEN;
+    a.d_read[d] = r;
+    a.d_hdr[d] = rlen | ((h & SH_N) ? PH_N : 0u) | ((h & SH_BAD) ? PH_BAD : 0u) | ((h & SH_LONG) ? PH_LONG : 0u);
+    const uint64_t st = (slot / a.tcap) * SM_TILE + (h >> 16) - a.head;
+    a.d_start[d] = st;
+    a.d_end[d] = (h & SH_LONG) ? ~0ull : st + rlen;
+    const uint4* src = reinterpret_cast<const uint4*>(a.rows + slot * a.row_words);
+    uint4* dst = reinterpret_cast<uint4*>(a.d_rows + d * a.row_words);
+    for (uint32_t q = 0; 4 * q < a.row_words; q++) dst[q] = __ldg(src + q);
+}
+
+// positions [base, base + n) of a device-side list for the lanes of this warp that want one (one atomic per warp)
+__device__ __forceinline__ unsigned long long warp_append(unsigned long long* count, bool want) {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want), lane = threadIdx.x & 31;
+    if (m == 0) return 0;
+    unsigned long long base = 0;
+    const int leader = __ffs((int)m) - 1;
+    if ((int)lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+
+// k_memo -- one thread per read of the chunk: finds the read's slot, settles the pair-skipping classes ('N', short),
+// sends reads that are not plain ACGT rows to the list-driven tiers, asks the memo, and lists what is left for k_walk
+// (one list append per block).
+static constexpr int MM_THREADS = 256;
+static_assert(MM_THREADS % WK_THREADS == 0, "blk_tile is indexed by blocks of WK_THREADS reads");
+
+template <int RW>
+__global__ void __launch_bounds__(MM_THREADS)
+k_memo(const WalkArgs a) {
+    __shared__ uint32_t s_cnt[MM_THREADS / 32], s_hit[MM_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    // sequence lines of the chunk = #{l in [line_base, line_base + total) : l % 4 == 1}
+    const uint64_t n_lines1 = (uint64_t)(a.line_base + *a.total + 2) / 4 - a.rec_first;
+    const uint64_t n_reads = n_lines1 < a.n_slots ? n_lines1 : a.n_slots;
+    const uint64_t r = a.r_lo + (uint64_t)blockIdx.x * MM_THREADS + threadIdx.x;
+    // a tile overflowed: the host repeats the chunk on the plain path, nothing of this launch is used
+    const bool live = r < n_reads && r < a.r_hi && !(*reinterpret_cast<const volatile unsigned long long*>(a.counters + CNT_ERR) & ERRF_TILE_FULL);
+    if (r == 0 && live) atomicAdd(&a.counters[CNT_FAST], (unsigned long long)n_reads);
+    bool walk = false, hit = false;
+    uint64_t slot = 0;
+    if (live) {
+        // the read's slot: its tile (the first tile of its 128-read block, or one of the next ones) and its index there
+        uint32_t t = __ldg(a.blk_tile + (r / WK_THREADS));
+        uint32_t f0 = __ldg(a.r_first + t), f1 = __ldg(a.r_first + t + 1);
+        while ((uint32_t)r >= f1) { t++; f0 = f1; f1 = __ldg(a.r_first + t + 1); }
+        slot = (uint64_t)t * a.tcap + ((uint32_t)r - f0);
+        const uint32_t h = __ldg(a.hdr + slot);
+        const uint32_t rlen = h & SH_RLEN;
+        uint32_t handle = H_PENDING;
+        bool defer = false;
+        if (h & SH_LONG) defer = true;
+        else if (h & SH_N) handle = H_N;                                   // 'N' before the length (PE_Inference.py:160-163)
+        else if (rlen < a.split_len) handle = H_SHORT;
+        else if (h & SH_BAD) defer = true;
+        else {
+            walk = true;
+            if (a.memo.tab != nullptr) {
+                uint32_t x[RW];
+                const uint4* src = reinterpret_cast<const uint4*>(a.rows + slot * RW);
+#pragma unroll
+                for (int q = 0; q < RW / 4; q++) {
+                    const uint4 v = __ldg(src + q);
+                    x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+                }
+                handle = memo_find<RW>(a.memo, x, rlen, memo_hash<RW>(x, rlen));
+                hit = handle != H_PENDING;
+                walk = !hit;
+            }
+        }
+        if (defer) defer_read(a, atomicAdd(a.defer_count, 1ull), (uint32_t)r, slot, h);
+        if (!walk) a.handles[r] = handle;                                  // (H_PENDING for a deferred read: the tiers fill it in)
+    }
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, walk), mh = __ballot_sync(0xFFFFFFFFu, hit);
+    if (lane == 0) { s_cnt[wid] = __popc(m); s_hit[wid] = __popc(mh); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0, hits = 0;
+        for (int w = 0; w < MM_THREADS / 32; w++) { tot += s_cnt[w]; hits += s_hit[w]; }
+        s_base = tot ? atomicAdd(a.walk_count, (unsigned long long)tot) : 0ull;
+        if (hits) atomicAdd(&a.counters[CNT_MEMO_HIT], (unsigned long long)hits);
+    }
+    __syncthreads();
+    if (walk) {
+        unsigned long long pos = s_base + __popc(m & ((1u << lane) - 1));
+        for (uint32_t w = 0; w < wid; w++) pos += s_cnt[w];
+        a.walk_list[pos] = make_uint2((uint32_t)r, (uint32_t)slot);
+    }
+}
+
+// k_walk -- one thread per listed read; a fixed grid walks the device-side list.
 #ifndef VSPE_WK_MINB
 #define VSPE_WK_MINB 10
 #endif
@@ -268,57 +439,59 @@ __global__ void __launch_bounds__(WK_THREADS, VSPE_WK_MINB)
 k_walk(const WalkArgs a, const IndexView ix, const LinkView lv) {
     __shared__ uint32_t s_rows[WK_THREADS * STRIDE];
     __shared__ uint32_t s_lst[SM_MAXST * WK_THREADS];
-    // sequence lines of the chunk = #{l in [line_base, line_base + total) : l % 4 == 1}
-    const uint64_t n_lines1 = (uint64_t)(a.line_base + *a.total + 2) / 4 - a.rec_first;
-    const uint64_t n_reads = n_lines1 < a.n_slots ? n_lines1 : a.n_slots;
-    const uint64_t r = (uint64_t)blockIdx.x * WK_THREADS + threadIdx.x;
-    if (r >= n_reads) return;
-    // a tile overflowed: the host repeats the chunk on the plain path, nothing of this launch is used
-    if (*reinterpret_cast<const volatile unsigned long long*>(a.counters + CNT_ERR) & ERRF_TILE_FULL) return;
-    if (r == 0) atomicAdd(&a.counters[CNT_FAST], (unsigned long long)n_reads);
-    // the read's slot: its tile (the block's first tile, or one of the next ones) and its index there
-    uint32_t t = __ldg(a.blk_tile + blockIdx.x);
-    uint32_t f0 = __ldg(a.r_first + t), f1 = __ldg(a.r_first + t + 1);
-    while ((uint32_t)r >= f1) { t++; f0 = f1; f1 = __ldg(a.r_first + t + 1); }
-    const uint64_t slot = (uint64_t)t * a.tcap + ((uint32_t)r - f0);
-    const uint32_t h = __ldg(a.hdr + slot);
-    const uint32_t rlen = h & SH_RLEN, L = ix.split_len;
-    uint32_t handle = H_PENDING;
-    bool defer = (h & (SH_LONG | SH_BAD)) != 0;
-    if (!(h & SH_LONG)) {
-        if (h & SH_N) handle = H_N;                                    // 'N' before the length (PE_Inference.py:160-163)
-        else if (rlen < L) handle = H_SHORT;
-    }
     constexpr int NW = STRIDE - 3, XW = (NW + 3) / 4 * 4;
-    const uint4* src = reinterpret_cast<const uint4*>(a.rows + slot * a.row_words);
-    if (handle == H_PENDING && !defer) {
-        uint32_t* row = s_rows + threadIdx.x * STRIDE;
-        uint32_t x[XW];
+    if (*reinterpret_cast<const volatile unsigned long long*>(a.counters + CNT_ERR) & ERRF_TILE_FULL) return;
+    const unsigned long long n = *a.walk_count;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * WK_THREADS; i0 < n; i0 += (uint64_t)gridDim.x * WK_THREADS) {
+        const uint64_t i = i0 + threadIdx.x;
+        bool defer = false;
+        uint32_t r = 0, h = 0;
+        uint64_t slot = 0;
+        if (i < n) {
+            const uint2 e = a.walk_list[i];
+            r = e.x;
+            slot = e.y;
+            h = __ldg(a.hdr + slot);
+            const uint32_t rlen = h & SH_RLEN;
+            const uint4* src = reinterpret_cast<const uint4*>(a.rows + slot * a.row_words);
+            uint32_t* row = s_rows + threadIdx.x * STRIDE;
+            {
+                uint32_t x[XW];
 #pragma unroll
-        for (int q = 0; q < XW / 4; q++) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if ((uint32_t)(4 * q) < a.row_words) v = __ldg(src + q);
-            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+                for (int q = 0; q < XW / 4; q++) {
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if ((uint32_t)(4 * q) < a.row_words) v = __ldg(src + q);
+                    x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int w = 0; w < NW; w++) row[w] = x[w];
+                row[NW] = 0; row[NW + 1] = 0; row[NW + 2] = 0;
+            }
+            uint32_t n_kept = 0;
+            bool clean = false;
+            if (walk_read<STRIDE, WK_THREADS>(ix, row, rlen, s_lst + threadIdx.x, n_kept, clean)) {
+                const uint32_t handle = intern_list(lv, n_kept, s_lst + threadIdx.x, WK_THREADS);
+                a.handles[r] = handle;
+                // only table handles outlive the call (private records are per call), only error-free reads are bounded by the graph
+                if (clean && a.memo.tab != nullptr && handle < lv.T) {
+                    uint32_t x[XW];                                        // (the walk may have reverse-complemented its copy)
+#pragma unroll
+                    for (int q = 0; q < XW / 4; q++) {
+                        const uint4 v = __ldg(src + q);
+                        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+                    }
+                    memo_insert<XW>(a.memo, x, rlen, memo_hash<XW>(x, rlen), handle);
+                }
+            } else {
+                defer = true;
+            }
         }
-#pragma unroll
-        for (int w = 0; w < NW; w++) row[w] = x[w];
-        row[NW] = 0; row[NW + 1] = 0; row[NW + 2] = 0;
-        uint32_t n_kept = 0;
-        if (walk_read<STRIDE, WK_THREADS>(ix, row, rlen, s_lst + threadIdx.x, n_kept)) handle = intern_list(lv, n_kept, s_lst + threadIdx.x, WK_THREADS);
-        else defer = true;
+        const unsigned long long d = warp_append(a.defer_count, defer);
+        if (defer) {
+            a.handles[r] = H_PENDING;
+            defer_read(a, d, r, slot, h);
+        }
     }
-    if (handle == H_PENDING && defer) {
-        // (the walk may have reverse-complemented its copy of the row: the tiers get the row as it was scanned)
-        const unsigned long long d = atomicAdd(a.defer_count, 1ull);
-        a.d_read[d] = (uint32_t)r;
-        a.d_hdr[d] = rlen | ((h & SH_N) ? PH_N : 0u) | ((h & SH_BAD) ? PH_BAD : 0u) | ((h & SH_LONG) ? PH_LONG : 0u);
-        const uint64_t st = (uint64_t)t * SM_TILE + (h >> 16) - a.head;
-        a.d_start[d] = st;
-        a.d_end[d] = (h & SH_LONG) ? ~0ull : st + rlen;
-        uint4* dst = reinterpret_cast<uint4*>(a.d_rows + d * a.row_words);
-        for (uint32_t q = 0; 4 * q < a.row_words; q++) dst[q] = __ldg(src + q);
-    }
-    a.handles[r] = handle;
 }
 
 static constexpr int SM_MAXTERM = 4 * SM_MAXREC + 8;                  // terminators a tile may hold (else the chunk takes the plain path)
@@ -733,6 +906,7 @@ int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base
     VSPE_TRY(mb.d_hdr.reserve(n_slots + 2));
     VSPE_TRY(mb.d_rows.reserve((n_slots + 2) * row_words));
     VSPE_TRY(c->defer_m[m].reserve(n_slots + 2));
+    VSPE_TRY(c->walk_list_m[m].reserve(n_slots + 2));
     unsigned long long* info = reinterpret_cast<unsigned long long*>(c->tile_base_m[m].p);
     ScanMapArgs a;
     a.buf = d_buf; a.n = n; a.head = head; a.n_tiles = (uint32_t)n_tiles; a.line_base = line_base;
@@ -770,19 +944,44 @@ int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base
     else if (row_words == 16) k_scan_redo<16><<<redo_grid, SM_THREADS, SM_SMEM, c->stream>>>(a);
     else k_scan_redo<20><<<redo_grid, SM_THREADS, SM_SMEM, c->stream>>>(a);
     VSPE_LAUNCH_CHECK(c);
+    // the memo lives as long as the list handles do (link_reset clears it); its entry size follows the row size
+    if (c->opt_memo && !c->memo_off) {
+        const uint32_t stride = 4 + row_words;
+        if (!c->memo.p || c->memo_stride != stride) {
+            c->memo.release();
+            VSPE_TRY(c->memo.reserve((size_t)MEMO_ENTRIES * stride));
+            c->memo_stride = stride;
+            VSPE_CUDA(cudaMemsetAsync(c->memo.p, 0, (size_t)MEMO_ENTRIES * stride * 4, c->stream));
+        }
+    }
     WalkArgs w;
     w.rows = mb.rec.rows.p; w.hdr = mb.rec.hdr.p; w.row_words = row_words; w.tcap = tcap; w.r_first = f.r_first; w.blk_tile = f.blk_tile;
-    w.head = head; w.n_slots = n_slots; w.total = f.total; w.line_base = line_base; w.rec_first = rec_first; w.handles = d_handles;
+    w.head = head; w.n_slots = n_slots; w.total = f.total; w.line_base = line_base; w.rec_first = rec_first; w.split_len = c->index.split_len;
+    w.handles = d_handles; w.walk_list = c->walk_list_m[m].p; w.walk_count = c->counters.p + (m == 0 ? CNT_WALK : CNT_WALK1);
     w.d_read = c->defer_m[m].p; w.d_hdr = mb.d_hdr.p; w.d_rows = mb.d_rows.p; w.d_start = mb.rec.seq_start.p; w.d_end = mb.rec.seq_end.p;
     w.defer_count = d_defer_count; w.counters = c->counters.p;
+    w.memo.tab = (c->opt_memo && !c->memo_off) ? c->memo.p : nullptr; w.memo.mask = MEMO_ENTRIES - 1; w.memo.stride = c->memo_stride;
     const IndexView ix = c->index.view();
     const LinkView lv = link_view(c);
-    const uint32_t grid = (uint32_t)n_blk;
     VSPE_CUDA(cudaEventRecord(c->ev_scan[1][2 * k], c->stream));
-    if (cap <= 160) k_walk<13><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
-    else if (cap <= 256) k_walk<19><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
-    else k_walk<23><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
-    VSPE_LAUNCH_CHECK(c);
+    // rounds of k_memo -> k_walk over growing ranges of reads (256 Ki, 1 Mi, 4 Mi, the rest): what a round's walks enter
+    // into the memo answers the later rounds, so one large chunk warms its own memo
+    for (uint64_t lo = 0, len = 1ull << 18; lo < n_slots; lo += len, len = len < (4ull << 20) ? len * 4 : n_slots) {
+        w.r_lo = lo;
+        w.r_hi = std::min<uint64_t>(n_slots, lo + len);
+        const uint64_t n_round = w.r_hi - w.r_lo;
+        VSPE_CUDA(cudaMemsetAsync(w.walk_count, 0, 8, c->stream));
+        const uint32_t mgrid = (uint32_t)((n_round + MM_THREADS - 1) / MM_THREADS);
+        if (row_words == 12) k_memo<12><<<mgrid, MM_THREADS, 0, c->stream>>>(w);
+        else if (row_words == 16) k_memo<16><<<mgrid, MM_THREADS, 0, c->stream>>>(w);
+        else k_memo<20><<<mgrid, MM_THREADS, 0, c->stream>>>(w);
+        VSPE_LAUNCH_CHECK(c);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_round + WK_THREADS - 1) / WK_THREADS, (uint64_t)c->sm_count * VSPE_WK_MINB);
+        if (cap <= 160) k_walk<13><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
+        else if (cap <= 256) k_walk<19><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
+        else k_walk<23><<<grid, WK_THREADS, 0, c->stream>>>(w, ix, lv);
+        VSPE_LAUNCH_CHECK(c);
+    }
     VSPE_CUDA(cudaEventRecord(c->ev_scan[1][2 * k + 1], c->stream));
     c->scan_map_pending[k] = true;
     c->scan_map_events++;
