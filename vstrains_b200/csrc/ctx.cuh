@@ -75,6 +75,7 @@ struct Ctx {
     DevBuf<uint2> walk_list_m[2];      // per mate: {read, slot} of the reads k_memo left for k_walk
     DevBuf<uint32_t> memo;             // read memo: packed row -> list handle (scan_map.cu)
     uint32_t memo_stride = 0;          // words per memo entry (4 + row words)
+    uint64_t memo_seen = 0;            // reads that went through k_memo since the memo was cleared (estimate: cold / warm)
     bool memo_off = false;             // switched off for this index: the input does not repeat reads
     DevBuf<uint32_t> tile_idx_m[2];    // per mate: first read of every tile, first tile of every k_walk block (k_tile_fix)
     // K5/K6: list table + pair table (link.cuh)

@@ -238,8 +238,11 @@ int index_build_device(Ctx* c, const uint8_t* seqs, const uint64_t* seq_off, uin
     h_ss[2 * (size_t)n_nodes] = (uint32_t)text_len;
     uint32_t nbits = 1;
     while (nbits < 31 && (1ull << nbits) < n_nodes) nbits++;
+    // load <= 1/4 while the table stays L2 sized (a miss -- the usual answer for a window with sequencing errors -- then
+    // ends after 1.4 slots on average instead of 2.5), <= 1/2 beyond
     uint64_t slots = 1024;
     while (slots < 2 * n_kmers + 2) slots <<= 1;
+    if (slots * sizeof(uint2) <= (32ull << 20)) slots <<= 1;
     if (slots > 0x80000000ull) { set_error("graph too large: hash table exceeds 2^31 slots"); return VSPE_ERR_LIMIT; }
 
     cudaStream_t st = c->stream;

@@ -67,6 +67,7 @@ int link_reset(Ctx* c) {
     // the read memo holds list handles: it is forgotten with the lists
     if (c->memo.p) VSPE_CUDA(cudaMemsetAsync(c->memo.p, 0, c->memo.cap * sizeof(uint32_t), c->stream));
     c->memo_off = false;
+    c->memo_seen = 0;
     return VSPE_OK;                                         // (the counters are zeroed by vspe_reset)
 }
 

@@ -265,25 +265,26 @@ __device__ __forceinline__ uint64_t memo_hash(const uint32_t (&x)[XW], uint32_t 
     return hs.finish();
 }
 
-// handle of an equal read, or H_PENDING
+// handle of an equal read, or H_PENDING.  The whole entry is requested at once (the lookup is one round trip to L2 / HBM
+// in the common case, not header-then-row).
 template <int XW>
 __device__ __forceinline__ uint32_t memo_find(const MemoView& mv, const uint32_t (&x)[XW], uint32_t rlen, uint64_t h) {
     const uint32_t tag = (uint32_t)(h >> 32) | 1u;
     uint32_t slot = (uint32_t)h & mv.mask;
 #pragma unroll 1
     for (int probe = 0; probe < MEMO_PROBES; probe++, slot = (slot + 1) & mv.mask) {
-        const uint32_t* e = mv.tab + (size_t)slot * mv.stride;
-        const uint4 w0 = __ldcg(reinterpret_cast<const uint4*>(e));            // tag, handle + 1, rlen, -
+        const uint4* e = reinterpret_cast<const uint4*>(mv.tab + (size_t)slot * mv.stride);
+        const uint4 w0 = __ldcg(e);                                             // tag, handle + 1, rlen, -
+        uint4 w[XW / 4];
+#pragma unroll
+        for (int q = 0; q < XW / 4; q++) w[q] = __ldcg(e + 1 + q);
         if (w0.x == 0) return H_PENDING;
         if (w0.x != tag || w0.y == 0 || w0.z != rlen) continue;
-        __threadfence();                                                        // the row was written before the handle
         bool eq = true;
 #pragma unroll
-        for (int q = 0; q < XW / 4; q++) {
-            const uint4 w = __ldcg(reinterpret_cast<const uint4*>(e) + 1 + q);
-            eq &= w.x == x[4 * q] && w.y == x[4 * q + 1] && w.z == x[4 * q + 2] && w.w == x[4 * q + 3];
-        }
+        for (int q = 0; q < XW / 4; q++) eq &= w[q].x == x[4 * q] && w[q].y == x[4 * q + 1] && w[q].z == x[4 * q + 2] && w[q].w == x[4 * q + 3];
         if (eq) return w0.y - 1;
+        // (a row read while its writer had not finished differs from x: the read is walked, which is always right)
     }
     return H_PENDING;
 }
@@ -386,7 +387,15 @@ k_memo(const WalkArgs a) {
         uint32_t f0 = __ldg(a.r_first + t), f1 = __ldg(a.r_first + t + 1);
         while ((uint32_t)r >= f1) { t++; f0 = f1; f1 = __ldg(a.r_first + t + 1); }
         slot = (uint64_t)t * a.tcap + ((uint32_t)r - f0);
+        // header and row are requested together (the row of a read that turns out to be 'N' / short / long is simply not used)
         const uint32_t h = __ldg(a.hdr + slot);
+        uint32_t x[RW];
+        const uint4* src = reinterpret_cast<const uint4*>(a.rows + slot * RW);
+#pragma unroll
+        for (int q = 0; q < RW / 4; q++) {
+            const uint4 v = __ldg(src + q);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
         const uint32_t rlen = h & SH_RLEN;
         uint32_t handle = H_PENDING;
         bool defer = false;
@@ -397,13 +406,6 @@ k_memo(const WalkArgs a) {
         else {
             walk = true;
             if (a.memo.tab != nullptr) {
-                uint32_t x[RW];
-                const uint4* src = reinterpret_cast<const uint4*>(a.rows + slot * RW);
-#pragma unroll
-                for (int q = 0; q < RW / 4; q++) {
-                    const uint4 v = __ldg(src + q);
-                    x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
-                }
                 handle = memo_find<RW>(a.memo, x, rlen, memo_hash<RW>(x, rlen));
                 hit = handle != H_PENDING;
                 walk = !hit;
@@ -964,9 +966,12 @@ int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base
     const IndexView ix = c->index.view();
     const LinkView lv = link_view(c);
     VSPE_CUDA(cudaEventRecord(c->ev_scan[1][2 * k], c->stream));
-    // rounds of k_memo -> k_walk over growing ranges of reads (256 Ki, 1 Mi, 4 Mi, the rest): what a round's walks enter
-    // into the memo answers the later rounds, so one large chunk warms its own memo
-    for (uint64_t lo = 0, len = 1ull << 18; lo < n_slots; lo += len, len = len < (4ull << 20) ? len * 4 : n_slots) {
+    // While the memo is cold: rounds of k_memo -> k_walk over growing ranges of reads (256 Ki, 1 Mi, 4 Mi, the rest) --
+    // what a round's walks enter into the memo answers the later rounds, so one large chunk warms its own memo.
+    // Afterwards: one round.
+    const bool memo_cold = w.memo.tab != nullptr && c->memo_seen < (2ull << 20);
+    c->memo_seen += n_slots;
+    for (uint64_t lo = 0, len = memo_cold ? 1ull << 18 : n_slots; lo < n_slots; lo += len, len = len < (4ull << 20) ? len * 4 : n_slots) {
         w.r_lo = lo;
         w.r_hi = std::min<uint64_t>(n_slots, lo + len);
         const uint64_t n_round = w.r_hi - w.r_lo;
