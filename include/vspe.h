@@ -177,6 +177,7 @@ void vspe_free_pinned(void* p);
  *   "scan_two_pass"  1: same as scan_mode 2
  *   "force_generic"  1: every read through the exhaustive ASCII tier (the reference's loop as is)
  *   "subst"          0: do not build / use the substitution-hit bitmap
+ *   "link_split"     k_bucket_count: keys of one matrix bucket per CTA before the bucket is shared by several CTAs (default 65536)
  *   "memo"           0: do not use the read memo (every read is walked, as if no read repeated)
  *   "tier_overlap"   0: vspe_count_device maps the two mates strictly one after the other (default 1: the list-driven
  *                    tiers of one mate run on a second stream beside the scan of the other)

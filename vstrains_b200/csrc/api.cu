@@ -1396,6 +1396,7 @@ int vspe_set_option(vspe_ctx* c, const char* name, int64_t value) {
     }
     else if (!strcmp(name, "tier_overlap")) c->opt_tier_overlap = value;
     else if (!strcmp(name, "memo")) c->opt_memo = value;
+    else if (!strcmp(name, "link_split")) c->opt_link_split = value < 256 ? 256 : value;
     else if (!strcmp(name, "pair_cap_log2")) c->opt_pair_cap_log2 = value;
     else if (!strcmp(name, "subst")) { c->opt_subst = value; if (!value) c->index.has_subst = false; }
     else if (!strcmp(name, "dbg_counters")) {

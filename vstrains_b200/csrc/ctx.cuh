@@ -103,6 +103,7 @@ struct Ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_chunk_mb = 256;
+    int64_t opt_link_split = 65536;    // k_bucket_count: keys of a bucket per CTA before the bucket is shared
     int64_t opt_memo = 1;              // ask / fill the read memo (scan_map.cu)
     int64_t opt_tier_overlap = 1;      // device-resident calls: run one mate's list-driven tiers beside the other mate's scan
     int64_t opt_pair_cap_log2 = 21;    // first size of the pair table (log2 entries); 0: size it by the pairs of the batch

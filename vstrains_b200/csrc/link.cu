@@ -295,6 +295,8 @@ __device__ __forceinline__ unsigned long long warp_alloc(unsigned long long* cur
     return base + inc - m;
 }
 
+// PACKED (dense mode: cell numbers and weights both fit 32 bits): one word key << 32 | weight per key, vals unused
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_comb_emit(LinkView lv, PairEnt* __restrict__ tab, uint64_t cap, uint64_t N,
             unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
@@ -316,11 +318,15 @@ k_comb_emit(LinkView lv, PairEnt* __restrict__ tab, uint64_t cap, uint64_t N,
         unsigned long long o = warp_alloc(lv.counters + CNT_EXP_CURSOR, (unsigned long long)L.n * R.n);
         for (uint32_t a = 0; a < L.n; a++) {
             const unsigned long long row = (unsigned long long)L[a] * N;
-            for (uint32_t b = 0; b < R.n; b++) { keys[o] = row + R[b]; vals[o++] = w; }
+            for (uint32_t b = 0; b < R.n; b++) {
+                if (PACKED) keys[o++] = ((row + R[b]) << 32) | w;
+                else { keys[o] = row + R[b]; vals[o++] = w; }
+            }
         }
     }
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_list_emit(LinkView lv, uint64_t N, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
     const unsigned long long n_tab = lv.counters[CNT_LISTS], n = n_tab + lv.counters[CNT_OVF];
@@ -340,8 +346,9 @@ k_list_emit(LinkView lv, uint64_t N, unsigned long long* __restrict__ keys, unsi
             const uint32_t x = A[a];
             for (uint32_t b = a; b < A.n; b++) {
                 const uint32_t y = A[b];
-                keys[o] = NN + (unsigned long long)min(x, y) * N + max(x, y);
-                vals[o++] = w;
+                const unsigned long long key = NN + (unsigned long long)min(x, y) * N + max(x, y);
+                if (PACKED) keys[o++] = (key << 32) | w;
+                else { keys[o] = key; vals[o++] = w; }
             }
         }
     }
@@ -353,9 +360,10 @@ k_list_emit(LinkView lv, uint64_t N, unsigned long long* __restrict__ keys, unsi
 //   k_wkey_hist     keys per bucket (bucket = key >> low_bits)
 //   k_wkey_scan     exclusive scan -> bucket segments
 //   k_wkey_scatter  (low digit, weight) scattered into the key's bucket segment (radix partition)
-//   k_bucket_count  one CTA per bucket: counting sort of the low digit in shared memory; the summed
-//                   weight of a digit value IS the run total of that key, stored to the matrix cell
-//                   with a plain read-modify-write -- each cell is owned by exactly one CTA.
+//   k_bucket_count  one CTA per bucket (a large bucket: up to 16 CTAs over shares of its segment): counting sort of the
+//                   low digit in shared memory; the summed weight of a digit value IS the run total of that key (of the
+//                   share), added to the matrix cell -- plain read-modify-write where one CTA owns the cell, integer
+//                   atomics where the bucket was shared.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_wkey_hist(const unsigned long long* __restrict__ keys, uint64_t n, uint64_t per_block, uint32_t low_bits, uint32_t n_buckets,
@@ -364,7 +372,7 @@ k_wkey_hist(const unsigned long long* __restrict__ keys, uint64_t n, uint64_t pe
     for (uint32_t b = threadIdx.x; b < n_buckets; b += blockDim.x) s_h[b] = 0;
     __syncthreads();
     const uint64_t lo = (uint64_t)blockIdx.x * per_block, hi = min(n, lo + per_block);
-    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_h[(uint32_t)(keys[i] >> low_bits)], 1u);
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_h[(uint32_t)(keys[i] >> (32 + low_bits))], 1u);
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < n_buckets; b += blockDim.x) {
         const uint32_t c = s_h[b];
@@ -405,7 +413,7 @@ k_wkey_scan(const uint32_t* __restrict__ hist, uint32_t n, uint32_t* __restrict_
 }
 
 __global__ void __launch_bounds__(256)
-k_wkey_scatter(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ vals, uint64_t n, uint64_t per_block,
+k_wkey_scatter(const unsigned long long* __restrict__ keys, uint64_t n, uint64_t per_block,
                uint32_t low_bits, uint32_t n_buckets, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ out_k,
                uint32_t* __restrict__ out_w) {
     extern __shared__ uint32_t s_mem[];
@@ -414,7 +422,7 @@ k_wkey_scatter(const unsigned long long* __restrict__ keys, const unsigned long 
     for (uint32_t b = threadIdx.x; b < n_buckets; b += blockDim.x) s_cnt[b] = 0;
     __syncthreads();
     const uint64_t lo = (uint64_t)blockIdx.x * per_block, hi = min(n, lo + per_block);
-    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[(uint32_t)(keys[i] >> low_bits)], 1u);
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[(uint32_t)(keys[i] >> (32 + low_bits))], 1u);
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < n_buckets; b += blockDim.x) {
         const uint32_t c = s_cnt[b];
@@ -424,35 +432,49 @@ k_wkey_scatter(const unsigned long long* __restrict__ keys, const unsigned long 
     __syncthreads();
     const uint32_t mask = (1u << low_bits) - 1;
     for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const unsigned long long k = keys[i];
-        const uint32_t b = (uint32_t)(k >> low_bits);
+        const unsigned long long kw = keys[i];                 // cell << 32 | weight
+        const uint32_t k = (uint32_t)(kw >> 32);
+        const uint32_t b = k >> low_bits;
         const uint32_t pos = s_base[b] + atomicAdd(&s_cnt[b], 1u);
-        out_k[pos] = (uint32_t)k & mask;
-        out_w[pos] = (uint32_t)vals[i];
+        out_k[pos] = k & mask;
+        out_w[pos] = (uint32_t)kw;
     }
 }
 
+// blockIdx.x = bucket, blockIdx.y = part: a bucket with more than BC_SPLIT keys is counted by up to gridDim.y CTAs, each
+// over a contiguous share of its segment; their partial run totals are integer-added to the cells (order independent).
+// A small bucket is counted by its part 0 alone, which owns the cells.
+static constexpr uint32_t BC_PARTS = 16;
 __global__ void __launch_bounds__(256)
 k_bucket_count(const uint32_t* __restrict__ k_lo, const uint32_t* __restrict__ w, const uint32_t* __restrict__ start,
-               uint32_t low_bits, uint64_t n_cells, uint64_t* __restrict__ mats) {
+               uint32_t low_bits, uint64_t n_cells, uint64_t* __restrict__ mats, const uint32_t split) {
     extern __shared__ uint32_t s_bins[];
     const uint32_t bucket = blockIdx.x;
     const uint32_t s0 = start[bucket], e0 = start[bucket + 1];
     if (s0 == e0) return;
+    const uint32_t n = e0 - s0;
+    const uint32_t parts = n <= split ? 1u : min((uint32_t)gridDim.y, (n + split - 1) / split);
+    if (blockIdx.y >= parts) return;
+    const uint32_t per = (n + parts - 1) / parts;
+    const uint32_t lo = s0 + blockIdx.y * per, hi = min(e0, lo + per);
     const uint32_t nb = 1u << low_bits;
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) s_bins[i] = 0;
     __syncthreads();
-    for (uint32_t i = s0 + threadIdx.x; i < e0; i += blockDim.x) atomicAdd(&s_bins[k_lo[i]], w[i]);
+    // (folding equal cells of a warp with __match_any_sync before the atomic was measured slower on every config)
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_bins[k_lo[i]], w[i]);
     __syncthreads();
     const uint64_t base = (uint64_t)bucket << low_bits;
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
         const uint32_t c = s_bins[i];
-        if (c && base + i < n_cells) mats[base + i] += c;
+        if (c && base + i < n_cells) {
+            if (parts == 1) mats[base + i] += c;
+            else atomicAdd(reinterpret_cast<unsigned long long*>(mats) + base + i, (unsigned long long)c);
+        }
     }
 }
 
-// keys / vals: the weighted keys of one batch (device arrays of n entries)
-static int dense_accumulate(Ctx* c, const unsigned long long* keys, const unsigned long long* vals, uint64_t n) {
+// keys: the weighted keys of one batch, cell << 32 | weight (device array of n entries)
+static int dense_accumulate(Ctx* c, const unsigned long long* keys, uint64_t n) {
     const uint64_t N = c->index.n_nodes, cells = 2 * N * N;
     if (n == 0 || cells == 0) return VSPE_OK;
     if (n > 0xFFFFFFF0ull) { set_error("key batch too large"); return VSPE_ERR_LIMIT; }
@@ -479,9 +501,10 @@ static int dense_accumulate(Ctx* c, const unsigned long long* keys, const unsign
     VSPE_LAUNCH_CHECK(c);
     k_wkey_scan<<<1, 1024, 0, st>>>(g_hist, n_buckets, g_start, g_cursor);
     VSPE_LAUNCH_CHECK(c);
-    k_wkey_scatter<<<(uint32_t)blocks, 256, n_buckets * 8, st>>>(keys, vals, n, per_block, low_bits, n_buckets, g_cursor, out_k, out_w);
+    k_wkey_scatter<<<(uint32_t)blocks, 256, n_buckets * 8, st>>>(keys, n, per_block, low_bits, n_buckets, g_cursor, out_k, out_w);
     VSPE_LAUNCH_CHECK(c);
-    k_bucket_count<<<n_buckets, 256, (1u << low_bits) * 4, st>>>(out_k, out_w, g_start, low_bits, cells, c->mats.p);
+    k_bucket_count<<<dim3(n_buckets, BC_PARTS), 256, (1u << low_bits) * 4, st>>>(out_k, out_w, g_start, low_bits, cells, c->mats.p,
+                                                                                     (uint32_t)c->opt_link_split);
     VSPE_LAUNCH_CHECK(c);
     return VSPE_OK;
 }
@@ -545,16 +568,18 @@ int count_links(Ctx* c, const uint32_t* d_hf, const uint32_t* d_hr, uint64_t tot
         VSPE_TRY(sparse_reserve(c, sp.n_runs + h_exp));
         unsigned long long* keys = sp.k[0].p + sp.n_runs;
         unsigned long long* vals = sp.v[0].p + sp.n_runs;
-        k_comb_emit<<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_cap, N, keys, vals);
+        if (sp.enabled) k_comb_emit<false><<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_cap, N, keys, vals);
+        else k_comb_emit<true><<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_cap, N, keys, vals);
         VSPE_LAUNCH_CHECK(c);
-        k_list_emit<<<grid_cap, 256, 0, st>>>(lv, N, keys, vals);
+        if (sp.enabled) k_list_emit<false><<<grid_cap, 256, 0, st>>>(lv, N, keys, vals);
+        else k_list_emit<true><<<grid_cap, 256, 0, st>>>(lv, N, keys, vals);
         VSPE_LAUNCH_CHECK(c);
         if (sp.enabled) {
             uint64_t runs = 0;
             VSPE_TRY(sparse_sort_reduce(c, sp.n_runs + h_exp, &runs));
             sp.n_runs = runs;
         } else {
-            VSPE_TRY(dense_accumulate(c, keys, vals, h_exp));
+            VSPE_TRY(dense_accumulate(c, keys, h_exp));
         }
     }
     return VSPE_OK;
