@@ -578,6 +578,7 @@ def main():
                    "l2": "inputs (%.0f MB resident per GPU) larger than the 126 MB L2; no flush needed" % (block_bytes / 1e6),
                    "index_build_ms": st["ms_index"], "keys_per_pair": st["n_keys"] / max(1, st["used_pairs"]),
                    "reads_fast": st["reads_fast"], "reads_generic": st["reads_generic"], "numa_node": numa,
+                   "read_memo_hit_rate": st["reads_memo"] / max(1, 2 * pairs), "scan_redo_tiles": st["scan_redo_tiles"],
                    "counting": "sparse runs (LSD radix sort + RLE)" if sparse else "dense matrices (pair aggregation + radix partition + counting sort)"},
         "clocks": clocks,
         "gpu_launches": int(launches),
@@ -589,11 +590,11 @@ def main():
         "whole_job_hbm_frac": whole,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "whole_path_frac": whole,
-                     "kernel": "k_scan_rows (K1+K2 in one pass: TMA tile -> record split with look-back -> 2-bit rows)",
+                     "kernel": "k_scan_rows (K1+K2 in one pass, tiles independent: TMA tile -> terminators -> guessed line phase -> 2-bit rows in tile-local slots)",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": k_bytes, "launch_ms": k_ms,
                      "launches_per_step": n_scan_launches / args.steps,
                      "kernel_share_of_step": stage["ms_k_scan_rows"] / max(1e-9, stage["ms_total"]),
-                     "second_kernel": {"kernel": "k_walk (K4 first tier: seed + flat walk + list interning, one thread per read)",
+                     "second_kernel": {"kernel": "k_memo + k_walk (K4 first tier: read memo lookup, then seed + flat walk + list interning for the reads it cannot answer)",
                                        "launch_ms": w_ms, "share_of_step": stage["ms_k_walk"] / max(1e-9, stage["ms_total"]),
                                        "reads_per_s": (block / (w_ms * 1e-3)) if w_ms > 0 else None}},
     }

@@ -523,7 +523,11 @@ map_fast_block(const IndexView& ix, const uint8_t* __restrict__ buf, const uint6
 // Direct mode (in_count == nullptr): one block per MF_THREADS reads.  List mode: a fixed grid walks the compact
 // arrays of the deferred reads (their number is only known on the device), so no empty blocks are launched.
 template <int STRIDE, int LPR, bool PACKED>
+#ifdef VSPE_MF_MINB
+__global__ void __launch_bounds__(MF_THREADS, VSPE_MF_MINB)
+#else
 __global__ void __launch_bounds__(MF_THREADS)
+#endif
 k_map_fast(IndexView ix, const uint8_t* __restrict__ buf, const uint64_t* __restrict__ seq_start,
            const uint64_t* __restrict__ seq_end, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ hdr,
            uint32_t row_words, uint64_t n_reads_arg,
