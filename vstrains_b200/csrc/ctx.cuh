@@ -86,6 +86,8 @@ struct Ctx {
     uint64_t pair_cap = 0;
     DevBuf<uint32_t> wk_hist, wk_keys;   // dense accumulation scratch: bucket histogram / segments, partitioned (digit, weight)
     bool link_attr_set = false;
+    int mf_blocks_per_sm = 0;          // resident k_map_fast blocks per SM for the row capacity mf_blocks_cap (occupancy query)
+    uint32_t mf_blocks_cap = 0;
     unsigned long long last_err_flags = 0;
     bool err_flags_fresh = false;
     cudaEvent_t ev_m[2][3] = {};       // per mate: scan start, scan end / map start, map end

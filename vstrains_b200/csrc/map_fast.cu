@@ -691,7 +691,18 @@ static int launch_map_fast(Ctx* c, const uint8_t* d_buf, const uint64_t* d_seq_s
     const unsigned long long* in_count = pre_count;
     const uint32_t* to_generic = c->worklist.p;                 // reads the ASCII tier must map
     const unsigned long long* to_generic_n = c->counters.p + CNT_WORK;
-    const uint32_t grid = pre_listed ? (uint32_t)std::min<uint64_t>((n_reads * LIST_SPREAD + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * 8)
+    // list mode: one resident wave (the blocks loop over the device-side list; more blocks than fit would run as a
+    // second, partly filled wave)
+    if (pre_listed && c->mf_blocks_per_sm == 0) {
+        int nb = 0;
+        cudaError_t e = cap <= 160 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_map_fast<13, 16, true>, MF_THREADS, 0)
+                      : cap <= 256 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_map_fast<19, 16, true>, MF_THREADS, 0)
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_map_fast<23, 32, true>, MF_THREADS, 0);
+        c->mf_blocks_per_sm = (e == cudaSuccess && nb > 0) ? nb : 4;
+        c->mf_blocks_cap = cap;
+    }
+    if (pre_listed && c->mf_blocks_cap != cap) { c->mf_blocks_per_sm = 0; return launch_map_fast(c, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, row_words, cap, n_reads, d_slots, pre_count); }
+    const uint32_t grid = pre_listed ? (uint32_t)std::min<uint64_t>((n_reads * LIST_SPREAD + MF_THREADS - 1) / MF_THREADS, (uint64_t)c->sm_count * c->mf_blocks_per_sm)
                                      : (uint32_t)((n_reads + MF_THREADS - 1) / MF_THREADS);
 #define VSPE_MF(S, LP, PK) k_map_fast<S, LP, PK><<<grid, MF_THREADS, 0, c->stream>>>(v, d_buf, d_seq_start, d_seq_end, d_rows, d_hdr, \
                                                                               row_words, n_reads, in_count, LIST_SPREAD, d_slots, \

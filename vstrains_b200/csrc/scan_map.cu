@@ -393,12 +393,12 @@ k_memo(const WalkArgs a) {
         while ((uint32_t)r >= f1) { t++; f0 = f1; f1 = __ldg(a.r_first + t + 1); }
         slot = (uint64_t)t * a.tcap + ((uint32_t)r - f0);
         // header and row are requested together (the row of a read that turns out to be 'N' / short / long is simply not used)
-        const uint32_t h = __ldg(a.hdr + slot);
+        const uint32_t h = __ldcs(a.hdr + slot);
         uint32_t x[RW];
         const uint4* src = reinterpret_cast<const uint4*>(a.rows + slot * RW);
 #pragma unroll
         for (int q = 0; q < RW / 4; q++) {
-            const uint4 v = __ldg(src + q);
+            const uint4 v = __ldcs(src + q);                               // streamed: keep L2 for the memo and the tables
             x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
         }
         const uint32_t rlen = h & SH_RLEN;
@@ -529,12 +529,15 @@ __device__ __forceinline__ void scan_tile(const ScanMapArgs& a, const uint32_t t
         const uint32_t bytes = (uint32_t)(ld_hi - ld_lo);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_bar)), "r"(bytes) : "memory");
         const uint8_t* src = a.buf - a.head + ld_lo;
+        // the FASTQ bytes are read exactly once: evict-first in L2, which the k-mer table, the memo and the link tables keep
+        unsigned long long policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         uint32_t done = 0;
         while (done < bytes) {
             const uint32_t part = min(bytes - done, 16384u);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                              smem_u32(s_bytes + s_off0 + done)),
-                         "l"(__cvta_generic_to_global(src + done)), "r"(part), "r"(smem_u32(s_bar))
+                         "l"(__cvta_generic_to_global(src + done)), "r"(part), "r"(smem_u32(s_bar)), "l"(policy)
                          : "memory");
             done += part;
         }
@@ -768,8 +771,8 @@ __device__ __forceinline__ void scan_tile(const ScanMapArgs& a, const uint32_t t
         const uint64_t slot = (uint64_t)tile * a.tcap + li;
         uint4* dst = reinterpret_cast<uint4*>(a.rows + slot * RW);
 #pragma unroll
-        for (int v = 0; v < RW; v += 4) dst[v >> 2] = make_uint4(rw[v], rw[v + 1], rw[v + 2], rw[v + 3]);
-        a.hdr[slot] = h | rlen | (st << 16);
+        for (int v = 0; v < RW; v += 4) __stcs(dst + (v >> 2), make_uint4(rw[v], rw[v + 1], rw[v + 2], rw[v + 3]));
+        __stcs(a.hdr + slot, h | rlen | (st << 16));
     }
 }
 
