@@ -8,12 +8,14 @@ for p in sorted(glob.glob("tests/golden/*.npz"))[:8] + ["tests/golden/synth_2x25
     z = np.load(p)
     if int(z["status"]) != 0:
         continue
-    for opts in ({}, {"scan_mode": 1}, {"force_generic": 1, "scan_mode": 1}, {"sparse": 1}, {"subst": 0}, {"tier_overlap": 0}):
+    for opts in ({}, {"scan_mode": 1}, {"force_generic": 1, "scan_mode": 1}, {"sparse": 1}, {"subst": 0}, {"tier_overlap": 0}, {"memo": 0}):
         ids, seqs = pe_inference.parse_gfa_nodes(z["gfa"].tobytes())
         with pe_inference.PEIndex(seqs, int(z["k"])) as ix:
             for k, v in opts.items():
                 ix.set_option(k, v)
             ix.count_host(z["fwd"].tobytes(), z["rve"].tobytes())
+            if not opts:
+                ix.count_host(z["fwd"].tobytes(), z["rve"].tobytes())      # second call: the read memo answers
             ix.sparse() if ix.is_sparse else ix.matrices()
 cfg = synth.CONFIGS["C2"]
 g, f, r = synth.generate(cfg, pairs=3000)
