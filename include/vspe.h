@@ -57,7 +57,7 @@ typedef struct vspe_stats {
     float ms_total;           /* device time of the last vspe_count_* call                  */
     float ms_k_scan_rows;     /* sum of k_scan_rows launch durations (CUDA events on its stream)  */
     uint32_t n_k_scan_rows;   /* ... and how many launches that was                               */
-    float ms_k_walk;          /* same for k_walk                                                  */
+    float ms_k_walk;          /* same for the k_memo + k_walk rounds of a chunk (one interval per chunk)      */
     uint32_t n_k_walk;
     uint32_t scan_redo_tiles; /* tiles k_scan_redo packed again because their guessed line phase was wrong  */
     uint32_t reserved0;
