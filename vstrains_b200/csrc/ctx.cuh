@@ -24,6 +24,7 @@ enum Counter {
     CNT_B_USED, CNT_B_N, CNT_B_SHORT,   // pair classes of the current batch (added to USED / N / SHORT once the batch is accepted)
     CNT_WALK, CNT_WALK1,     // per mate: reads k_memo listed for k_walk
     CNT_MEMO_HIT,            // reads whose handle came from the read memo
+    CNT_PAIR_LIST,           // occupied pair-table entries listed by k_comb_weigh for k_comb_emit
     CNT_COUNT_
 };
 static constexpr uint64_t ERRF_NON_ASCII = 1, ERRF_SPILL_FULL = 2, ERRF_KEYS_FULL = 4, ERRF_SLOTS_FULL = 8, ERRF_TILE_FULL = 16, ERRF_LISTS_FULL = 32, ERRF_INTERNAL = 64, ERRF_PAIRS_FULL = 128;
@@ -83,6 +84,7 @@ struct Ctx {
     DevBuf<uint32_t> list_occ;         // [list_T]
     uint32_t list_T = 0, list_ov_cap = 0;
     DevBuf<PairEnt> pair_tab;          // [pair_cap] (power of two), all zero between batches
+    DevBuf<uint32_t> pair_occ;         // occupied entries of the pair table (k_comb_weigh -> k_comb_emit)
     uint64_t pair_cap = 0;
     DevBuf<uint32_t> wk_hist, wk_keys;   // dense accumulation scratch: bucket histogram / segments, partitioned (digit, weight)
     bool link_attr_set = false;

@@ -241,24 +241,46 @@ __device__ __forceinline__ void add_exp(unsigned long long* counters, unsigned l
     }
 }
 
-// every distinct combination: weights of its lists, number of node_mat keys
+// every distinct combination: weights of its lists, number of node_mat keys.  The whole table is visited once, here;
+// the occupied entries are listed (one atomic per block and turn) so that every lane of k_comb_emit has a combination
+// to expand.
 __global__ void __launch_bounds__(256)
-k_comb_weigh(LinkView lv, const PairEnt* __restrict__ tab, uint64_t cap) {
-    const uint64_t n = cap;                                 // the whole table is visited: free entries are skipped
+k_comb_weigh(LinkView lv, const PairEnt* __restrict__ tab, uint64_t cap, uint32_t* __restrict__ pocc, unsigned long long* __restrict__ pocc_n) {
+    __shared__ uint32_t s_wc[2][8];
+    __shared__ unsigned long long s_b[2];
     if (blockIdx.x == 0 && threadIdx.x < 3)                 // the batch was accepted: its pair classes count
         atomicAdd(&lv.counters[CNT_USED + (threadIdx.x == 0 ? 0 : threadIdx.x == 1 ? CNT_N - CNT_USED : CNT_SHORT - CNT_USED)],
                   lv.counters[CNT_B_USED + threadIdx.x]);
     unsigned long long exp = 0, keys = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const PairEnt e = tab[i];
-        if (e.key1 == 0) continue;
+    const uint64_t span = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int turn = 0;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < cap; i0 += span, turn ^= 1) {       // block-uniform trip count
+        const uint64_t i = i0 + threadIdx.x;
+        PairEnt e;
+        e.key1 = 0; e.count = 0; e.pad = 0;
+        if (i < cap) e = tab[i];
+        const bool occ = e.key1 != 0;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
+        if (lane == 0) s_wc[turn][wid] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) tot += s_wc[turn][w];
+            s_b[turn] = tot ? atomicAdd(pocc_n, (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        if (!occ) continue;
+        unsigned long long pos = s_b[turn] + __popc(m & ((1u << lane) - 1));
+        for (uint32_t w = 0; w < wid; w++) pos += s_wc[turn][w];
+        pocc[pos] = (uint32_t)i;
         const unsigned long long k = e.key1 - 1;
         const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
         atomicAdd(&lv.recs[a].used, e.count);
         atomicAdd(&lv.recs[b].used, e.count);
-        const unsigned long long m = (unsigned long long)(lv.recs[a].nplus1 - 1) * (lv.recs[b].nplus1 - 1);
-        exp += m;
-        keys += m * e.count;
+        const unsigned long long mm = (unsigned long long)(lv.recs[a].nplus1 - 1) * (lv.recs[b].nplus1 - 1);
+        exp += mm;
+        keys += mm * e.count;
     }
     add_exp(lv.counters, exp, keys);
 }
@@ -298,16 +320,16 @@ __device__ __forceinline__ unsigned long long warp_alloc(unsigned long long* cur
 // PACKED (dense mode: cell numbers and weights both fit 32 bits): one word key << 32 | weight per key, vals unused
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
-k_comb_emit(LinkView lv, PairEnt* __restrict__ tab, uint64_t cap, uint64_t N,
+k_comb_emit(LinkView lv, PairEnt* __restrict__ tab, const uint32_t* __restrict__ pocc, const unsigned long long* __restrict__ pocc_n, uint64_t N,
             unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
-    const uint64_t n = cap;
+    const uint64_t n = *pocc_n;
     const uint64_t span = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < n; i0 += span) {      // warp-uniform trip count
         const uint64_t i = i0 + threadIdx.x;
         ListRef L = {nullptr, 0, 0}, R = {nullptr, 0, 0};
         unsigned long long w = 0;
-        PairEnt* e = tab + i;
-        if (i < n && e->key1 != 0) {
+        if (i < n) {
+            PairEnt* e = tab + pocc[i];
             const unsigned long long k = e->key1 - 1;
             w = e->count;
             L = list_ref(lv, (uint32_t)(k >> 32));
@@ -535,6 +557,7 @@ int count_links(Ctx* c, const uint32_t* d_hf, const uint32_t* d_hr, uint64_t tot
                 c->pair_cap = cap;
             }
             VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_PAIR_OCC, 0, 6 * 8, st));     // PAIR_OCC, EXP, EXP_CURSOR, B_USED, B_N, B_SHORT
+            VSPE_CUDA(cudaMemsetAsync(c->counters.p + CNT_PAIR_LIST, 0, 8, st));
             k_pair_agg<<<grid, 256, 0, st>>>(d_hf + off, d_hr + off, n, c->pair_tab.p, (uint32_t)(c->pair_cap - 1), c->counters.p,
                                          c->list_T + c->list_ov_cap, cap == cap_max ? 0xFFFFFFFFu : 256u);
             VSPE_LAUNCH_CHECK(c);
@@ -549,7 +572,8 @@ int count_links(Ctx* c, const uint32_t* d_hf, const uint32_t* d_hr, uint64_t tot
             VSPE_CUDA(cudaMemsetAsync(c->pair_tab.p, 0, c->pair_cap * sizeof(PairEnt), st));
             cap = std::min<uint64_t>(cap * 4, cap_max);
         }
-        k_comb_weigh<<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_cap);
+        VSPE_TRY(c->pair_occ.reserve(std::min<uint64_t>(n, c->pair_cap) + 1));
+        k_comb_weigh<<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_cap, c->pair_occ.p, c->counters.p + CNT_PAIR_LIST);
         VSPE_LAUNCH_CHECK(c);
         k_list_weigh<<<grid_cap, 256, 0, st>>>(lv);
         VSPE_LAUNCH_CHECK(c);
@@ -568,8 +592,8 @@ int count_links(Ctx* c, const uint32_t* d_hf, const uint32_t* d_hr, uint64_t tot
         VSPE_TRY(sparse_reserve(c, sp.n_runs + h_exp));
         unsigned long long* keys = sp.k[0].p + sp.n_runs;
         unsigned long long* vals = sp.v[0].p + sp.n_runs;
-        if (sp.enabled) k_comb_emit<false><<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_cap, N, keys, vals);
-        else k_comb_emit<true><<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_cap, N, keys, vals);
+        if (sp.enabled) k_comb_emit<false><<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_occ.p, c->counters.p + CNT_PAIR_LIST, N, keys, vals);
+        else k_comb_emit<true><<<grid_cap, 256, 0, st>>>(lv, c->pair_tab.p, c->pair_occ.p, c->counters.p + CNT_PAIR_LIST, N, keys, vals);
         VSPE_LAUNCH_CHECK(c);
         if (sp.enabled) k_list_emit<false><<<grid_cap, 256, 0, st>>>(lv, N, keys, vals);
         else k_list_emit<true><<<grid_cap, 256, 0, st>>>(lv, N, keys, vals);
