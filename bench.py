@@ -505,7 +505,13 @@ def main():
     assert check["equal"], "merged counts != link keys counted on all ranks: %r" % (check,)
     assert kt[2] == kt[1] + kt[3] + kt[4], "total != used + N + short"
 
-    # ---- end to end: pinned host buffers -> matrices on the host ------------------------
+    # ---- end to end: pinned host buffers -> matrices on the host (pinned too: the D2H read of the result then runs at
+    # PCIe speed; into fresh pageable arrays it cost 45 ms of a 615 ms step) ------------------------
+    h_out = None
+    if not sparse:
+        h_pin = torch.empty((2, n_nodes, n_nodes), dtype=torch.int64).pin_memory()
+        h_out = (h_pin[0].numpy().view(np.uint64), h_pin[1].numpy().view(np.uint64))
+
     def step_e2e():
         ix.reset()
         for _ in range(replay):
@@ -513,7 +519,7 @@ def main():
         reduce_step()
         if world > 1:
             lib_stream.synchronize()
-        return ix.sparse() if sparse else ix.matrices()
+        return ix.sparse() if sparse else ix.matrices(out=h_out)
 
     # the end-to-end ceiling: a plain pinned host->device copy of the same bytes (PCIe), all ranks at once
     h2d_gbs = None

@@ -666,3 +666,20 @@ def test_read_memo_is_exact_and_used():
                 ix.count_host(f2, r2)
                 node3, short3 = ix.matrices()
                 assert np.array_equal(node3.astype(np.int64), onode) and np.array_equal(short3.astype(np.int64), oshort), (name, memo)
+
+
+def test_matrices_into_caller_buffers():
+    """PEIndex.matrices(out=...) fills the caller's (e.g. pinned) arrays with the same counts."""
+    cfg = synth.CONFIGS["C1"]
+    g, f, r = synth.generate(cfg, pairs=2000)
+    ids, seqs = pe_inference.parse_gfa_nodes(g.to_gfa())
+    with pe_inference.PEIndex(seqs, cfg.k) as ix:
+        ix.count_host(f, r)
+        node, short = ix.matrices()
+        n = len(ids)
+        out = (np.full((n, n), 7, dtype=np.uint64), np.full((n, n), 7, dtype=np.uint64))
+        node2, short2 = ix.matrices(out=out)
+        assert node2 is out[0] and short2 is out[1]
+        assert np.array_equal(node, node2) and np.array_equal(short, short2)
+        with pytest.raises(VspeError):
+            ix.matrices(out=(np.zeros((n, n), dtype=np.int32), out[1]))

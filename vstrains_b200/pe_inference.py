@@ -147,8 +147,18 @@ class PEIndex:
         c = np.ascontiguousarray(counts, dtype=np.uint64)
         check(self._L.vspe_sparse_merge(self._ctx, k.ctypes.data if k.size else None, c.ctypes.data if c.size else None, k.size))
 
-    def matrices(self) -> Tuple[np.ndarray, np.ndarray]:
+    def matrices(self, out: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """(node_mat, short_mat), uint64 [N, N].  ``out``: two C-contiguous uint64 [N, N] arrays to copy into -- e.g.
+        views of pinned host memory (``vspe_alloc_pinned`` / a pinned torch tensor), which the device-to-host copy
+        then reaches at PCIe speed instead of through the driver's staging of pageable memory."""
         n = self.n_nodes
+        if out is not None and not self.is_sparse:
+            node, short = out
+            for a in (node, short):
+                if a.dtype != np.uint64 or a.shape != (n, n) or not a.flags["C_CONTIGUOUS"]:
+                    raise VspeError(-1, "matrices(out=...): need two C-contiguous uint64 arrays of shape (N, N)")
+            check(self._L.vspe_matrices_host(self._ctx, node.ctypes.data, short.ctypes.data))
+            return node, short
         if self.is_sparse:
             if n > 20000:
                 raise VspeError(-1, "graph too large for dense matrices: use PEIndex.sparse()")
