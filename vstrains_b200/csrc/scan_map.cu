@@ -905,6 +905,7 @@ int scan_map(Ctx* c, int m, const uint8_t* d_buf, uint64_t n, uint64_t line_base
     // still overflows sends the chunk to the plain path
     uint32_t tcap = 4 * (SM_TILE / (2 * std::max<uint32_t>(c->read_len_hint, 1) + 6) + 2);
     tcap = std::min<uint32_t>((tcap + 7) & ~7u, SM_MAXREC);
+    if (n_tiles * tcap > 0xFFFFFFFFull) { set_error("buffer too large for one scan launch (tile slots exceed 2^32)"); return VSPE_ERR_LIMIT; }
     const uint64_t n_blk = (n_slots + WK_THREADS - 1) / WK_THREADS;
     VSPE_TRY(mb.rec.rows.reserve(n_tiles * tcap * row_words));
     VSPE_TRY(mb.rec.hdr.reserve(n_tiles * tcap));
