@@ -677,77 +677,106 @@ __device__ __forceinline__ void scan_tile(const ScanMapArgs& a, const uint32_t t
         if (threadIdx.x == 0) atomicOr(&a.counters[CNT_ERR], (unsigned long long)ERRF_TILE_FULL);
         return;
     }
-    // ---- pack: one thread per read, the row goes from registers to HBM with 16-byte stores.  16 bases = four words
-    // per step: code = (ascii >> 1) & 3; the only byte with code k is "ACTG"[k] = 0x41 + 2k (+15 when k == 2), which
-    // is the validity test.
+    // ---- pack: the row goes from registers to HBM.  Rows of 16 / 20 words (reads of up to 256 / 320 bases) are packed by
+    // TWO threads per read, each half of the words: a tile owns ~80 such reads, so this keeps 5 warps busy instead of 3 and
+    // halves the phase's critical path (measured on 2x250: k_scan_rows 0.274 -> 0.237 ms per 516 MB).  Rows of 12 words
+    // (up to 160 bases; a tile owns ~130 reads) stay with one thread per read: the halves would be 6 and 4 steps and the
+    // split was measured 5 % slower there.  16 bases = four words per step: code = (ascii >> 1) & 3; the only byte with
+    // code k is "ACTG"[k] = 0x41 + 2k (+15 when k == 2), which is the validity test.
     constexpr int NW = RW == 12 ? 10 : RW;                             // row words that can hold bases (cap / 16)
-    for (uint32_t li = threadIdx.x; li < n_local; li += SM_THREADS) {
-        uint32_t st, en = 0xFFFFFFFFu;
-        if (li < shift) {
-            st = a.head;                                                // buffer position 0, tile-relative
-            if (tile_total > 0) en = s_tp[0];
-        } else {
-            const uint32_t i = h0 + 4 * (li - shift);
-            st = (uint32_t)s_tp[i] + 1;
-            if (i + 1 < tile_total) en = s_tp[i + 1];
-        }
-        uint32_t h = 0;
-        if (en != 0xFFFFFFFFu) {
-            if (en > st && tb[en] == '\n' && tb[en - 1] == '\r') en--;  // "\r\n": the '\r' is not part of the line
-        } else {
-            // the line ends beyond the tile: first '\n' or '\r' in the back margin, if any (four bytes per step:
-            // only a word with a byte < 0x10 is looked at byte by byte)
-            for (uint32_t j = SM_TILE; j < (uint32_t)(SM_TILE + SM_BACK) && en == 0xFFFFFFFFu; j += 4) {
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(tb + j);
-                if (!(((w - 0x10101010u) | w) & 0x80808080u) && pos0 + (int64_t)j + 4 <= nn) continue;
-                for (uint32_t k = 0; k < 4 && pos0 + (int64_t)(j + k) < nn; k++) {
-                    const uint32_t ch = (w >> (8 * k)) & 0xFF;
-                    if (ch == '\n' || ch == '\r') { en = j + k; break; }
-                }
-                if (pos0 + (int64_t)j + 4 > nn) break;
+    constexpr int TPR = RW >= 16 ? 2 : 1;                              // threads per read
+    constexpr int HW = RW / TPR;                                       // row words per thread
+    const uint32_t half = TPR == 2 ? (threadIdx.x & 1) : 0u;
+    for (uint32_t base_li = 0; base_li < n_local; base_li += SM_THREADS / TPR) {   // block-uniform trips: the exchange below is a full-warp shuffle
+        const uint32_t li = base_li + (TPR == 2 ? (threadIdx.x >> 1) : threadIdx.x);
+        const bool act = li < n_local;
+        uint32_t st = 0, en = 0xFFFFFFFFu, h = 0, rlen = 0, diff = 0, sh = 0;
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(s_bytes);
+        uint32_t rw[HW];
+#pragma unroll
+        for (int k = 0; k < HW; k++) rw[k] = 0;
+        if (act) {
+            if (li < shift) {
+                st = a.head;                                            // buffer position 0, tile-relative
+                if (tile_total > 0) en = s_tp[0];
+            } else {
+                const uint32_t i = h0 + 4 * (li - shift);
+                st = (uint32_t)s_tp[i] + 1;
+                if (i + 1 < tile_total) en = s_tp[i + 1];
             }
-            if (en == 0xFFFFFFFFu) h |= SH_LONG;
-        }
-        uint32_t rlen = (h & SH_LONG) ? 0u : en - st;
-        if (rlen > a.cap) { h |= SH_LONG; rlen = 0; }
-        const uint32_t a0 = SM_FRONT + st;                              // offset of the first base in s_bytes
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(s_bytes + (a0 & ~3u));
-        const uint32_t sh = (a0 & 3) * 8;
-        uint32_t carry = p[0], diff = 0;
-        uint32_t rw[RW];
-#pragma unroll
-        for (int v = 0; v < RW; v++) {
-            uint32_t word = 0;
-            if (v < NW && 16u * v < rlen) {
-                uint32_t x[5];
-                x[0] = carry;
-#pragma unroll
-                for (int q = 1; q < 5; q++) x[q] = p[4 * v + q];
-                carry = x[4];
-                const uint32_t rem = rlen - 16u * v;                    // bases left, >= 1
-                if (rem >= 16) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
-                        const uint32_t c2 = (c >> 1) & 0x03030303u;
-                        const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
-                        diff |= expect ^ c;
-                        word |= ((c2 * 0x01041040u) >> 24) << (8 * q);
+            if (en != 0xFFFFFFFFu) {
+                if (en > st && tb[en] == '\n' && tb[en - 1] == '\r') en--;  // "\r\n": the '\r' is not part of the line
+            } else {
+                // the line ends beyond the tile: first '\n' or '\r' in the back margin, if any (four bytes per step:
+                // only a word with a byte < 0x10 is looked at byte by byte)
+                for (uint32_t j = SM_TILE; j < (uint32_t)(SM_TILE + SM_BACK) && en == 0xFFFFFFFFu; j += 4) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(tb + j);
+                    if (!(((w - 0x10101010u) | w) & 0x80808080u) && pos0 + (int64_t)j + 4 <= nn) continue;
+                    for (uint32_t k = 0; k < 4 && pos0 + (int64_t)(j + k) < nn; k++) {
+                        const uint32_t ch = (w >> (8 * k)) & 0xFF;
+                        if (ch == '\n' || ch == '\r') { en = j + k; break; }
                     }
-                } else {                                                // the read ends inside this step: mask the bytes beyond it
+                    if (pos0 + (int64_t)j + 4 > nn) break;
+                }
+                if (en == 0xFFFFFFFFu) h |= SH_LONG;
+            }
+            rlen = (h & SH_LONG) ? 0u : en - st;
+            if (rlen > a.cap) { h |= SH_LONG; rlen = 0; }
+            const uint32_t a0 = SM_FRONT + st;                          // offset of the first base in s_bytes
+            p = reinterpret_cast<const uint32_t*>(s_bytes + (a0 & ~3u));
+            sh = (a0 & 3) * 8;
+            const uint32_t v0 = half * HW;                              // this thread's first row word
+            if (16u * v0 < rlen) {
+                uint32_t carry = p[4 * v0];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
-                        const uint32_t vm = rem >= 4u * q + 4 ? 0xFFFFFFFFu : rem <= 4u * q ? 0u : (0xFFFFFFFFu >> (8 * (4u * q + 4 - rem)));
-                        const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
-                        const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
-                        diff |= (expect ^ c) & vm;
-                        word |= ((c2 * 0x01041040u) >> 24) << (8 * q);
+                for (int k = 0; k < HW; k++) {
+                    const uint32_t v = v0 + k;
+                    uint32_t word = 0;
+                    if (v < (uint32_t)NW && 16u * v < rlen) {
+                        uint32_t x[5];
+                        x[0] = carry;
+#pragma unroll
+                        for (int q = 1; q < 5; q++) x[q] = p[4 * v + q];
+                        carry = x[4];
+                        const uint32_t rem = rlen - 16u * v;            // bases left, >= 1
+                        if (rem >= 16) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
+                                const uint32_t c2 = (c >> 1) & 0x03030303u;
+                                const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
+                                diff |= expect ^ c;
+                                word |= ((c2 * 0x01041040u) >> 24) << (8 * q);
+                            }
+                        } else {                                        // the read ends inside this step: mask the bytes beyond it
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t c = __funnelshift_r(x[q], x[q + 1], sh);
+                                const uint32_t vm = rem >= 4u * q + 4 ? 0xFFFFFFFFu : rem <= 4u * q ? 0u : (0xFFFFFFFFu >> (8 * (4u * q + 4 - rem)));
+                                const uint32_t c2 = ((c & vm) >> 1) & 0x03030303u;
+                                const uint32_t expect = 0x41414141u + 2 * c2 + 15 * ((c2 >> 1) & ~c2 & 0x01010101u);
+                                diff |= (expect ^ c) & vm;
+                                word |= ((c2 * 0x01041040u) >> 24) << (8 * q);
+                            }
+                        }
                     }
+                    rw[k] = word;
                 }
             }
-            rw[v] = word;
         }
+        if (TPR == 2) diff |= __shfl_xor_sync(0xFFFFFFFFu, diff, 1);    // either half saw a byte that is not ACGT
+        if (!act) continue;
+        const uint64_t slot = (uint64_t)tile * a.tcap + li;
+        if (TPR == 2) {
+            uint2* dst = reinterpret_cast<uint2*>(a.rows + slot * RW + half * HW);
+#pragma unroll
+            for (int k = 0; k + 1 < HW; k += 2) __stcs(dst + (k >> 1), make_uint2(rw[k], rw[k + 1]));
+        } else {
+            uint4* dst = reinterpret_cast<uint4*>(a.rows + slot * RW);
+#pragma unroll
+            for (int k = 0; k + 3 < HW; k += 4) __stcs(dst + (k >> 2), make_uint4(rw[k], rw[k + 1], rw[k + 2], rw[k + 3]));
+        }
+        if (half != 0) continue;
         if (diff) {
             // rare: some byte is not ACGT -- 'N' (pair skipped, PE_Inference.py:160) or anything else (exhaustive tier), word by word
             bool hasN = false, badc = false;
@@ -768,10 +797,6 @@ __device__ __forceinline__ void scan_tile(const ScanMapArgs& a, const uint32_t t
             }
             h |= (hasN ? SH_N : 0) | (badc ? SH_BAD : 0);
         }
-        const uint64_t slot = (uint64_t)tile * a.tcap + li;
-        uint4* dst = reinterpret_cast<uint4*>(a.rows + slot * RW);
-#pragma unroll
-        for (int v = 0; v < RW; v += 4) __stcs(dst + (v >> 2), make_uint4(rw[v], rw[v + 1], rw[v + 2], rw[v + 3]));
         __stcs(a.hdr + slot, h | rlen | (st << 16));
     }
 }
