@@ -15,7 +15,8 @@ ix = pe_inference.PEIndex([bytes(s) for s in g.seqs], cfg.k)
 d_f = torch.from_numpy(f).cuda(); d_r = torch.from_numpy(r).cuda()
 for _ in range(3):
     ix.reset(); ix.count_device(d_f.data_ptr(), f.size, d_r.data_ptr(), r.size)
-names = ["TOTAL", "N", "SHORT", "USED", "KEYS", "SPILL_CURSOR", "ERR", "FAST", "GENERIC", "WORK", "BAILED", "DEFER", "WORK2", "-", "-", "LISTS", "OVF", "PAIR_OCC", "EXP", "EXP_CURSOR"]
+names = ["TOTAL", "N", "SHORT", "USED", "KEYS", "SPILL_CURSOR", "ERR", "FAST", "GENERIC", "WORK", "BAILED", "DEFER", "WORK2", "DEFER1", "-", "LISTS", "OVF", "PAIR_OCC", "EXP", "EXP_CURSOR",
+         "B_USED", "B_N", "B_SHORT", "WALK", "WALK1", "MEMO_HIT", "PAIR_LIST"]
 buf = np.zeros(len(names), dtype=np.uint64)
 ix.set_option("dbg_counters", buf.ctypes.data)
 print("%s %s pairs=%d (per-mate counters are those of the second mate)" % (opts, cfgn, pairs))

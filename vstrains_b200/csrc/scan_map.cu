@@ -3,7 +3,7 @@
 //
 // Replaces `readlines()` + `[s[:-1] ...]` (reference utils/VStrains_PE_Inference.py:149-159), the
 // per-character work of `fseq.count("N")` / k-mer slicing (:160, :25) and single_end_read_mapping
-// (:16-48) for every read whose result the walk can PROVE; the rest (about 3 % on the bench
+// (:16-48) for every read whose result the walk can PROVE; the rest (about 2 % on the bench
 // workloads: two or more sequencing errors, repeats, non-ACGT characters, very long reads) is
 // listed for the list-driven tiers of map_fast.cu / map_generic.cu.
 //
@@ -18,18 +18,21 @@
 //      warps' tables into the tile's terminator table and give the tile's terminator count;
 //   3. which of the tile's lines are sequence lines depends on the number of lines before the tile
 //      (mod 4).  Instead of waiting for the earlier tiles (a decoupled look-back was 40 % of the
-//      kernel's warp time, profiles/r02_ncu_c4_block.txt) the tile GUESSES that phase from its own
+//      kernel's warp time, profiles/r02_ncu_c4_block_before.txt) the tile GUESSES that phase from its own
 //      bytes ('@' / '+' at the starts of its first 32 lines), packs its reads into TILE-LOCAL slots
 //      and records {terminator count, guessed phase};
-//   4. one thread per read packs the read the tile owns (its sequence line STARTS here) to 2 bits/base
-//      straight from the tile, 16 bases per step (SIMD-in-word ACGT validity test, 'N' flag), and stores
-//      the row from registers with 16-byte stores (48 / 64 / 80 bytes per read + a header word).
-// k_tile_fix -- one CTA: exact prefix sum of the tiles' terminator counts -> first read of every tile,
+//   4. one thread per read (two for rows of 16 / 20 words) packs the read the tile owns (its sequence line STARTS
+//      here) to 2 bits/base straight from the tile, 16 bases per step (SIMD-in-word ACGT validity test, 'N' flag), and
+//      stores the row from registers (48 / 64 / 80 bytes per read + a header word), streaming.
+// k_tile_sum / k_tile_fix -- exact prefix sum of the tiles' terminator counts -> first read of every tile,
 //      first tile of every k_walk block, terminator total; every guess is CHECKED against the exact
 //      phase and a tile that guessed wrong (text that merely looks like FASTQ structure) is listed;
 // k_scan_redo -- the listed tiles again with their exact phase (normally none): the results never
 //      depend on a guess.
-// k_walk -- one thread per read, 128-thread blocks, 8 blocks per SM (the walk is a chain of dependent
+// k_memo -- one thread per read: finds the read's tile slot, settles 'N' / short reads, sends rows that are not plain
+//      ACGT to the list-driven tiers, asks the READ MEMO (packed row -> list handle of an identical read walked before;
+//      exact: the whole row is compared) and lists what is left for k_walk.
+// k_walk -- list-driven, one thread per read, 128-thread blocks, 10 blocks per SM (the walk is a chain of dependent
 // L2 accesses: it wants many warps and a large L1, which is why it is NOT fused into the scan kernel --
 // the fused variant was built, bit-exact, and 3x slower: 15 warps per SM, 31 % issue slots):
 //   6. seed window 0 (hash + probe + verify + uniq bit; on a miss the reverse complement is seeded from
@@ -39,8 +42,8 @@
 //      stretch was entered.  ONE mismatching base is tolerated when the substitution-hit bit proves that
 //      the windows covering it have no posting.  The saturation predicate (:36-47, integer form) is
 //      applied as each stretch is booked;
-//   7. the kept node list is interned (link.cuh) and its handle stored; an unresolved read is copied (row,
-//      header, byte range) to the compact arrays the list-driven tiers work on.
+//   7. the kept node list is interned (link.cuh) and its handle stored (and entered into the memo if the read had no
+//      error); an unresolved read is copied (row, header, byte range) to the compact arrays the list-driven tiers work on.
 // Why this is exact: see map_fast.cu (a window is counted without a table access only if its text
 // equality and the uniq bit of that text window were both checked; it is skipped only if the
 // index build already looked that k-mer up and found nothing).
