@@ -213,3 +213,25 @@ def test_every_library_option_is_documented_in_the_header():
     documented = set(re.findall(r'"([a-z_0-9]+)"', doc))
     assert names <= documented, sorted(names - documented)
     assert documented <= names, sorted(documented - names)
+
+
+def test_stats_struct_mirror_matches_the_header():
+    """vstrains_b200._lib.Stats (ctypes) must declare the fields of vspe_stats (include/vspe.h) in the same order and
+    with the same types: a drift would silently shift every counter the tests and the bench read."""
+    import ctypes
+    import re
+    from vstrains_b200 import _lib
+    with open(os.path.join(ROOT, "include", "vspe.h")) as f:
+        hdr = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    body = hdr[hdr.index("typedef struct vspe_stats {") + len("typedef struct vspe_stats {"):hdr.index("} vspe_stats;")]
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        for name in names.split(","):
+            fields.append((name.strip(), ctype))
+    cmap = {"uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32, "float": ctypes.c_float}
+    assert [(n, cmap[t]) for n, t in fields] == list(_lib.Stats._fields_)
+    assert ctypes.sizeof(_lib.Stats) % 8 == 0
