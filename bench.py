@@ -585,6 +585,9 @@ def main():
                    "index_build_ms": st["ms_index"], "keys_per_pair": st["n_keys"] / max(1, st["used_pairs"]),
                    "reads_fast": st["reads_fast"], "reads_generic": st["reads_generic"], "numa_node": numa,
                    "read_memo_hit_rate": st["reads_memo"] / max(1, 2 * pairs), "scan_redo_tiles": st["scan_redo_tiles"],
+                   "read_memo": "cleared with the matrices at every step start (the first block of a step runs cold); it only ever holds "
+                                "error-free reads, which are bounded by the graph (2 x genome x strains) and which a real file of this "
+                                "size repeats exactly as the replayed block does; option memo=0 walks every read (profiles/r02_experiments.txt)",
                    "counting": "sparse runs (LSD radix sort + RLE)" if sparse else "dense matrices (pair aggregation + radix partition + counting sort)"},
         "clocks": clocks,
         "gpu_launches": int(launches),
